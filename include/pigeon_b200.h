@@ -1,0 +1,150 @@
+/*
+ * pigeon_b200 — C ABI of the B200-native PIGEON inference hot path.
+ *
+ * The reference (LukasHaas/PIGEON) has no FFI: its hot path sits behind Python nn.Module calls.  This header
+ * is the seam a maintainer binds underneath those modules (ctypes stub in INTEGRATION.md); every entry point
+ * names the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the caller owns every buffer;
+ *   - no hidden device allocations: scratch comes from the caller (`*_workspace_bytes` tells how much);
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns immediately;
+ *   - return value 0 = success, non-zero = failure with a message in pg_last_error() (thread-local);
+ *     no exceptions cross the boundary; there is NO CPU fallback anywhere behind this ABI;
+ *   - fp16 means IEEE binary16 (`__half`), "f32"/"f64" IEEE float/double, i64 = int64_t.
+ */
+#ifndef PIGEON_B200_H_
+#define PIGEON_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_ABI_VERSION 1
+
+/* ---------------------------------------------------------------------------------------------------
+ * Library
+ * ------------------------------------------------------------------------------------------------- */
+int pg_abi_version(void);
+/* Message of the last failing call on this thread ("" if none). */
+const char* pg_last_error(void);
+/* Number of SMs of the current device (grid sizing); < 0 on failure. */
+int pg_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * CLIP ViT vision tower  (HF CLIPVisionTransformer as driven by reference
+ * models/clip_embedder.py:58-65 and models/super_guessr.py:386-398)
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct pg_vit_config {
+  int32_t image_size;   /* 336 */
+  int32_t patch_size;   /* 14  */
+  int32_t hidden;       /* 1024, multiple of 256 */
+  int32_t heads;        /* 16, hidden / heads must be 64 */
+  int32_t intermediate; /* 4096, multiple of 256 */
+  int32_t layers;       /* 24 */
+  float ln_eps;         /* 1e-5 */
+  int32_t patch_k_pad;  /* padded im2col K: multiple of 64, >= 3*patch*patch (640 for 14x14) */
+} pg_vit_config;
+
+/* One encoder block (HF CLIPEncoderLayer).  Matrices are fp16 in nn.Linear layout [out, in]. */
+typedef struct pg_vit_layer {
+  const float* ln1_g; const float* ln1_b;       /* layer_norm1 [hidden] */
+  const void* w_qkv; const float* b_qkv;        /* [3*hidden, hidden] = [Wq; Wk; Wv], bias [3*hidden] */
+  const void* w_o; const float* b_o;            /* out_proj [hidden, hidden] */
+  const float* ln2_g; const float* ln2_b;       /* layer_norm2 [hidden] */
+  const void* w_fc1; const float* b_fc1;        /* mlp.fc1 [intermediate, hidden] */
+  const void* w_fc2; const float* b_fc2;        /* mlp.fc2 [hidden, intermediate] */
+} pg_vit_layer;
+
+typedef struct pg_vit_weights {
+  const void* patch_w;      /* fp16 [hidden, patch_k_pad]: Conv2d weight flattened (c, ky, kx), zero padded */
+  const float* class_emb;   /* [hidden] */
+  const float* pos_emb;     /* [tokens, hidden], tokens = (image/patch)^2 + 1 */
+  const float* pre_ln_g; const float* pre_ln_b; /* pre_layrnorm [hidden] */
+  const pg_vit_layer* layers_host;              /* HOST array of `layers` entries (device pointers inside) */
+} pg_vit_weights;
+
+typedef struct pg_vit pg_vit;
+
+/* Copies the config and the pointer tables (not the weights).  Replaces CLIPVisionModel construction at
+ * reference models/clip_embedder.py:26 / evaluation/evaluate.py:36 for the forward path. */
+int pg_vit_create(const pg_vit_config* cfg, const pg_vit_weights* w, pg_vit** out);
+void pg_vit_destroy(pg_vit* h);
+/* Scratch needed by pg_vit_forward for `n_views` images. */
+size_t pg_vit_workspace_bytes(const pg_vit* h, int32_t n_views);
+/* pixels [n_views, 3, image, image] (fp32 if pixels_f16 == 0 else fp16), NCHW contiguous
+ *   -> emb_out f32 [n_views, hidden] = mean over all tokens of last_hidden_state (pre post_layernorm),
+ *      i.e. reference models/clip_embedder.py:63-65 / models/super_guessr.py:395-398;
+ *   -> hidden_out (optional, may be NULL) f32 [n_views, tokens, hidden] = last_hidden_state. */
+int pg_vit_forward(pg_vit* h, const void* pixels, int32_t pixels_f16, int32_t n_views, void* workspace,
+                   size_t workspace_bytes, float* emb_out, float* hidden_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Geocell head (reference models/super_guessr.py:437-459: view mean, cell_layer, softmax, argmax, top-k)
+ * ------------------------------------------------------------------------------------------------- */
+/* One-off: cell_layer.weight f32 [C, D] -> packed fp16 [C, 3*D] = [Whi | Whi | Wlo] (error-compensated split). */
+int pg_head_pack_weight(const float* w, void* w3_out, int32_t C, int32_t D, void* stream);
+size_t pg_head_workspace_bytes(int32_t B, int32_t D);
+/* emb f32 [B, V, D] (V = 4 for panoramas, 1 otherwise)
+ *   -> pooled f32 [B, D]; logits f32 [B, C]; probs f32 [B, C]; pred_cell i64 [B];
+ *      pred_lnglat f64 [B, 2] = centroids[pred_cell] (lng, lat);
+ *      topk_val f32 [B, k] (descending), topk_idx i64 [B, k]. */
+int pg_head_forward(const float* emb, int32_t B, int32_t V, int32_t D, const void* w3, const float* bias,
+                    const double* centroids, int32_t C, int32_t k, void* workspace, size_t workspace_bytes,
+                    float* pooled, float* logits, float* probs, int64_t* pred_cell, double* pred_lnglat,
+                    float* topk_val, int64_t* topk_idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * ProtoRefiner (reference models/proto_refiner.py:121-255, 332-357; preprocessing/geo_utils.py:40-55)
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct pg_refiner_bank {
+  int32_t num_cells;           /* C */
+  int32_t dim;                 /* D, multiple of 128, <= 1024 */
+  const int64_t* cell_off;     /* [C+1] prototype range per geocell; empty range <=> protos[cell] is None */
+  const float* proto_emb;      /* [P, D] */
+  const float* proto_lnglat;   /* [P, 2] (lng, lat) */
+  const int32_t* proto_count;  /* [P] */
+  const int64_t* member_off;   /* [P+1] */
+  const int64_t* member_idx;   /* [sum count] rows of data_emb/data_lnglat */
+  const float* data_emb;       /* [Ntrain, D] */
+  const float* data_lnglat;    /* [Ntrain, 2] */
+} pg_refiner_bank;
+
+size_t pg_refiner_workspace_bytes(int64_t B, int32_t topk, int32_t D);
+/* emb f32 [B, V, D]; init_lnglat f64 [B, 2]; cand_idx i64 [B, cand_stride]; cand_prob f32 [B, cand_stride];
+ * only the first `topk` candidates of each row are used (topk <= cand_stride).
+ *   -> out_lnglat f32 [B, 2], out_cell i64 [B]   (ProtoRefiner.forward's preds_LLH, preds_geocell)
+ *   -> optional debug outputs (may be NULL): best_logit f32 [B, topk] (negative Euclidean distance to the
+ *      nearest prototype, -100000 for an empty cell), best_lnglat f32 [B, topk, 2], best_proto i32 [B, topk],
+ *      choice i32 [B] (index into the candidate list that was emitted). */
+int pg_refiner_forward(const pg_refiner_bank* bank, const float* emb, int64_t B, int32_t V,
+                       const double* init_lnglat, const int64_t* cand_idx, const float* cand_prob,
+                       int32_t cand_stride, int32_t topk, float temperature, double max_refinement_km,
+                       void* workspace, size_t workspace_bytes, float* out_lnglat, int64_t* out_cell,
+                       float* best_logit, float* best_lnglat, int32_t* best_proto, int32_t* choice, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Building blocks (exported for unit tests and for callers that fuse differently)
+ * ------------------------------------------------------------------------------------------------- */
+enum {
+  PG_EPI_F16_BIAS = 0,       /* out fp16 = A W^T + bias                       (q/k/v projection) */
+  PG_EPI_F16_BIAS_QGELU = 1, /* out fp16 = quick_gelu(A W^T + bias)            (mlp.fc1)          */
+  PG_EPI_F32_BIAS_RESID = 2, /* out f32 += A W^T + bias                        (out_proj, mlp.fc2) */
+  PG_EPI_F32_BIAS = 3        /* out f32 = A W^T + bias (bias may be NULL)                          */
+};
+/* D[M,N] = A[M,K] (fp16, row stride lda) * W[N,K]^T (fp16, row stride ldw), fp32 accumulate on tcgen05. */
+int pg_gemm_f16(const void* a, int32_t lda, const void* w, int32_t ldw, void* out, int32_t ldo, const float* bias,
+                int32_t M, int32_t N, int32_t K, int32_t epilogue, void* stream);
+/* LayerNorm over the last dim: x f32 [rows, hidden] -> y fp16 [rows, hidden]. */
+int pg_layernorm_f16(const float* x, void* y, const float* gamma, const float* beta, int64_t rows, int32_t hidden,
+                     float eps, void* stream);
+/* softmax(q k^T / 8) v per (view, head); qkv fp16 [n_views*seq, 3*heads*64] -> out fp16 [n_views*seq, heads*64]. */
+int pg_attention_f16(const void* qkv, void* out, int32_t n_views, int32_t seq, int32_t heads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIGEON_B200_H_ */

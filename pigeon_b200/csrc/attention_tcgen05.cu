@@ -1,0 +1,308 @@
+// Multi-head self-attention core for the CLIP vision tower on sm_100a (tcgen05 + TMEM + TMA).
+//
+//   out[v, s, h*64 + :] = softmax_s'( q[v,s,h,:] . k[v,s',h,:] / sqrt(64) ) @ v[v,s',h,:]
+//
+// Restates the attention core of HF CLIPAttention.forward (bmm -> fp32 softmax -> bmm; no mask, no
+// dropout in eval) that the reference reaches through models/clip_embedder.py:63 and
+// models/super_guessr.py:395.  head_dim is fixed to 64 (ViT-L/14: 16 heads x 64).
+//
+// Input  qkv : fp16 [n_views * S, 3 * hidden]   row = (view, token); cols = [q | k | v], head-major inside
+// Output out : fp16 [n_views * S, hidden]
+//
+// One CTA per (q-tile of 128 rows, head, view); 192 threads; two CTAs co-reside per SM so one CTA's
+// softmax overlaps the other's MMAs.
+//   warp 0     TMA producer: Q tile once, then K/V tiles (128 x 64 halves, 128B swizzle) through a 4-slot ring
+//   warp 1     TMEM allocator + MMA issuer (tcgen05.mma cta_group::1, M = 128)
+//   warps 2-5  softmax, one TMEM lane (= one query row) per thread
+// Exact two-pass softmax: pass 1 forms S = Q K^T block by block to get the row max; pass 2 re-forms S,
+// writes P = exp2(S*c - max*c) as fp16 over the S columns in TMEM and issues O += P V with P as the
+// TMEM A-operand and V as an MN-major smem B-operand.  No online rescale, O stays in TMEM until the end.
+#include "attention.h"
+#include "ptx.cuh"
+#include "tma_host.h"
+
+namespace pg {
+
+namespace {
+
+constexpr int kHeadDim = 64;
+constexpr int kBlockQ = 128;
+constexpr int kBlockKV = 128;
+constexpr int kSlots = 4;
+constexpr int kTileBytes = kBlockKV * kHeadDim * 2;  // 16 KB
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 256;  // S/P: [0,128)  O: [128,192)
+constexpr int kOCol = 128;
+constexpr int kSmemBytes = (1 + kSlots) * kTileBytes + 1024 + 256;
+
+struct AttnArgs {
+  int seq;      // tokens per view (577)
+  int hidden;   // heads * 64
+  __half* out;  // [n_views*seq, hidden]
+  float scale_log2;  // (1/sqrt(64)) * log2(e)
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void tmem_ld16_(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8_(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;
+  uint8_t* smem_kv = smem + kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + kSlots) * kTileBytes);
+  uint64_t* full_bar = bars;             // [kSlots]
+  uint64_t* empty_bar = bars + kSlots;   // [kSlots]
+  uint64_t* q_full = bars + 2 * kSlots;
+  uint64_t* s_full = q_full + 1;         // MMA -> softmax : an S block is complete in TMEM
+  uint64_t* sm_done = q_full + 2;        // softmax -> MMA : S consumed (pass 1) / P written (pass 2)
+  uint64_t* o_full = q_full + 3;         // MMA -> softmax : O complete
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(q_full + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, head = blockIdx.y, view = blockIdx.z;
+  const int S = args.seq;
+  const int nb = (S + kBlockKV - 1) / kBlockKV;                 // KV blocks (5 for S = 577)
+  const int last_valid = S - (nb - 1) * kBlockKV;               // valid kv columns in the last block (65)
+  const int last_n = (last_valid + 15) & ~15;                   // MMA N / K extent of the last block (80)
+  const int row0 = view * S;                                    // first row of this view in qkv / out
+  const int q_col = head * kHeadDim, k_col = args.hidden + q_col, v_col = 2 * args.hidden + q_col;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(q_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(sm_done, 4);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kTileBytes);
+      tma_load_2d(smem_q, &tmap_qkv, q_full, q_col, row0 + q_tile * kBlockQ);
+      int slot = 0;
+      uint32_t phase = 0;
+      auto load = [&](int col, int blk) {
+        mbar_wait(&empty_bar[slot], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[slot], kTileBytes);
+        tma_load_2d(smem_kv + slot * kTileBytes, &tmap_qkv, &full_bar[slot], col, row0 + blk * kBlockKV);
+        if (++slot == kSlots) { slot = 0; phase ^= 1; }
+      };
+      for (int j = 0; j < nb; ++j) load(k_col, j);  // pass 1: K only
+      for (int j = 0; j < nb; ++j) {                // pass 2: K_j then V_j
+        load(k_col, j);
+        load(v_col, j);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      uint32_t sm_phase = 0;
+      const uint32_t s_tmem = tmem_base;          // S (fp32) and P (fp16, aliased from column 0)
+      const uint32_t o_tmem = tmem_base + kOCol;
+      const uint32_t q_addr = smem_u32(smem_q);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+
+      auto issue_s = [&](int j) {
+        const int n = (j == nb - 1) ? last_n : kBlockKV;
+        const uint32_t idesc = make_idesc_f16(kBlockQ, n, 0, 0);
+        mbar_wait(&full_bar[slot], phase);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(smem_kv + slot * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k) {
+          const uint64_t a_desc = make_smem_desc(q_addr + k * 32, 16, 1024, kLayoutSw128);
+          const uint64_t b_desc = make_smem_desc(k_addr + k * 32, 16, 1024, kLayoutSw128);
+          umma_ss(s_tmem, a_desc, b_desc, idesc, k != 0);
+        }
+        tc_commit(&empty_bar[slot]);
+        tc_commit(s_full);
+        if (++slot == kSlots) { slot = 0; phase ^= 1; }
+      };
+      auto issue_pv = [&](int j) {
+        const int kext = (j == nb - 1) ? last_n : kBlockKV;  // contraction extent = kv rows of this block
+        const uint32_t idesc = make_idesc_f16(kBlockQ, kHeadDim, 0, 1);  // B (= V) is MN-major
+        mbar_wait(&full_bar[slot], phase);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(smem_kv + slot * kTileBytes);
+        for (int k = 0; k < kext / 16; ++k) {
+          // V tile: row = kv index (128 B each, 64 halves of head_dim), 8-row groups 1024 B apart.
+          const uint64_t b_desc = make_smem_desc(v_addr + k * 16 * 128, 1024, 1024, kLayoutSw128);
+          umma_ts(o_tmem, s_tmem + k * 8, b_desc, idesc, (j | k) != 0);
+        }
+        tc_commit(&empty_bar[slot]);
+        if (++slot == kSlots) { slot = 0; phase ^= 1; }
+      };
+
+      const int total = 2 * nb;
+      for (int b = 0; b < total; ++b) {
+        if (b > 0) {
+          mbar_wait(sm_done, sm_phase);
+          sm_phase ^= 1;
+          tc_fence_after();
+          if (b - 1 >= nb) issue_pv(b - 1 - nb);
+        }
+        issue_s(b < nb ? b : b - nb);
+      }
+      mbar_wait(sm_done, sm_phase);
+      tc_fence_after();
+      issue_pv(nb - 1);
+      tc_commit(o_full);
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax warps
+    const int q = warp & 3;
+    const uint32_t lane_base = uint32_t(q * 32) << 16;
+    const uint32_t s_tmem = tmem_base + lane_base;
+    const uint32_t o_tmem = tmem_base + lane_base + kOCol;
+    const int q_row = q_tile * kBlockQ + q * 32 + lane;  // token index inside the view
+    uint32_t s_phase = 0;
+    const float c = args.scale_log2;
+
+    // pass 1: row max
+    float m = -INFINITY;
+    for (int j = 0; j < nb; ++j) {
+      const int ncols = (j == nb - 1) ? last_n : kBlockKV;
+      const int nvalid = (j == nb - 1) ? last_valid : kBlockKV;
+      mbar_wait(s_full, s_phase);
+      s_phase ^= 1;
+      tc_fence_after();
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16_(s_tmem + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < nvalid) m = fmaxf(m, __uint_as_float(r[i]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm_done);
+    }
+
+    // pass 2: P = exp2(S*c - m*c), row sum, P -> TMEM (fp16 pairs)
+    const float mc = m * c;
+    float l = 0.f;
+    for (int j = 0; j < nb; ++j) {
+      const int ncols = (j == nb - 1) ? last_n : kBlockKV;
+      const int nvalid = (j == nb - 1) ? last_valid : kBlockKV;
+      mbar_wait(s_full, s_phase);
+      s_phase ^= 1;
+      tc_fence_after();
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16_(s_tmem + c0, r);
+        tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          float p0 = (c0 + i < nvalid) ? ex2(fmaf(__uint_as_float(r[i]), c, -mc)) : 0.f;
+          float p1 = (c0 + i + 1 < nvalid) ? ex2(fmaf(__uint_as_float(r[i + 1]), c, -mc)) : 0.f;
+          l += p0 + p1;
+          pk[i >> 1] = pack_half2(p0, p1);
+        }
+        tmem_st8_(s_tmem + (c0 >> 1), pk);  // P overwrites S columns already consumed by this thread
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm_done);
+    }
+
+    // epilogue: O / l -> fp16 -> global
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    __half* orow = args.out + (size_t)(row0 + q_row) * args.hidden + q_col;
+#pragma unroll
+    for (int c0 = 0; c0 < kHeadDim; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(o_tmem + c0, r);
+      tmem_ld_wait();
+      if (q_row < S) {
+        uint4* o4 = reinterpret_cast<uint4*>(orow + c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 v;
+          v.x = pack_half2(__uint_as_float(r[8 * i + 0]) * inv_l, __uint_as_float(r[8 * i + 1]) * inv_l);
+          v.y = pack_half2(__uint_as_float(r[8 * i + 2]) * inv_l, __uint_as_float(r[8 * i + 3]) * inv_l);
+          v.z = pack_half2(__uint_as_float(r[8 * i + 4]) * inv_l, __uint_as_float(r[8 * i + 5]) * inv_l);
+          v.w = pack_half2(__uint_as_float(r[8 * i + 6]) * inv_l, __uint_as_float(r[8 * i + 7]) * inv_l);
+          o4[i] = v;
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+int attention_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream) {
+  if (n_views <= 0) return 0;
+  const int hidden = heads * kHeadDim;
+  CUtensorMap tm;
+  if (make_tmap_f16_2d(&tm, qkv, (uint64_t)n_views * seq, 3 * hidden, 3 * hidden, kBlockKV, kHeadDim)) return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) { set_last_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
+    attr_set = true;
+  }
+  AttnArgs a;
+  a.seq = seq;
+  a.hidden = hidden;
+  a.out = reinterpret_cast<__half*>(out);
+  a.scale_log2 = 0.125f * 1.4426950408889634f;
+  dim3 grid((seq + kBlockQ - 1) / kBlockQ, heads, n_views);
+  attention_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tm, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_last_error("attention launch: %s", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
+}  // namespace pg

@@ -1,0 +1,278 @@
+// C ABI (include/pigeon_b200.h) over the kernels in this directory.  Host-side orchestration only:
+// argument checks, workspace carving and the launch sequence of the vision tower.
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/pigeon_b200.h"
+#include "attention.h"
+#include "gemm.h"
+#include "head.h"
+#include "refiner.h"
+#include "tma_host.h"
+#include "vit_misc.h"
+
+using namespace pg;
+
+namespace {
+
+int g_sm_count = 0;
+int sm_count() {
+  if (g_sm_count <= 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      set_last_error("no usable CUDA device (cudaDeviceGetAttribute failed)");
+      return -1;
+    }
+    g_sm_count = n;
+  }
+  return g_sm_count;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(reinterpret_cast<uint8_t*>(p)) {}
+  void* take(size_t bytes) {
+    void* p = base ? base + off : nullptr;
+    off += align_up(bytes, 1024);
+    return p;
+  }
+};
+
+}  // namespace
+
+struct pg_vit {
+  pg_vit_config cfg;
+  pg_vit_weights w;
+  std::vector<pg_vit_layer> layers;
+  int tokens;
+  int grid_patches;
+};
+
+extern "C" {
+
+int pg_abi_version(void) { return PG_ABI_VERSION; }
+const char* pg_last_error(void) { return last_error(); }
+int pg_device_sm_count(void) { return sm_count(); }
+
+// ---------------------------------------------------------------------------------------------- ViT
+int pg_vit_create(const pg_vit_config* cfg, const pg_vit_weights* w, pg_vit** out) {
+  if (!cfg || !w || !out) { set_last_error("pg_vit_create: null argument"); return 1; }
+  if (cfg->hidden % 256 || cfg->intermediate % 256) { set_last_error("pg_vit_create: hidden/intermediate must be multiples of 256"); return 1; }
+  if (cfg->heads <= 0 || cfg->hidden != cfg->heads * 64) { set_last_error("pg_vit_create: head_dim must be 64"); return 1; }
+  if (cfg->patch_size <= 0 || cfg->image_size % cfg->patch_size) { set_last_error("pg_vit_create: image_size %% patch_size != 0"); return 1; }
+  if (cfg->patch_k_pad % 64 || cfg->patch_k_pad < 3 * cfg->patch_size * cfg->patch_size) { set_last_error("pg_vit_create: bad patch_k_pad"); return 1; }
+  if (cfg->layers <= 0 || !w->layers_host) { set_last_error("pg_vit_create: no layers"); return 1; }
+  pg_vit* h = new (std::nothrow) pg_vit();
+  if (!h) { set_last_error("pg_vit_create: out of host memory"); return 1; }
+  h->cfg = *cfg;
+  h->w = *w;
+  h->layers.assign(w->layers_host, w->layers_host + cfg->layers);
+  h->w.layers_host = h->layers.data();
+  h->grid_patches = cfg->image_size / cfg->patch_size;
+  h->tokens = h->grid_patches * h->grid_patches + 1;
+  *out = h;
+  return 0;
+}
+
+void pg_vit_destroy(pg_vit* h) { delete h; }
+
+static size_t vit_carve(const pg_vit* h, int n_views, void* ws, float** x, void** xn, void** u) {
+  const size_t rows = (size_t)n_views * h->tokens;
+  const int wide = h->cfg.intermediate > 3 * h->cfg.hidden ? h->cfg.intermediate : 3 * h->cfg.hidden;
+  size_t u_elems = rows * (size_t)wide;
+  const size_t im2col_elems = (size_t)n_views * h->grid_patches * h->grid_patches * h->cfg.patch_k_pad;
+  if (im2col_elems > u_elems) u_elems = im2col_elems;
+  Carver c(ws);
+  *x = reinterpret_cast<float*>(c.take(rows * h->cfg.hidden * sizeof(float)));  // residual stream, fp32
+  *xn = c.take(rows * h->cfg.hidden * 2);  // LayerNorm output / attention output (fp16), time-shared
+  *u = c.take(u_elems * 2);                // im2col | qkv | fc1 activations (fp16), time-shared
+  return c.off;
+}
+
+size_t pg_vit_workspace_bytes(const pg_vit* h, int32_t n_views) {
+  if (!h || n_views <= 0) return 0;
+  float* x; void* xn; void* u;
+  return vit_carve(h, n_views, nullptr, &x, &xn, &u);
+}
+
+int pg_vit_forward(pg_vit* h, const void* pixels, int32_t pixels_f16, int32_t n_views, void* workspace,
+                   size_t workspace_bytes, float* emb_out, float* hidden_out, void* stream_) {
+  if (!h || !pixels || !workspace || !emb_out) { set_last_error("pg_vit_forward: null argument"); return 1; }
+  if (n_views <= 0) return 0;
+  const int sms = sm_count();
+  if (sms < 0) return 1;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  float* x; void* xn; void* u;
+  const size_t need = vit_carve(h, n_views, workspace, &x, &xn, &u);
+  if (workspace_bytes < need) { set_last_error("pg_vit_forward: workspace %zu < required %zu", workspace_bytes, need); return 1; }
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) { set_last_error("pg_vit_forward: workspace must be 1024-byte aligned"); return 1; }
+  const pg_vit_config& c = h->cfg;
+  const long rows = (long)n_views * h->tokens;
+  const int np = h->grid_patches * h->grid_patches;
+
+  // patch embedding: im2col -> GEMM whose epilogue scatters row (view, patch) to token (view, 1 + patch)
+  if (im2col(pixels, pixels_f16, u, n_views, c.image_size, c.patch_size, c.patch_k_pad, sms, stream)) return 1;
+  {
+    GemmProblem p{};
+    p.M = n_views * np; p.N = c.hidden; p.K = c.patch_k_pad;
+    p.a = u; p.lda = c.patch_k_pad; p.w = h->w.patch_w; p.ldw = c.patch_k_pad;
+    p.out = x; p.ldo = c.hidden; p.bias = nullptr; p.epi = EPI_F32_ROWMAP;
+    p.rowmap_div = np; p.rowmap_mul = h->tokens; p.rowmap_add = 1;
+    if (gemm_f16(p, sms, stream)) return 1;
+  }
+  if (embed_preln(x, h->w.class_emb, h->w.pos_emb, h->w.pre_ln_g, h->w.pre_ln_b, rows, h->tokens, c.hidden, c.ln_eps,
+                  sms, stream))
+    return 1;
+
+  for (int l = 0; l < c.layers; ++l) {
+    const pg_vit_layer& L = h->layers[l];
+    if (layernorm_f16(x, xn, L.ln1_g, L.ln1_b, rows, c.hidden, c.ln_eps, sms, stream)) return 1;
+    GemmProblem p{};
+    p.M = (int)rows; p.N = 3 * c.hidden; p.K = c.hidden;
+    p.a = xn; p.lda = c.hidden; p.w = L.w_qkv; p.ldw = c.hidden;
+    p.out = u; p.ldo = 3 * c.hidden; p.bias = L.b_qkv; p.epi = EPI_F16_BIAS;
+    if (gemm_f16(p, sms, stream)) return 1;
+    if (attention_f16(u, xn, n_views, h->tokens, c.heads, stream)) return 1;
+    p = GemmProblem{};
+    p.M = (int)rows; p.N = c.hidden; p.K = c.hidden;
+    p.a = xn; p.lda = c.hidden; p.w = L.w_o; p.ldw = c.hidden;
+    p.out = x; p.ldo = c.hidden; p.bias = L.b_o; p.epi = EPI_F32_BIAS_RESID;
+    if (gemm_f16(p, sms, stream)) return 1;
+    if (layernorm_f16(x, xn, L.ln2_g, L.ln2_b, rows, c.hidden, c.ln_eps, sms, stream)) return 1;
+    p = GemmProblem{};
+    p.M = (int)rows; p.N = c.intermediate; p.K = c.hidden;
+    p.a = xn; p.lda = c.hidden; p.w = L.w_fc1; p.ldw = c.hidden;
+    p.out = u; p.ldo = c.intermediate; p.bias = L.b_fc1; p.epi = EPI_F16_BIAS_QGELU;
+    if (gemm_f16(p, sms, stream)) return 1;
+    p = GemmProblem{};
+    p.M = (int)rows; p.N = c.hidden; p.K = c.intermediate;
+    p.a = u; p.lda = c.intermediate; p.w = L.w_fc2; p.ldw = c.intermediate;
+    p.out = x; p.ldo = c.hidden; p.bias = L.b_fc2; p.epi = EPI_F32_BIAS_RESID;
+    if (gemm_f16(p, sms, stream)) return 1;
+  }
+  if (token_mean(x, emb_out, n_views, h->tokens, c.hidden, stream)) return 1;
+  if (hidden_out) {
+    cudaError_t e = cudaMemcpyAsync(hidden_out, x, (size_t)rows * c.hidden * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) { set_last_error("pg_vit_forward: hidden copy: %s", cudaGetErrorString(e)); return 1; }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- head
+int pg_head_pack_weight(const float* w, void* w3_out, int32_t C, int32_t D, void* stream) {
+  if (!w || !w3_out || C <= 0 || D <= 0) { set_last_error("pg_head_pack_weight: bad argument"); return 1; }
+  return weight_split(w, w3_out, C, D, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t pg_head_workspace_bytes(int32_t B, int32_t D) {
+  if (B <= 0 || D <= 0) return 0;
+  return align_up((size_t)B * 3 * D * 2, 1024);
+}
+
+int pg_head_forward(const float* emb, int32_t B, int32_t V, int32_t D, const void* w3, const float* bias,
+                    const double* centroids, int32_t C, int32_t k, void* workspace, size_t workspace_bytes,
+                    float* pooled, float* logits, float* probs, int64_t* pred_cell, double* pred_lnglat,
+                    float* topk_val, int64_t* topk_idx, void* stream_) {
+  if (!emb || !w3 || !centroids || !workspace || !pooled || !logits || !probs || !pred_cell || !pred_lnglat ||
+      !topk_val || !topk_idx) { set_last_error("pg_head_forward: null argument"); return 1; }
+  if (B <= 0) return 0;
+  if (V <= 0 || D % 8 || C <= 0 || k <= 0 || k > C) { set_last_error("pg_head_forward: bad shape B=%d V=%d D=%d C=%d k=%d", B, V, D, C, k); return 1; }
+  if (workspace_bytes < pg_head_workspace_bytes(B, D)) { set_last_error("pg_head_forward: workspace too small"); return 1; }
+  const int sms = sm_count();
+  if (sms < 0) return 1;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (view_mean_split(emb, pooled, workspace, B, V, D, stream)) return 1;
+  GemmProblem p{};
+  p.M = B; p.N = C; p.K = 3 * D;
+  p.a = workspace; p.lda = 3 * D; p.w = w3; p.ldw = 3 * D;
+  p.out = logits; p.ldo = C; p.bias = bias; p.epi = EPI_F32_BIAS;
+  if (gemm_f16(p, sms, stream)) return 1;
+  return softmax_topk(logits, probs, reinterpret_cast<long long*>(pred_cell), pred_lnglat, topk_val,
+                      reinterpret_cast<long long*>(topk_idx), centroids, B, C, k, stream);
+}
+
+// ---------------------------------------------------------------------------------------------- refiner
+size_t pg_refiner_workspace_bytes(int64_t B, int32_t topk, int32_t D) {
+  if (B <= 0 || topk <= 0 || D <= 0) return 0;
+  Carver c(nullptr);
+  c.take((size_t)B * D * 4);         // pooled queries
+  c.take((size_t)B * topk * 4);      // best_logit
+  c.take((size_t)B * topk * 2 * 4);  // best_lnglat
+  c.take((size_t)B * topk * 4);      // best_proto
+  return c.off;
+}
+
+int pg_refiner_forward(const pg_refiner_bank* bank, const float* emb, int64_t B, int32_t V, const double* init_lnglat,
+                       const int64_t* cand_idx, const float* cand_prob, int32_t cand_stride, int32_t topk,
+                       float temperature, double max_refinement_km, void* workspace, size_t workspace_bytes,
+                       float* out_lnglat, int64_t* out_cell, float* best_logit, float* best_lnglat,
+                       int32_t* best_proto, int32_t* choice, void* stream_) {
+  if (!bank || !emb || !init_lnglat || !cand_idx || !cand_prob || !workspace || !out_lnglat || !out_cell) {
+    set_last_error("pg_refiner_forward: null argument"); return 1;
+  }
+  if (B <= 0) return 0;
+  // mirrors the reference assert at models/proto_refiner.py:135-137
+  if (topk <= 0 || topk > cand_stride) { set_last_error("pg_refiner_forward: \"topk\" (%d) must be <= number of candidates (%d)", topk, cand_stride); return 1; }
+  if (V <= 0 || bank->dim % 128 || bank->dim > 1024) { set_last_error("pg_refiner_forward: bad V=%d / dim=%d", V, bank->dim); return 1; }
+  if (workspace_bytes < pg_refiner_workspace_bytes(B, topk, bank->dim)) { set_last_error("pg_refiner_forward: workspace too small"); return 1; }
+  const int sms = sm_count();
+  if (sms < 0) return 1;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  Carver c(workspace);
+  float* q = reinterpret_cast<float*>(c.take((size_t)B * bank->dim * 4));
+  float* bl = reinterpret_cast<float*>(c.take((size_t)B * topk * 4));
+  float* bll = reinterpret_cast<float*>(c.take((size_t)B * topk * 2 * 4));
+  int* bp = reinterpret_cast<int*>(c.take((size_t)B * topk * 4));
+  if (best_logit) bl = best_logit;
+  if (best_lnglat) bll = best_lnglat;
+  if (best_proto) bp = best_proto;
+  RefinerBank rb;
+  rb.num_cells = bank->num_cells; rb.dim = bank->dim;
+  rb.cell_off = reinterpret_cast<const long long*>(bank->cell_off);
+  rb.proto_emb = bank->proto_emb; rb.proto_lnglat = bank->proto_lnglat; rb.proto_count = bank->proto_count;
+  rb.member_off = reinterpret_cast<const long long*>(bank->member_off);
+  rb.member_idx = reinterpret_cast<const long long*>(bank->member_idx);
+  rb.data_emb = bank->data_emb; rb.data_lnglat = bank->data_lnglat;
+  if (refiner_pool(emb, q, B, V, bank->dim, stream)) return 1;
+  if (refiner_scan(rb, q, reinterpret_cast<const long long*>(cand_idx), cand_stride, B, topk, bl, bll, bp, sms, stream)) return 1;
+  return refiner_finalize(bl, bll, reinterpret_cast<const long long*>(cand_idx), cand_prob, cand_stride, init_lnglat, B,
+                          topk, temperature, max_refinement_km, out_lnglat, reinterpret_cast<long long*>(out_cell),
+                          choice, stream);
+}
+
+// ---------------------------------------------------------------------------------------------- blocks
+int pg_gemm_f16(const void* a, int32_t lda, const void* w, int32_t ldw, void* out, int32_t ldo, const float* bias,
+                int32_t M, int32_t N, int32_t K, int32_t epilogue, void* stream) {
+  if (!a || !w || !out) { set_last_error("pg_gemm_f16: null argument"); return 1; }
+  if (epilogue < 0 || epilogue > PG_EPI_F32_BIAS) { set_last_error("pg_gemm_f16: bad epilogue %d", epilogue); return 1; }
+  const int sms = sm_count();
+  if (sms < 0) return 1;
+  GemmProblem p{};
+  p.M = M; p.N = N; p.K = K; p.a = a; p.lda = lda; p.w = w; p.ldw = ldw; p.out = out; p.ldo = ldo; p.bias = bias;
+  p.epi = epilogue;
+  return gemm_f16(p, sms, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pg_layernorm_f16(const float* x, void* y, const float* gamma, const float* beta, int64_t rows, int32_t hidden,
+                     float eps, void* stream) {
+  if (!x || !y || !gamma || !beta) { set_last_error("pg_layernorm_f16: null argument"); return 1; }
+  const int sms = sm_count();
+  if (sms < 0) return 1;
+  return layernorm_f16(x, y, gamma, beta, rows, hidden, eps, sms, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pg_attention_f16(const void* qkv, void* out, int32_t n_views, int32_t seq, int32_t heads, void* stream) {
+  if (!qkv || !out) { set_last_error("pg_attention_f16: null argument"); return 1; }
+  if (n_views > 65535) { set_last_error("pg_attention_f16: n_views %d > 65535 (grid.z)", n_views); return 1; }
+  return attention_f16(qkv, out, n_views, seq, heads, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

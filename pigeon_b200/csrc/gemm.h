@@ -1,0 +1,31 @@
+// Internal (C++) interface of the tcgen05 GEMM; the C ABI in capi.cu wraps it.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pg {
+
+enum GemmEpilogue {
+  EPI_F16_BIAS = 0,        // out fp16 = acc + bias
+  EPI_F16_BIAS_QGELU = 1,  // out fp16 = quick_gelu(acc + bias)
+  EPI_F32_BIAS_RESID = 2,  // out fp32 += acc + bias     (in-place residual stream update)
+  EPI_F32_BIAS = 3,        // out fp32 = acc + bias      (bias may be null)
+  EPI_F32_ROWMAP = 4,      // out fp32[rowmap(row)] = acc + bias ; rowmap(r) = mul*(r/div) + r%div + add
+};
+
+struct GemmProblem {
+  int M, N, K;
+  const void* a;  // fp16 [M, lda]
+  int lda;
+  const void* w;  // fp16 [N, ldw]
+  int ldw;
+  void* out;
+  int ldo;
+  const float* bias;
+  int epi;
+  int rowmap_div, rowmap_mul, rowmap_add;
+};
+
+// Enqueues the GEMM on `stream`. Returns 0 on success; on failure the message is in pg::last_error().
+int gemm_f16(const GemmProblem& p, int num_sms, cudaStream_t stream);
+
+}  // namespace pg

@@ -1,0 +1,169 @@
+"""Host-side owner of the CLIP vision tower on the GPU: packs HF-named weights into the kernel layouts,
+holds the C handle and the scratch buffer, and runs `pg_vit_forward` in view chunks.
+
+Accepts the state-dict key names of HF `CLIPVisionModel` (the module the reference builds at
+models/clip_embedder.py:26 and evaluation/evaluate.py:36), so checkpoints written by the reference load by name.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import PigeonB200Error, check, current_stream_ptr, load, ptr
+
+
+@dataclass
+class VitDims:
+    image_size: int = 336
+    patch_size: int = 14
+    hidden: int = 1024
+    heads: int = 16
+    intermediate: int = 4096
+    layers: int = 24
+    ln_eps: float = 1e-5
+
+    @property
+    def tokens(self) -> int:
+        return (self.image_size // self.patch_size) ** 2 + 1
+
+    @property
+    def patch_k(self) -> int:
+        return 3 * self.patch_size * self.patch_size
+
+    @property
+    def patch_k_pad(self) -> int:
+        return (self.patch_k + 63) // 64 * 64
+
+    @classmethod
+    def from_hf_config(cls, cfg) -> "VitDims":
+        return cls(image_size=cfg.image_size, patch_size=cfg.patch_size, hidden=cfg.hidden_size,
+                   heads=cfg.num_attention_heads, intermediate=cfg.intermediate_size, layers=cfg.num_hidden_layers,
+                   ln_eps=float(cfg.layer_norm_eps))
+
+
+def _strip_prefix(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Normalise HF key names to start at 'embeddings.' / 'encoder.' / 'pre_layrnorm.'."""
+    out = {}
+    for k, v in sd.items():
+        for pre in ("base_model.", "clip_model.", "vision_model."):
+            while k.startswith(pre):
+                k = k[len(pre):]
+        out[k] = v
+    return out
+
+
+class VitEngine:
+    """B200 execution engine of HF CLIPVisionTransformer.forward(...).last_hidden_state (+ token mean)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], dims: VitDims, device: torch.device | str = "cuda",
+                 max_views_per_pass: int = 256):
+        self.dims = dims
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise PigeonB200Error("VitEngine runs on a CUDA device only (no CPU path)")
+        self.max_views_per_pass = int(max_views_per_pass)
+        self._lib = load()
+        self._handle = C.c_void_p()
+        self._ws: Optional[torch.Tensor] = None
+        self._keep = []  # tensors referenced by raw pointer from the C side
+        self.load_state_dict(state_dict)
+
+    # ------------------------------------------------------------------------------------------ weights
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        d, dev = self.dims, self.device
+        sd = _strip_prefix(state_dict)
+
+        def f32(name):
+            t = sd[name].detach().to(device=dev, dtype=torch.float32).contiguous()
+            self._keep.append(t)
+            return t
+
+        def f16(t):
+            t = t.detach().to(device=dev, dtype=torch.float32).to(torch.float16).contiguous()
+            self._keep.append(t)
+            return t
+
+        self._keep = []
+        pw = sd["embeddings.patch_embedding.weight"].detach().to(dev, torch.float32).reshape(d.hidden, d.patch_k)
+        pw_pad = torch.zeros((d.hidden, d.patch_k_pad), dtype=torch.float32, device=dev)
+        pw_pad[:, : d.patch_k] = pw
+        patch_w = f16(pw_pad)
+        cls = f32("embeddings.class_embedding")
+        pos = f32("embeddings.position_embedding.weight")
+        if pos.shape != (d.tokens, d.hidden):
+            raise PigeonB200Error(f"position_embedding {tuple(pos.shape)} != ({d.tokens}, {d.hidden})")
+        pre_g, pre_b = f32("pre_layrnorm.weight"), f32("pre_layrnorm.bias")
+
+        layers = (_lib.VitLayer * d.layers)()
+        for i in range(d.layers):
+            p = f"encoder.layers.{i}."
+            wq, wk, wv = (sd[p + f"self_attn.{n}_proj.weight"] for n in "qkv")
+            bq, bk, bv = (sd[p + f"self_attn.{n}_proj.bias"] for n in "qkv")
+            w_qkv = f16(torch.cat([wq, wk, wv], dim=0))
+            b_qkv = torch.cat([bq, bk, bv], dim=0).detach().to(dev, torch.float32).contiguous()
+            self._keep.append(b_qkv)
+            L = layers[i]
+            L.ln1_g, L.ln1_b = ptr(f32(p + "layer_norm1.weight")), ptr(f32(p + "layer_norm1.bias"))
+            L.w_qkv, L.b_qkv = ptr(w_qkv), ptr(b_qkv)
+            L.w_o, L.b_o = ptr(f16(sd[p + "self_attn.out_proj.weight"])), ptr(f32(p + "self_attn.out_proj.bias"))
+            L.ln2_g, L.ln2_b = ptr(f32(p + "layer_norm2.weight")), ptr(f32(p + "layer_norm2.bias"))
+            L.w_fc1, L.b_fc1 = ptr(f16(sd[p + "mlp.fc1.weight"])), ptr(f32(p + "mlp.fc1.bias"))
+            L.w_fc2, L.b_fc2 = ptr(f16(sd[p + "mlp.fc2.weight"])), ptr(f32(p + "mlp.fc2.bias"))
+
+        cfg = _lib.VitConfig(d.image_size, d.patch_size, d.hidden, d.heads, d.intermediate, d.layers, d.ln_eps,
+                             d.patch_k_pad)
+        w = _lib.VitWeights(ptr(patch_w), ptr(cls), ptr(pos), ptr(pre_g), ptr(pre_b), layers)
+        if self._handle:
+            self._lib.pg_vit_destroy(self._handle)
+            self._handle = C.c_void_p()
+        check(self._lib.pg_vit_create(C.byref(cfg), C.byref(w), C.byref(self._handle)), "pg_vit_create")
+
+    def __del__(self):
+        try:
+            if self._handle:
+                self._lib.pg_vit_destroy(self._handle)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------ forward
+    def workspace_bytes(self, n_views: int) -> int:
+        return int(self._lib.pg_vit_workspace_bytes(self._handle, n_views))
+
+    def _workspace(self, n_views: int) -> torch.Tensor:
+        need = self.workspace_bytes(n_views)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    @torch.no_grad()
+    def forward(self, pixel_values: torch.Tensor, return_hidden: bool = False):
+        """pixel_values [N, 3, H, W] (fp32 or fp16, CUDA) -> token-mean embedding [N, hidden] fp32
+        (and last_hidden_state [N, tokens, hidden] fp32 when `return_hidden`)."""
+        d = self.dims
+        if not pixel_values.is_cuda:
+            raise PigeonB200Error("pixel_values must be a CUDA tensor (the module moves host tensors first)")
+        if pixel_values.dim() != 4 or tuple(pixel_values.shape[1:]) != (3, d.image_size, d.image_size):
+            raise ValueError(f"Input image size ({tuple(pixel_values.shape[1:])}) doesn't match model "
+                             f"(3, {d.image_size}, {d.image_size}).")
+        if pixel_values.dtype not in (torch.float32, torch.float16):
+            pixel_values = pixel_values.float()
+        pixel_values = pixel_values.contiguous()
+        n = pixel_values.shape[0]
+        emb = torch.empty((n, d.hidden), dtype=torch.float32, device=self.device)
+        hidden = torch.empty((n, d.tokens, d.hidden), dtype=torch.float32, device=self.device) if return_hidden else None
+        step = max(1, min(self.max_views_per_pass, n))
+        ws = self._workspace(step)
+        stream = current_stream_ptr()
+        for s in range(0, n, step):
+            e = min(n, s + step)
+            check(self._lib.pg_vit_forward(self._handle, ptr(pixel_values[s:e]), int(pixel_values.dtype == torch.float16),
+                                           e - s, ptr(ws), ws.numel(), ptr(emb[s:e]),
+                                           ptr(hidden[s:e]) if hidden is not None else None, stream), "pg_vit_forward")
+        return (emb, hidden) if return_hidden else emb
+
+    __call__ = forward

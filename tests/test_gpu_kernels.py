@@ -1,0 +1,158 @@
+"""Kernel-level parity on the B200: each hand-written kernel against the same op in plain PyTorch fp32
+(a floating-point kernel's torch reference, evaluated on the SAME fp16-rounded operands so that the
+tolerance measures the kernel, not the quantisation)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 256, 128), (300, 384, 192), (577 * 2, 3072, 1024),
+                                   (1154, 1024, 4096), (64, 1000, 3072), (1, 1000, 3072), (1000, 2076, 96)])
+def test_gemm_f32_bias(cuda, M, N, K):
+    from pigeon_b200 import _lib, ops
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).half().to(cuda)
+    w = (torch.randn(N, K, generator=g) * 0.05).half().to(cuda)
+    b = torch.randn(N, generator=g).to(cuda)
+    ref = a.float() @ w.float().t() + b
+    out = ops.gemm_f16(a, w, b, _lib.EPI_F32_BIAS)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 2e-6, _rel(out, ref)
+    out2 = ops.gemm_f16(a, w, None, _lib.EPI_F32_BIAS)
+    assert _rel(out2, ref - b) < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 512, 256), (1154, 4096, 1024), (130, 384, 64)])
+def test_gemm_epilogues(cuda, M, N, K):
+    from pigeon_b200 import _lib, ops
+    g = torch.Generator(device="cpu").manual_seed(11)
+    a = (torch.randn(M, K, generator=g)).half().to(cuda)
+    w = (torch.randn(N, K, generator=g) * 0.05).half().to(cuda)
+    b = torch.randn(N, generator=g).to(cuda)
+    acc = a.float() @ w.float().t() + b
+    out = ops.gemm_f16(a, w, b, _lib.EPI_F16_BIAS)
+    assert out.dtype == torch.float16 and _rel(out.float(), acc) < 6e-4
+    out = ops.gemm_f16(a, w, b, _lib.EPI_F16_BIAS_QGELU)
+    ref = acc * torch.sigmoid(1.702 * acc)
+    assert _rel(out.float(), ref) < 8e-4
+    resid = torch.randn(M, N, generator=g).to(cuda)
+    out = resid.clone()
+    ops.gemm_f16(a, w, b, _lib.EPI_F32_BIAS_RESID, out=out)
+    assert _rel(out, resid + acc) < 2e-6
+
+
+def test_gemm_many_tiles_persistent(cuda):
+    """more tiles than SMs: exercises the persistent loop, both TMEM accumulator stages and the ring wrap."""
+    from pigeon_b200 import _lib, ops
+    g = torch.Generator(device="cpu").manual_seed(5)
+    M, N, K = 577 * 64, 1024, 1024
+    a = (torch.randn(M, K, generator=g)).half().to(cuda)
+    w = (torch.randn(N, K, generator=g) * 0.03).half().to(cuda)
+    out = ops.gemm_f16(a, w, None, _lib.EPI_F32_BIAS)
+    ref = a.float() @ w.float().t()
+    assert _rel(out, ref) < 2e-6
+    assert torch.equal(ops.gemm_f16(a, w, None, _lib.EPI_F32_BIAS), out), "GEMM must be run-to-run deterministic"
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("rows,hidden", [(577, 1024), (1000, 256), (3, 768)])
+def test_layernorm(cuda, rows, hidden):
+    from pigeon_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(rows)
+    x = (torch.randn(rows, hidden, generator=g) * 3 + 0.5).to(cuda)
+    gam = (1 + 0.1 * torch.randn(hidden, generator=g)).to(cuda)
+    bet = (0.1 * torch.randn(hidden, generator=g)).to(cuda)
+    y = ops.layernorm_f16(x, gam, bet, 1e-5)
+    ref = torch.nn.functional.layer_norm(x, (hidden,), gam, bet, 1e-5)
+    assert (y.float() - ref).abs().max().item() < 4e-3  # fp16 output rounding of O(1..10) values
+    assert _rel(y.float(), ref) < 5e-4
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("n_views,seq,heads", [(1, 128, 1), (1, 64, 2), (2, 577, 2), (3, 200, 1), (1, 577, 16),
+                                               (2, 65, 1), (1, 129, 1), (1, 17, 4)])
+def test_attention(cuda, n_views, seq, heads):
+    from pigeon_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(seq * 3 + heads)
+    hidden = heads * 64
+    qkv = (torch.randn(n_views * seq, 3 * hidden, generator=g) * 1.5).half().to(cuda)
+    out = ops.attention_f16(qkv, n_views, seq, heads)
+    torch.cuda.synchronize()
+    x = qkv.float().view(n_views, seq, 3, heads, 64)
+    q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    att = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1)
+    ref = (att @ v).permute(0, 2, 1, 3).reshape(n_views * seq, hidden)
+    err = _rel(out.float(), ref)
+    assert err < 2e-3, err  # P and the output are rounded to fp16
+    assert torch.isfinite(out.float()).all()
+
+
+# ------------------------------------------------------------------------------------------------ head
+@pytest.mark.parametrize("B,V,D,C,k", [(8, 4, 1024, 1000, 50), (3, 1, 1024, 2076, 5), (256, 4, 1024, 1000, 50),
+                                       (5, 4, 256, 331, 7)])
+def test_head(cuda, B, V, D, C, k):
+    from pigeon_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(B + C)
+    emb = (torch.randn(B, V, D, generator=g) * 0.3).to(cuda)
+    lin = torch.nn.Linear(D, C)
+    W, bias = lin.weight.detach().to(cuda), lin.bias.detach().to(cuda)
+    cent = torch.rand(C, 2, generator=g, dtype=torch.float64).to(cuda) * 100
+    out = ops.head_forward(emb, ops.head_pack_weight(W), bias, cent, k)
+    pooled = emb.mean(1)
+    logits = pooled.double() @ W.double().t() + bias.double()
+    probs = torch.softmax(logits, -1)
+    assert _rel(out["pooled"], pooled) < 1e-6
+    assert _rel(out["logits"], logits) < 5e-6, _rel(out["logits"], logits)
+    assert _rel(out["probs"], probs) < 5e-6
+    tk = torch.topk(probs, k, dim=-1)
+    assert torch.equal(out["pred_cell"], probs.argmax(-1))
+    assert torch.equal(out["topk_idx"], tk.indices)
+    assert torch.allclose(out["topk_val"].double(), tk.values, rtol=1e-5, atol=0)
+    assert torch.equal(out["pred_lnglat"], cent[out["pred_cell"]])
+
+
+# ------------------------------------------------------------------------------------------------ refiner
+@pytest.mark.parametrize("C,P,D,B,kc,topk,members,T,maxref", [
+    (50, 600, 1024, 64, 10, 5, 0.0, 1.6, 1000.0),
+    (50, 600, 768, 64, 10, 10, 6.0, 0.6, 100000.0),
+    (40, 300, 256, 33, 5, 5, 3.0, 1.0, 2000.0),
+])
+def test_refiner_vs_oracle(cuda, C, P, D, B, kc, topk, members, T, maxref):
+    import numpy as np
+    from oracle import refiner as oref
+    from pigeon_b200 import ops, synthetic
+    bank = synthetic.synthetic_bank(C, P, D, seed=2, members_mean=members, empty_cells=3)
+    cand, probs = synthetic.synthetic_candidates(B, kc, C, seed=3)
+    emb = torch.from_numpy(synthetic.synthetic_queries(bank, cand, views=4, seed=4))
+    init = torch.from_numpy(synthetic.synthetic_geocells(B, seed=9))
+    candt, probst = torch.from_numpy(cand), torch.from_numpy(probs)
+    # put every other initial guess next to its refined location so that both outcomes of the
+    # max-refinement gate (proto_refiner.py:202-203) occur
+    ll0, _, _ = oref.refiner_forward(bank, emb, init, candt, probst, topk, T, 1e12)
+    init[::2] = ll0[::2].double() + 0.25
+    ll, cell, info = oref.refiner_forward(bank, emb, init, candt, probst, topk, T, maxref)
+    dbank = ops.DeviceBank(cuda, **bank)
+    oll, ocell, dbg = ops.refiner_forward(dbank, emb.to(cuda), init.to(cuda), candt.to(cuda), probst.to(cuda), topk, T,
+                                          maxref, debug=True)
+    torch.cuda.synchronize()
+    # fp32 summation order differs between torch.cdist and the kernel: compare selections only where the
+    # oracle's own decision margins are above that noise (and require that this is nearly everywhere)
+    pair_ok = info["proto_gap"] > 2e-4
+    row_ok = pair_ok.all(axis=1) & (info["margin"] > 1e-4)
+    assert pair_ok.mean() > 0.95 and row_ok.mean() > 0.8
+    assert np.array_equal(dbg["best_proto"].cpu().numpy()[pair_ok], info["best_proto"][pair_ok])
+    np.testing.assert_allclose(dbg["best_logit"].cpu().numpy(), info["best_logit"], rtol=2e-5)
+    assert np.array_equal(dbg["best_lnglat"].cpu().numpy()[pair_ok], info["best_lnglat"][pair_ok])
+    assert np.array_equal(dbg["choice"].cpu().numpy()[row_ok], info["choice"][row_ok])
+    assert (info["choice"] != 0).any(), "test data must exercise a refinement that changes the geocell"
+    assert torch.equal(ocell.cpu()[row_ok], cell[row_ok])
+    assert torch.equal(oll.cpu()[row_ok], ll[row_ok])

@@ -1,0 +1,70 @@
+"""Vision-tower parity on the B200: pg_vit_forward (fp16 tensor-core operands, fp32 accumulate / residual /
+statistics) against the fp32 CPU oracle of HF CLIPVisionTransformer (oracle/vit.py).
+
+Tolerance (BASELINE.json north_star): <= 1e-3 relative on fp32 embeddings."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-3
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def _run(cuda, dims, n_views, seed, std=0.02):
+    from oracle import vit as ovit
+    from pigeon_b200 import synthetic
+    from pigeon_b200.vit_engine import VitEngine
+    sd = synthetic.random_vit_state_dict(dims, seed=seed, std=std)
+    g = torch.Generator().manual_seed(seed + 100)
+    px = torch.randn(n_views, 3, dims.image_size, dims.image_size, generator=g)
+    ref_h, ref_layers = ovit.vit_last_hidden_state(sd, px, patch=dims.patch_size, heads=dims.heads, layers=dims.layers,
+                                                   eps=dims.ln_eps, return_layers=True)
+    eng = VitEngine(sd, dims, device=cuda, max_views_per_pass=3)
+    emb, hid = eng.forward(px.to(cuda), return_hidden=True)
+    torch.cuda.synchronize()
+    return emb, hid, ref_h
+
+
+def test_vit_tiny(cuda):
+    from pigeon_b200.vit_engine import VitDims
+    dims = VitDims(image_size=56, patch_size=14, hidden=256, heads=4, intermediate=512, layers=2)
+    emb, hid, ref_h = _run(cuda, dims, n_views=5, seed=1, std=0.05)
+    assert torch.isfinite(hid).all()
+    assert _rel(hid, ref_h) < REL_TOL, _rel(hid, ref_h)
+    assert _rel(emb, ref_h.mean(1)) < REL_TOL
+
+
+def test_vit_tiny_wide_tokens(cuda):
+    """more than one 128-row q tile and a ragged last KV block (tokens = 10*10+1 = 101 ... 17*17+1 = 290)."""
+    from pigeon_b200.vit_engine import VitDims
+    dims = VitDims(image_size=238, patch_size=14, hidden=256, heads=4, intermediate=768, layers=2)
+    emb, hid, ref_h = _run(cuda, dims, n_views=2, seed=2, std=0.05)
+    assert _rel(hid, ref_h) < REL_TOL, _rel(hid, ref_h)
+    assert _rel(emb, ref_h.mean(1)) < REL_TOL
+
+
+def test_vit_large_336(cuda):
+    """The real geometry: ViT-L/14 at 336 px (577 tokens, 24 layers), random-init weights, 2 views."""
+    from pigeon_b200.vit_engine import VitDims
+    dims = VitDims()
+    emb, hid, ref_h = _run(cuda, dims, n_views=2, seed=3)
+    e_h, e_e = _rel(hid, ref_h), _rel(emb, ref_h.mean(1))
+    print(f"ViT-L/14-336 rel-L2: last_hidden_state {e_h:.3e}  embedding {e_e:.3e}")
+    assert e_h < REL_TOL and e_e < REL_TOL, (e_h, e_e)
+
+
+def test_vit_fp16_pixels_and_chunking(cuda):
+    """fp16 pixel input path and chunked execution give the same answer as one pass on fp32 pixels of the same values."""
+    from pigeon_b200 import synthetic
+    from pigeon_b200.vit_engine import VitDims, VitEngine
+    dims = VitDims(image_size=56, patch_size=14, hidden=256, heads=4, intermediate=512, layers=1)
+    sd = synthetic.random_vit_state_dict(dims, seed=7, std=0.05)
+    px = torch.randn(7, 3, 56, 56, generator=torch.Generator().manual_seed(1)).half()
+    a = VitEngine(sd, dims, device=cuda, max_views_per_pass=2).forward(px.to(cuda))
+    b = VitEngine(sd, dims, device=cuda, max_views_per_pass=64).forward(px.float().to(cuda))
+    assert torch.equal(a, b)
