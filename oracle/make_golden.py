@@ -1,0 +1,255 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference modules (behind oracle/reference_shim.py)
+on seeded inputs.  Runs only in the authoring container (needs /root/reference); the fixtures are committed.
+
+    python -m oracle.make_golden            # writes tests/golden/
+
+Weights are never stored: every fixture records the seeds from which `pigeon_b200.synthetic` regenerates
+them bit-identically (torch CPU generator), so the files stay small.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pandas as pd
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import reference_shim as rs  # noqa: E402
+from pigeon_b200 import synthetic  # noqa: E402
+from pigeon_b200.vit_engine import VitDims  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def hf_model(dims: VitDims, sd):
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    cfg = CLIPVisionConfig(hidden_size=dims.hidden, intermediate_size=dims.intermediate, num_hidden_layers=dims.layers,
+                           num_attention_heads=dims.heads, image_size=dims.image_size, patch_size=dims.patch_size,
+                           projection_dim=768, layer_norm_eps=dims.ln_eps, attn_implementation="eager")
+    m = CLIPVisionModel(cfg)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    return m.eval()
+
+
+def head_weights(C, D, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(C, D, generator=g) * 0.03, torch.randn(C, generator=g) * 0.01
+
+
+def geo_fixture():
+    from preprocessing import haversine, haversine_matrix, smooth_labels
+    rng = np.random.default_rng(11)
+    n, m = 64, 37
+    x = np.stack([rng.uniform(-180, 180, n), rng.uniform(-90, 90, n)], 1)
+    y = np.stack([rng.uniform(-180, 180, n), rng.uniform(-90, 90, n)], 1)
+    x[0], y[0] = [10.0, 20.0], [10.0, 20.0]            # zero distance
+    x[1], y[1] = [0.0, 0.0], [180.0, 0.0]              # antipodes: pi * R
+    x[2], y[2] = [-179.9, 89.9], [179.9, -89.9]
+    c = np.stack([rng.uniform(-180, 180, m), rng.uniform(-90, 90, m)], 1)
+    xt, yt, ct = torch.tensor(x), torch.tensor(y), torch.tensor(c)
+    hm = haversine_matrix(xt, ct.t())
+    np.savez(os.path.join(OUT, "geo.npz"), x=x, y=y, c=c,
+             haversine=haversine(xt, yt).numpy(),
+             haversine_f64_f32=haversine(xt, yt.float()).numpy(),   # the dtype mix ProtoRefiner produces (:198-201)
+             haversine_matrix=hm.numpy(), smooth_labels=smooth_labels(hm).numpy())
+
+
+def head_fixture(tmp):
+    from models.super_guessr import SuperGuessr
+    C, D, B = 1000, 1024, 6
+    W, b = head_weights(C, D, seed=21)
+    g = torch.Generator().manual_seed(22)
+    emb4 = torch.randn(B, 4, D, generator=g) * 0.3
+    emb1 = torch.randn(B, D, generator=g) * 0.3
+    cells = synthetic.synthetic_geocells(C, 0)
+    labels = torch.tensor(synthetic.synthetic_geocells(B, 5))
+    labels_clf = torch.tensor([3, 999, 0, 17, 500, 250])
+    out = {}
+    with rs.chdir(tmp):
+        for name, kw, emb in (("pano", dict(panorama=True, num_candidates=50), emb4),
+                              ("pano_smooth", dict(panorama=True, num_candidates=5, should_smooth_labels=True), emb4),
+                              ("single", dict(panorama=False, num_candidates=5), emb1),
+                              ("single_from4", dict(panorama=False, num_candidates=7), emb4)):
+            sg = SuperGuessr(None, **kw).eval()
+            with torch.no_grad():
+                sg.cell_layer.weight.copy_(W)
+                sg.cell_layer.bias.copy_(b)
+                o = sg(embedding=emb, labels=labels, labels_clf=labels_clf)
+            # pandas' default CSV float parser is not round-trip exact: keep the table the reference actually loaded
+            assert np.allclose(sg.lla_geocells.numpy(), cells, rtol=1e-12, atol=1e-12)
+            out["centroids"] = sg.lla_geocells.detach().numpy().copy()
+            out[f"{name}_loss"] = o.loss.numpy()
+            out[f"{name}_preds_LLH"] = o.preds_LLH.numpy()
+            out[f"{name}_preds_geocell"] = o.preds_geocell.numpy()
+            out[f"{name}_topk_val"] = o.top5_geocells.values.numpy()
+            out[f"{name}_topk_idx"] = o.top5_geocells.indices.numpy()
+    np.savez(os.path.join(OUT, "head.npz"), emb4=emb4.numpy(), emb1=emb1.numpy(), labels=labels.numpy(),
+             labels_clf=labels_clf.numpy(), meta=json.dumps(dict(C=C, D=D, w_seed=21, cells_seed=0)), **out)
+
+
+def vit_fixture(tmp, name, dims: VitDims, sd_seed, n_samples, panorama, px_seed, std):
+    """pixel_values -> reference SuperGuessr(HF CLIPVisionModel.base_model) -> ModelOutput; plus CLIPEmbedding."""
+    from models.clip_embedder import CLIPEmbedding
+    from models.super_guessr import SuperGuessr
+    C = 1000
+    sd = synthetic.random_vit_state_dict(dims, seed=sd_seed, std=std)
+    hf = hf_model(dims, sd)
+    W, b = head_weights(C, dims.hidden, seed=31)
+    g = torch.Generator().manual_seed(px_seed)
+    ch = 12 if panorama else 3
+    px = torch.randn(n_samples, ch, dims.image_size, dims.image_size, generator=g)
+    labels = torch.tensor(synthetic.synthetic_geocells(n_samples, 6))
+    labels_clf = torch.arange(n_samples) * 7 % C
+    with rs.chdir(tmp):
+        sg = SuperGuessr(hf.base_model, panorama=panorama, freeze_base=True, num_candidates=50).eval()
+    with torch.no_grad():
+        sg.cell_layer.weight.copy_(W)
+        sg.cell_layer.bias.copy_(b)
+        if dims.image_size != 336:
+            # super_guessr.py:388 hard-codes 336x336 in the panorama reshape; for the small geometry feed the
+            # already-unfolded views through the non-panorama branch of the SAME reference forward.
+            views = px.reshape(-1, 3, dims.image_size, dims.image_size)
+            sg.panorama = False
+            o = sg(pixel_values=views, labels=labels.repeat_interleave(ch // 3, 0), labels_clf=labels_clf.repeat_interleave(ch // 3))
+            emb_views = o.embedding
+        else:
+            o = sg(pixel_values=px, labels=labels, labels_clf=labels_clf)
+            emb_views = o.embedding
+        ce = object.__new__(CLIPEmbedding)
+        torch.nn.Module.__init__(ce)
+        ce.device, ce.clip_model, ce.panorama = "cpu", hf, panorama
+        views = px.reshape(-1, 3, dims.image_size, dims.image_size)
+        ce_emb = ce.forward(views)                       # clip_embedder.py:79-89 -> :42-66
+    np.savez(os.path.join(OUT, f"{name}.npz"),
+             meta=json.dumps(dict(dims=dims.__dict__, sd_seed=sd_seed, std=std, px_seed=px_seed, n_samples=n_samples,
+                                  panorama=panorama, C=C, w_seed=31, cells_seed=0)),
+             embedding=emb_views.numpy(), clip_embedding=ce_emb.numpy(), loss=o.loss.numpy(),
+             preds_LLH=o.preds_LLH.numpy(), preds_geocell=o.preds_geocell.numpy(),
+             topk_val=o.top5_geocells.values.numpy(), topk_idx=o.top5_geocells.indices.numpy(),
+             labels=labels.numpy(), labels_clf=labels_clf.numpy(), centroids=sg.lla_geocells.detach().numpy().copy())
+
+
+class _DuckProtos:
+    """protos[cell]: what the reference's per-cell HF Dataset (torch format) yields, for datasets>=3 where
+    Dataset['embedding'] no longer returns a Tensor: ['embedding'] -> Tensor, [i] -> row dict."""
+
+    def __init__(self, ds):
+        self.rows = [ds[i] for i in range(len(ds))]
+        self.emb = torch.stack([r["embedding"] for r in self.rows])
+
+    def __getitem__(self, k):
+        return self.emb if isinstance(k, str) and k == "embedding" else self.rows[k]
+
+    def __len__(self):
+        return len(self.rows)
+
+
+def refiner_fixture(tmp, name, C, P, D, B, kc, topk, members, T, maxref, seed):
+    """Build the reference's on-disk inputs (HF DatasetDict + prototype CSV), run the UNMODIFIED ProtoRefiner
+    constructor (bank building, proto_refiner.py:53-90,257-313,359-378) and forward (:121-255)."""
+    import concurrent.futures as cf
+    import datasets
+    import models.proto_refiner as pr
+    bank = synthetic.synthetic_bank(C, P, D, seed=seed, members_mean=members, empty_cells=3)
+    n_train = bank["data_emb"].shape[0]
+    ds_path, csv_path = os.path.join(tmp, f"hf_{name}"), os.path.join(tmp, f"protos_{name}.csv")
+    # training embeddings as the reference stores them: (4, D) per sample (4-view panoramas) -> the refiner
+    # averages views itself (:370-371).  Views are the stored mean +- a perturbation that cancels exactly.
+    rng = np.random.default_rng(seed + 1)
+    pert = rng.standard_normal((n_train, 2, D)).astype(np.float32) * 0.01
+    e = bank["data_emb"]
+    views = np.stack([e + pert[:, 0], e - pert[:, 0], e + pert[:, 1], e - pert[:, 1]], axis=1).astype(np.float32)
+    ds = datasets.Dataset.from_dict({"embedding": views.tolist(), "labels": bank["data_lnglat"].tolist()})
+    datasets.DatasetDict(train=ds.with_format("torch")).save_to_disk(ds_path)
+    rows = []
+    for c in range(C):
+        for p in range(bank["cell_off"][c], bank["cell_off"][c + 1]):
+            idx = bank["member_idx"][bank["member_off"][p]: bank["member_off"][p + 1]]
+            rows.append(dict(geocell_idx=c, cluster=int(p - bank["cell_off"][c]), lng=float(bank["proto_lnglat"][p, 0]),
+                             lat=float(bank["proto_lnglat"][p, 1]), count=int(len(idx)), indices=json.dumps([int(i) for i in idx])))
+    pd.DataFrame(rows).to_csv(csv_path, index=False)
+
+    class _Serial(cf.Executor):  # ProcessPoolExecutor(max_workers=64) stand-in: same calls, in-process
+        def __init__(self, *a, **kw):
+            pass
+
+        def submit(self, fn, *a, **kw):
+            f = cf.Future()
+            try:
+                f.set_result(fn(*a, **kw))
+            except Exception as ex:  # noqa: BLE001
+                f.set_exception(ex)
+            return f
+
+    real_pool = pr.ProcessPoolExecutor
+    pr.ProcessPoolExecutor = _Serial
+    try:
+        ref = pr.ProtoRefiner(topk=topk, max_refinement=maxref, temperature=T, proto_path=csv_path, dataset_path=ds_path)
+    finally:
+        pr.ProcessPoolExecutor = real_pool
+    ref.eval()
+    ref.dataset = datasets.DatasetDict(train=ref.dataset["train"].with_format("torch"))
+    # pack the bank FROM THE REFERENCE-BUILT prototypes (validates the CSR packing + prototype means)
+    cells = []
+    for c in range(C):
+        d = ref.protos[c] if c < len(ref.protos) else None
+        if d is None:
+            cells.append(None)
+            continue
+        cells.append([dict(lng=float(r["lng"]), lat=float(r["lat"]), count=int(r["count"]),
+                           indices=[int(i) for i in r["indices"]], embedding=r["embedding"].numpy()) for r in
+                      (d[i] for i in range(len(d)))])
+    while len(cells) < C:
+        cells.append(None)
+    from oracle.refiner import pack_bank
+    data_emb = torch.stack([x for x in ref.dataset["train"]["embedding"]]).mean(1).numpy() if False else views.mean(axis=1)
+    # the reference averages views with torch (.mean(dim=1), :250-251): reproduce with torch for bit-equality
+    data_emb = torch.from_numpy(views).mean(dim=1).numpy()
+    packed = pack_bank(cells, data_emb, bank["data_lnglat"])
+    ref.protos = [None if d is None else _DuckProtos(d) for d in ref.protos] + [None] * (C - len(ref.protos))
+
+    cand, probs = synthetic.synthetic_candidates(B, kc, C, seed=seed + 2)
+    q = synthetic.synthetic_queries(packed, cand, views=4, seed=seed + 3)
+    init = synthetic.synthetic_geocells(B, seed=seed + 4)
+    qt, candt, probst = torch.from_numpy(q), torch.from_numpy(cand), torch.from_numpy(probs)
+    with rs.device_redirect(), torch.no_grad():
+        ref.max_refinement = 1e12
+        _, ll0, _ = ref(qt, initial_preds=torch.from_numpy(init), candidate_cells=candt, candidate_probs=probst)
+        init[::2] = ll0[::2].double().numpy() + 0.25      # both outcomes of the max-refinement gate
+        ref.max_refinement = maxref
+        _, ll, cell = ref(qt, initial_preds=torch.from_numpy(init), candidate_cells=candt, candidate_probs=probst)
+        _, ll_np, cell_np = ref(qt, initial_preds=torch.from_numpy(init), candidate_cells=candt, candidate_probs=None)
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"),
+                        meta=json.dumps(dict(C=C, P=P, D=D, B=B, kc=kc, topk=topk, members=members, T=T, maxref=maxref, seed=seed)),
+                        emb=q, init=init, cand=cand, probs=probs, preds_LLH=ll.numpy(), preds_geocell=cell.numpy(),
+                        preds_LLH_noprob=ll_np.numpy(), preds_geocell_noprob=cell_np.numpy(), **{f"bank_{k}": v for k, v in packed.items()})
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="pigeon_golden_")
+    os.makedirs(os.path.join(tmp, "data"))
+    cells = synthetic.synthetic_geocells(1000, 0)
+    pd.DataFrame({"lng": cells[:, 0], "lat": cells[:, 1]}).to_csv(os.path.join(tmp, "data", "geocells_2203.csv"), index=False)
+    rs.install()
+    torch.set_num_threads(os.cpu_count())
+    geo_fixture()
+    head_fixture(tmp)
+    small = VitDims(image_size=56, patch_size=14, hidden=256, heads=4, intermediate=512, layers=2)
+    vit_fixture(tmp, "vit_small", small, sd_seed=41, n_samples=3, panorama=True, px_seed=42, std=0.05)
+    vit_fixture(tmp, "vit_large_single", VitDims(), sd_seed=0, n_samples=1, panorama=False, px_seed=1, std=0.02)
+    vit_fixture(tmp, "vit_large_pano", VitDims(), sd_seed=0, n_samples=2, panorama=True, px_seed=2, std=0.02)
+    refiner_fixture(tmp, "refiner_count1", C=40, P=400, D=128, B=48, kc=10, topk=5, members=0.0, T=1.6, maxref=1000, seed=50)
+    refiner_fixture(tmp, "refiner_members", C=30, P=200, D=128, B=40, kc=12, topk=12, members=5.0, T=0.6, maxref=100000, seed=60)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
