@@ -97,6 +97,15 @@ int pg_head_forward(const float* emb, int32_t B, int32_t V, int32_t D, const voi
                     float* pooled, float* logits, float* probs, int64_t* pred_cell, double* pred_lnglat,
                     float* topk_val, int64_t* topk_idx, void* stream);
 
+/* Classification loss of reference models/super_guessr.py:468-474 (CrossEntropyLoss, mean over the batch).
+ *   mode 0: labels_idx i64 [B] class indices;  mode 1: soft f32 [B, C] target probabilities;
+ *   mode 2: haversine-smoothed targets from labels_lnglat f64 [B, 2] and centroids f64 [C, 2]
+ *           (preprocessing/geo_utils.py:58-74 + preprocessing/utils.py:7-19, smoothing_km = 65).
+ * per_sample f64 [B] is scratch/out; loss_out f64 [1]. */
+int pg_head_loss(const float* logits, int32_t B, int32_t C, int32_t mode, const int64_t* labels_idx,
+                 const float* soft, const double* labels_lnglat, const double* centroids, double smoothing_km,
+                 double* per_sample, double* loss_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * ProtoRefiner (reference models/proto_refiner.py:121-255, 332-357; preprocessing/geo_utils.py:40-55)
  * ------------------------------------------------------------------------------------------------- */
@@ -125,6 +134,16 @@ int pg_refiner_forward(const pg_refiner_bank* bank, const float* emb, int64_t B,
                        int32_t cand_stride, int32_t topk, float temperature, double max_refinement_km,
                        void* workspace, size_t workspace_bytes, float* out_lnglat, int64_t* out_cell,
                        float* best_logit, float* best_lnglat, int32_t* best_proto, int32_t* choice, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Per-launch device timing (measurement aid for bench.py; not part of the reference-facing surface).
+ * begin: subsequent launches of this library are bracketed with CUDA events on their launch stream;
+ * end: synchronises the device, stops recording and returns the number of kernel families seen;
+ * read: fills `n` entries (family name, summed milliseconds, launch count).
+ * ------------------------------------------------------------------------------------------------- */
+void pg_profile_begin(void);
+int pg_profile_end(void);
+void pg_profile_read(const char** names, float* ms, int32_t* counts, int32_t n);
 
 /* ---------------------------------------------------------------------------------------------------
  * Building blocks (exported for unit tests and for callers that fuse differently)

@@ -19,6 +19,7 @@
 // TMEM A-operand and V as an MN-major smem B-operand.  No online rescale, O stays in TMEM until the end.
 #include "attention.h"
 #include "ptx.cuh"
+#include "prof.h"
 #include "tma_host.h"
 
 namespace pg {
@@ -299,6 +300,7 @@ int attention_f16(const void* qkv, void* out, int n_views, int seq, int heads, c
   a.out = reinterpret_cast<__half*>(out);
   a.scale_log2 = 0.125f * 1.4426950408889634f;
   dim3 grid((seq + kBlockQ - 1) / kBlockQ, heads, n_views);
+  ProfScope prof("attention", stream);
   attention_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tm, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_last_error("attention launch: %s", cudaGetErrorString(e)); return 1; }

@@ -199,6 +199,14 @@ int pg_head_forward(const float* emb, int32_t B, int32_t V, int32_t D, const voi
                       reinterpret_cast<long long*>(topk_idx), centroids, B, C, k, stream);
 }
 
+int pg_head_loss(const float* logits, int32_t B, int32_t C, int32_t mode, const int64_t* labels_idx, const float* soft,
+                 const double* labels_lnglat, const double* centroids, double smoothing_km, double* per_sample,
+                 double* loss_out, void* stream) {
+  if (!logits || !per_sample || !loss_out || B <= 0 || C <= 0) { set_last_error("pg_head_loss: bad argument"); return 1; }
+  return ce_loss(logits, B, C, mode, reinterpret_cast<const long long*>(labels_idx), soft, labels_lnglat, centroids,
+                 smoothing_km, per_sample, loss_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
 // ---------------------------------------------------------------------------------------------- refiner
 size_t pg_refiner_workspace_bytes(int64_t B, int32_t topk, int32_t D) {
   if (B <= 0 || topk <= 0 || D <= 0) return 0;
@@ -247,6 +255,11 @@ int pg_refiner_forward(const pg_refiner_bank* bank, const float* emb, int64_t B,
                           topk, temperature, max_refinement_km, out_lnglat, reinterpret_cast<long long*>(out_cell),
                           choice, stream);
 }
+
+// ---------------------------------------------------------------------------------------------- profiler
+void pg_profile_begin(void) { prof_begin(); }
+int pg_profile_end(void) { return prof_end(); }
+void pg_profile_read(const char** names, float* ms, int32_t* counts, int32_t n) { prof_read(names, ms, counts, n); }
 
 // ---------------------------------------------------------------------------------------------- blocks
 int pg_gemm_f16(const void* a, int32_t lda, const void* w, int32_t ldw, void* out, int32_t ldo, const float* bias,

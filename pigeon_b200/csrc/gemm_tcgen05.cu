@@ -16,6 +16,7 @@
 // Two TMEM accumulator stages (2 x BLOCK_N columns) so tile i's epilogue overlaps tile i+1's MMAs.
 #include "gemm.h"
 #include "ptx.cuh"
+#include "prof.h"
 #include "tma_host.h"
 
 namespace pg {
@@ -276,6 +277,8 @@ int launch(const GemmProblem& p, int num_sms, cudaStream_t stream) {
   const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M, n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int tiles = m_blocks * n_blocks;
   const int grid = tiles < num_sms ? tiles : num_sms;
+  static const char* const kNames[] = {"gemm_f16_bias", "gemm_f16_bias_qgelu", "gemm_f32_bias_resid", "gemm_f32_bias", "gemm_f32_rowmap"};
+  ProfScope prof(kNames[EPI], stream);
   kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_last_error("gemm launch: %s", cudaGetErrorString(e)); return 1; }

@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "prof.h"
 #include "tma_host.h"
 
 namespace pg {
@@ -136,6 +137,81 @@ softmax_topk_kernel(const float* __restrict__ logits, float* __restrict__ probs,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Classification loss of reference models/super_guessr.py:468-474 (nn.CrossEntropyLoss, mean reduction):
+//   mode 0: integer class labels            loss_b = lse(x_b) - x_b[y_b]
+//   mode 1: soft targets t [B, C] (f32)     loss_b = sum_c t_bc (lse(x_b) - x_bc)
+//   mode 2: haversine-smoothed targets      t_bc = exp(-(d_bc - min_c d_bc) / smoothing), NaN/inf -> 0
+//           with d = haversine_matrix(labels, centroids) in km, fp64 (preprocessing/geo_utils.py:58-74,
+//           preprocessing/utils.py:7-19)
+// One CTA per sample; per-sample losses in fp64, then a single-block mean.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_reduce(double v, double* red, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmax(v, u) : v + u;
+  }
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = red[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) t = is_max ? fmax(t, red[w]) : t + red[w];
+  return t;
+}
+
+__device__ __forceinline__ double haversine_km(double lng0, double lat0, double lng1, double lat1) {
+  const double kDeg = 3.14159265358979323846 / 180.0;
+  const double x_lng = lng0 * kDeg, x_lat = lat0 * kDeg, y_lng = lng1 * kDeg, y_lat = lat1 * kDeg;
+  const double s_lat = sin((x_lat - y_lat) / 2), s_lng = sin((x_lng - y_lng) / 2);
+  const double a = s_lat * s_lat + (cos(x_lat) * cos(y_lat)) * (s_lng * s_lng);
+  return (6378137.0 * (2 * asin(sqrt(a)))) / 1000;
+}
+
+__global__ void __launch_bounds__(256)
+ce_loss_kernel(const float* __restrict__ logits, int C, int mode, const long long* __restrict__ labels_idx,
+               const float* __restrict__ soft, const double* __restrict__ labels_lnglat,
+               const double* __restrict__ centroids, double smoothing, double* __restrict__ per_sample) {
+  __shared__ double red[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* x = logits + (long)b * C;
+  double m = -INFINITY;
+  for (int c = tid; c < C; c += 256) m = fmax(m, (double)x[c]);
+  m = block_reduce(m, red, true);
+  double s = 0;
+  for (int c = tid; c < C; c += 256) s += exp((double)x[c] - m);
+  s = block_reduce(s, red, false);
+  const double lse = m + log(s);
+  double loss = 0;
+  if (mode == 0) {
+    if (tid == 0) loss = lse - (double)x[labels_idx[b]];
+  } else if (mode == 1) {
+    for (int c = tid; c < C; c += 256) loss += (double)soft[(long)b * C + c] * (lse - (double)x[c]);
+  } else {
+    const double lng = labels_lnglat[2 * b], lat = labels_lnglat[2 * b + 1];
+    double dmin = INFINITY;
+    for (int c = tid; c < C; c += 256) dmin = fmin(dmin, haversine_km(lng, lat, centroids[2 * c], centroids[2 * c + 1]));
+    dmin = -block_reduce(-dmin, red, true);
+    for (int c = tid; c < C; c += 256) {
+      double t = exp(-(haversine_km(lng, lat, centroids[2 * c], centroids[2 * c + 1]) - dmin) / smoothing);
+      if (isnan(t) || isinf(t)) t = 0;
+      loss += t * (lse - (double)x[c]);
+    }
+  }
+  loss = block_reduce(loss, red, false);
+  if (tid == 0) per_sample[b] = loss;
+}
+
+__global__ void mean_f64_kernel(const double* __restrict__ v, int n, double* __restrict__ out) {
+  __shared__ double red[8];
+  double s = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+  s = block_reduce(s, red, false);
+  if (threadIdx.x == 0) *out = s / n;
+}
+
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_last_error("%s launch: %s", what, cudaGetErrorString(e)); return 1; }
@@ -148,6 +224,7 @@ int view_mean_split(const float* emb, float* pooled, void* a3_f16, int B, int V,
   const long total = (long)B * D;
   int grid = (int)((total + 255) / 256);
   if (grid > 4096) grid = 4096;
+  ProfScope prof("head_view_mean_split", stream);
   view_mean_split_kernel<<<grid, 256, 0, stream>>>(emb, pooled, reinterpret_cast<__half*>(a3_f16), B, V, D);
   return check_launch("view_mean_split");
 }
@@ -169,9 +246,26 @@ int softmax_topk(const float* logits, float* probs, long long* pred_cell, double
     cudaError_t e = cudaFuncSetAttribute(softmax_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_last_error("softmax_topk: smem attr: %s", cudaGetErrorString(e)); return 1; }
   }
+  ProfScope prof("head_softmax_topk", stream);
   softmax_topk_kernel<<<B, 256, smem, stream>>>(logits, probs, pred_cell, pred_lnglat, topk_val, topk_idx, centroids,
                                                 C, k);
   return check_launch("softmax_topk");
+}
+
+int ce_loss(const float* logits, int B, int C, int mode, const long long* labels_idx, const float* soft,
+            const double* labels_lnglat, const double* centroids, double smoothing, double* per_sample,
+            double* loss_out, cudaStream_t stream) {
+  if (mode < 0 || mode > 2) { set_last_error("ce_loss: bad mode %d", mode); return 1; }
+  if ((mode == 0 && !labels_idx) || (mode == 1 && !soft) || (mode == 2 && (!labels_lnglat || !centroids))) {
+    set_last_error("ce_loss: missing labels for mode %d", mode);
+    return 1;
+  }
+  ProfScope prof("head_ce_loss", stream);
+  ce_loss_kernel<<<B, 256, 0, stream>>>(logits, C, mode, labels_idx, soft, labels_lnglat, centroids, smoothing,
+                                        per_sample);
+  if (check_launch("ce_loss")) return 1;
+  mean_f64_kernel<<<1, 256, 0, stream>>>(per_sample, B, loss_out);
+  return check_launch("ce_loss_mean");
 }
 
 }  // namespace pg

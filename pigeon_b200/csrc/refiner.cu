@@ -13,6 +13,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "prof.h"
 #include "tma_host.h"
 
 namespace pg {
@@ -177,6 +178,7 @@ int refiner_pool(const float* emb, float* q, long B, int V, int D, cudaStream_t 
   const long total = B * D;
   int grid = (int)((total + 255) / 256);
   if (grid > 8192) grid = 8192;
+  ProfScope prof("refiner_pool", stream);
   pool_views_kernel<<<grid, 256, 0, stream>>>(emb, q, B, V, D);
   return check_launch("refiner_pool");
 }
@@ -189,6 +191,7 @@ int refiner_scan(const RefinerBank& bank, const float* q, const long long* cand,
   const long cap = (long)num_sms * 8;
   if (blocks > cap) blocks = cap;
   const int grid = (int)blocks;
+  ProfScope prof("refiner_scan", stream);
   switch (bank.dim / 128) {
 #define PG_CASE(N)                                                                                           \
   case N:                                                                                                    \
@@ -211,6 +214,7 @@ int refiner_finalize(const float* best_logit, const float* best_lnglat, const lo
                      cudaStream_t stream) {
   if (B == 0) return 0;
   const int grid = (int)((B + 127) / 128);
+  ProfScope prof("refiner_finalize", stream);
   finalize_kernel<<<grid, 128, 0, stream>>>(best_logit, best_lnglat, cand, cand_prob, cand_stride, init_lnglat, B,
                                             topk, temperature, max_refinement, out_lnglat, out_cell, out_choice);
   return check_launch("refiner_finalize");

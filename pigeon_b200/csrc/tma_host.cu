@@ -1,8 +1,14 @@
 #include "tma_host.h"
 
+#include "prof.h"
+
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
 
 namespace pg {
 
@@ -58,6 +64,55 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
     return 1;
   }
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------- profiler
+namespace {
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_recs;
+std::vector<std::string> g_prof_names;
+std::vector<float> g_prof_ms;
+std::vector<int> g_prof_counts;
+}  // namespace
+
+bool prof_enabled() { return g_prof_on; }
+void prof_record(const char* name, cudaEvent_t start, cudaEvent_t stop) { g_prof_recs.push_back({name, start, stop}); }
+
+void prof_begin() {
+  g_prof_recs.clear();
+  g_prof_on = true;
+}
+
+int prof_end() {
+  g_prof_on = false;
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<float, int>> agg;
+  for (auto& r : g_prof_recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    auto& a = agg[r.name];
+    a.first += ms;
+    a.second += 1;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof_recs.clear();
+  g_prof_names.clear(); g_prof_ms.clear(); g_prof_counts.clear();
+  for (auto& kv : agg) {
+    g_prof_names.push_back(kv.first);
+    g_prof_ms.push_back(kv.second.first);
+    g_prof_counts.push_back(kv.second.second);
+  }
+  return (int)g_prof_names.size();
+}
+
+void prof_read(const char** names, float* ms, int* counts, int n) {
+  for (int i = 0; i < n && i < (int)g_prof_names.size(); ++i) {
+    names[i] = g_prof_names[i].c_str();
+    ms[i] = g_prof_ms[i];
+    counts[i] = g_prof_counts[i];
+  }
 }
 
 }  // namespace pg

@@ -16,4 +16,8 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 void set_last_error(const char* fmt, ...);
 const char* last_error();
 
+void prof_begin();
+int prof_end();
+void prof_read(const char** names, float* ms, int* counts, int n);
+
 }  // namespace pg

@@ -7,6 +7,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+#include "prof.h"
 #include "tma_host.h"
 
 namespace pg {
@@ -182,6 +183,7 @@ int im2col(const void* pixels, int pixels_are_f16, void* out, int n_views, int i
   if (kpad < 3 * patch * patch) { set_last_error("im2col: kpad too small"); return 1; }
   const long total = (long)n_views * 3 * img * img;
   const int grid = grid_for(total, 256 * 4, num_sms);
+  ProfScope prof("im2col", stream);
   if (pixels_are_f16)
     im2col_kernel<__half><<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(pixels),
                                                     reinterpret_cast<__half*>(out), n_views, img, patch, kpad);
@@ -205,6 +207,7 @@ int layernorm_f16(const float* x, void* y, const float* gamma, const float* beta
                   int num_sms, cudaStream_t stream) {
   if (hidden % 128) { set_last_error("layernorm: hidden %d not a multiple of 128", hidden); return 1; }
   const int grid = grid_for(rows, 8, num_sms);
+  ProfScope prof("layernorm", stream);
   PG_DISPATCH_NV4(hidden, (layernorm_f16_kernel<NV4><<<grid, 256, 0, stream>>>(
                               x, reinterpret_cast<__half*>(y), gamma, beta, rows, eps)));
   return check_launch("layernorm");
@@ -214,6 +217,7 @@ int embed_preln(float* x, const float* cls, const float* pos, const float* gamma
                 int tokens, int hidden, float eps, int num_sms, cudaStream_t stream) {
   if (hidden % 128) { set_last_error("embed_preln: hidden %d not a multiple of 128", hidden); return 1; }
   const int grid = grid_for(rows, 8, num_sms);
+  ProfScope prof("embed_preln", stream);
   PG_DISPATCH_NV4(hidden, (embed_preln_kernel<NV4><<<grid, 256, 0, stream>>>(x, cls, pos, gamma, beta, rows,
                                                                                tokens, eps)));
   return check_launch("embed_preln");
@@ -226,6 +230,7 @@ int token_mean(const float* x, float* out, int n_views, int tokens, int hidden, 
   if (ny > 8) ny = 8;
   if (ny < 1) ny = 1;
   dim3 block(h4, ny);
+  ProfScope prof("token_mean", stream);
   token_mean_kernel<<<n_views, block, (size_t)ny * h4 * sizeof(float4), stream>>>(x, out, tokens, hidden);
   return check_launch("token_mean");
 }

@@ -1,0 +1,386 @@
+"""SuperGuessr — geocell classification model, B200 execution behind the reference's interface.
+
+Mirror of reference models/super_guessr.py (same constructor arguments, `forward(...)` keyword names,
+`ModelOutput` / serving tuple, `load_state`, `lla_geocells`, `cell_layer`, `num_cells`).  The arithmetic
+of the inference branch (:386-466) and of the classification loss (:468-474) runs in the sm_100a kernels
+of libpigeon_b200.so; there is no PyTorch/CPU fallback for it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from types import SimpleNamespace
+from typing import Optional
+
+import pandas as pd
+import torch
+from torch import Tensor, nn
+from torch.nn.parameter import Parameter
+
+from . import _lib, ops
+from ._lib import PigeonB200Error, check, current_stream_ptr, load, ptr
+from .config import (CLIP_EMBED_DIM, CLIP_PRETRAINED_HEAD, CLIP_PRETRAINED_HEAD_YFCC, GEOCELL_PATH, GEOCELL_PATH_YFCC,
+                     LABEL_SMOOTHING_CONSTANT)
+from .model_utils import ModelOutput, TopK
+from .vit_engine import VitDims, VitEngine
+
+NUM_MULTI_TASK_VARIABLES = 6   # super_guessr.py:16-25
+REGRESSION_LOSS_SCALING = 8
+NUM_CLIMATES = 28
+CLIMATE_LOSS_SCALING = 2
+NUM_MONTHS = 12
+MONTHS_LOSS_SCALING = 1
+
+
+class _Holder(nn.Module):
+    """Parameter container (no forward): keeps the HF module tree so state_dict() key names match."""
+
+
+def _linear(out_f: int, in_f: int) -> nn.Module:
+    h = _Holder()
+    h.weight = Parameter(torch.zeros(out_f, in_f))
+    h.bias = Parameter(torch.zeros(out_f))
+    return h
+
+
+def _norm(n: int) -> nn.Module:
+    h = _Holder()
+    h.weight = Parameter(torch.ones(n))
+    h.bias = Parameter(torch.zeros(n))
+    return h
+
+
+class CLIPVisionTower(nn.Module):
+    """Drop-in for HF `CLIPVisionModel` on the path the reference uses (models/clip_embedder.py:26,63;
+    evaluation/evaluate.py:36; models/super_guessr.py:137-160,395-398): same parameter names
+    (`vision_model.embeddings...`, `vision_model.pre_layrnorm`, `vision_model.encoder.layers.N....`), `.config`,
+    `.base_model`, `.vision_model.encoder.layers`, and `tower(pixel_values=...)` -> `.last_hidden_state`.
+    fp32 master parameters live here; the fp16 kernel layouts are (re)packed lazily by `VitEngine`."""
+
+    def __init__(self, dims: VitDims = VitDims(), name_or_path: str = ""):
+        super().__init__()
+        self.dims = dims
+        self.config = SimpleNamespace(hidden_size=dims.hidden, intermediate_size=dims.intermediate,
+                                      num_hidden_layers=dims.layers, num_attention_heads=dims.heads,
+                                      image_size=dims.image_size, patch_size=dims.patch_size,
+                                      layer_norm_eps=dims.ln_eps, _name_or_path=name_or_path)
+        vm = _Holder()
+        emb = _Holder()
+        emb.class_embedding = Parameter(torch.zeros(dims.hidden))
+        pe = _Holder()
+        pe.weight = Parameter(torch.zeros(dims.hidden, 3, dims.patch_size, dims.patch_size))
+        emb.patch_embedding = pe
+        pos = _Holder()
+        pos.weight = Parameter(torch.zeros(dims.tokens, dims.hidden))
+        emb.position_embedding = pos
+        vm.embeddings = emb
+        vm.pre_layrnorm = _norm(dims.hidden)  # [sic] HF spelling
+        enc = _Holder()
+        layers = []
+        for _ in range(dims.layers):
+            L = _Holder()
+            sa = _Holder()
+            for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+                setattr(sa, n, _linear(dims.hidden, dims.hidden))
+            L.self_attn = sa
+            L.layer_norm1 = _norm(dims.hidden)
+            mlp = _Holder()
+            mlp.fc1 = _linear(dims.intermediate, dims.hidden)
+            mlp.fc2 = _linear(dims.hidden, dims.intermediate)
+            L.mlp = mlp
+            L.layer_norm2 = _norm(dims.hidden)
+            layers.append(L)
+        enc.layers = nn.ModuleList(layers)
+        vm.encoder = enc
+        vm.post_layernorm = _norm(dims.hidden)  # present in HF checkpoints; unused by PIGEON (pooler_output)
+        self.vision_model = vm
+        self._engine: Optional[VitEngine] = None
+        self._packed_version = None
+        self.max_views_per_pass = 256
+
+    # HF: `CLIPVisionModel.base_model` is the model itself
+    @property
+    def base_model(self):
+        return self
+
+    @classmethod
+    def from_hf(cls, hf_model) -> "CLIPVisionTower":
+        """Build from a HuggingFace CLIPVisionModel / CLIPVisionTransformer instance (weights copied by name)."""
+        cfg = hf_model.config
+        tower = cls(VitDims.from_hf_config(cfg), name_or_path=getattr(cfg, "_name_or_path", ""))
+        sd = {k if k.startswith("vision_model.") else "vision_model." + k: v for k, v in hf_model.state_dict().items()
+              if "position_ids" not in k}
+        missing, unexpected = tower.load_state_dict(sd, strict=False)
+        if unexpected or any("post_layernorm" not in m for m in missing):
+            raise PigeonB200Error(f"cannot map HF weights: missing={missing} unexpected={unexpected}")
+        return tower
+
+    def _weights_changed(self):
+        self._packed_version = None
+
+    def _version(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def engine(self) -> VitEngine:
+        p0 = next(self.parameters())
+        if not p0.is_cuda:
+            raise PigeonB200Error("CLIPVisionTower is on the CPU: move the model with .to('cuda') — the B200 path "
+                                  "has no CPU implementation")
+        v = self._version()
+        if self._engine is None or self._packed_version != v:
+            sd = {k: t.detach() for k, t in self.state_dict().items()}
+            if self._engine is None or self._engine.device != p0.device:
+                self._engine = VitEngine(sd, self.dims, device=p0.device, max_views_per_pass=self.max_views_per_pass)
+            else:
+                self._engine.load_state_dict(sd)
+            self._packed_version = v
+        return self._engine
+
+    @torch.no_grad()
+    def embed(self, pixel_values: Tensor) -> Tensor:
+        """Token mean of last_hidden_state, fused path (last_hidden_state is not returned)."""
+        return self.engine().forward(pixel_values.to(next(self.parameters()).device))
+
+    @torch.no_grad()
+    def forward(self, pixel_values: Tensor = None, **kwargs):
+        emb, hidden = self.engine().forward(pixel_values.to(next(self.parameters()).device), return_hidden=True)
+        return SimpleNamespace(last_hidden_state=hidden, pooler_output=None, token_mean=emb)
+
+
+def as_tower(base_model) -> Optional[CLIPVisionTower]:
+    if base_model is None or isinstance(base_model, CLIPVisionTower):
+        return base_model
+    if hasattr(base_model, "config") and hasattr(base_model, "state_dict"):
+        return CLIPVisionTower.from_hf(base_model)
+    raise PigeonB200Error(f"unsupported base_model type {type(base_model).__name__}")
+
+
+class SuperGuessr(nn.Module):
+    def __init__(self, base_model: nn.Module, panorama: bool = False, hierarchical: bool = False,
+                 should_smooth_labels: bool = False, multi_task: bool = False, heading: bool = False,
+                 yfcc: bool = False, serving: bool = False, freeze_base: bool = False,
+                 num_candidates: int = 5, embed_dim: int = CLIP_EMBED_DIM, **kwargs):
+        """Same arguments as reference models/super_guessr.py:31-34.  `base_model` may be a `CLIPVisionTower`, a
+        HuggingFace `CLIPVisionModel` (converted by name) or None (the model then runs on `embedding`).
+
+        Extension (keyword-only): `geocells=` a (C, 2) array/tensor of (lng, lat) instead of reading the CSV."""
+        super().__init__()
+        geocells = kwargs.pop("geocells", None)
+        if len(kwargs) > 0:
+            print(f'Not using keyword arguments: {list(kwargs.keys())}')  # :67-68
+        if hierarchical:
+            raise NotImplementedError("hierarchical=True (experimental self-attention pooling, disabled in the shipped "
+                                      "configs: evaluate.py:42, train_modes.py:99,126) is outside the B200 hot path")
+        if heading and not panorama:
+            raise NotImplementedError("heading features for single images are outside the B200 hot path")
+
+        self.base_model = as_tower(base_model)
+        self.panorama = panorama
+        self.hidden_size = embed_dim
+        self.serving = serving
+        self.should_smooth_labels = should_smooth_labels
+        self.multi_task = multi_task
+        self.heading = heading
+        self.yfcc = yfcc
+        self.freeze_base = freeze_base
+        self.hierarchical = hierarchical
+        self.num_candidates = num_candidates
+
+        self._set_hidden_size()
+        if geocells is not None:
+            self.lla_geocells = Parameter(torch.as_tensor(geocells, dtype=torch.float64).clone(), requires_grad=False)
+        else:
+            self.lla_geocells = self.load_geocells(GEOCELL_PATH_YFCC if self.yfcc else GEOCELL_PATH)
+        self.num_cells = self.lla_geocells.size(0)
+        self.input_dim = self.hidden_size   # panorama + heading leaves the input unchanged (:279-280)
+
+        self.cell_layer = nn.Linear(self.input_dim, self.num_cells)
+        self.softmax = nn.Softmax(dim=-1)
+        if self.multi_task:
+            print('Model is multi-task.')
+            self.multi_task_head = nn.Linear(self.hidden_size, NUM_MULTI_TASK_VARIABLES)
+            self.loss_fnc_mt = nn.MSELoss(reduction='mean')
+            self.climate_layer = nn.Linear(self.input_dim, NUM_CLIMATES)
+            self.loss_fnc_climate = nn.CrossEntropyLoss()
+            if not self.yfcc:
+                self.month_layer = nn.Linear(self.input_dim, NUM_MONTHS)
+                self.loss_fnc_month = nn.CrossEntropyLoss()
+        self._freeze_params()
+        self.loss_fnc = nn.CrossEntropyLoss()
+        self._w3 = None
+        self._w3_key = None
+        self.last_pooled = None
+        print(f'Initialized SuperGuessr classification model with {self.num_cells} geocells.')
+
+    # ---------------------------------------------------------------------------------- setup (reference :133-174)
+    def _set_hidden_size(self):
+        if self.base_model is not None:
+            self.hidden_size = self.base_model.config.hidden_size
+            self.mode = 'transformer'
+
+    def _freeze_params(self):
+        if self.base_model is not None:
+            if self.freeze_base:
+                for param in self.base_model.parameters():
+                    param.requires_grad = False
+            elif 'clip-vit' in self.base_model.config._name_or_path and not self.serving:
+                head = CLIP_PRETRAINED_HEAD_YFCC if self.yfcc else CLIP_PRETRAINED_HEAD
+                self.load_state(head)
+                print(f'Initialized model parameters from model: {head}')
+                for param in self.base_model.vision_model.encoder.layers[:-1].parameters():
+                    param.requires_grad = False
+
+    def load_geocells(self, path: str) -> Tensor:
+        geo_df = pd.read_csv(path)
+        lla_coords = torch.tensor(geo_df[['lng', 'lat']].values)
+        return Parameter(data=lla_coords, requires_grad=False)
+
+    def load_state(self, path: str):
+        """reference :222-238 — by-name copy, unknown keys printed and skipped."""
+        own_state = self.state_dict()
+        state_dict = torch.load(path, map_location=torch.device('cuda'))
+        for name, param in state_dict.items():
+            if name not in own_state:
+                print(f'Parameter {name} not in model\'s state.')
+                continue
+            if isinstance(param, Parameter):
+                param = param.data
+            own_state[name].copy_(param)
+        if self.base_model is not None:
+            self.base_model._weights_changed()
+
+    def _assert_requirements(self, pixel_values=None, embedding=None, heading=None):
+        if self.training and self.heading:
+            assert heading is not None, 'If model is in heading mode, headings must be supplied during training.'
+        if self.base_model is not None:
+            assert pixel_values is not None, 'Parameter "pixel_values" must be supplied if model has a base model.'
+        else:
+            assert embedding is not None, 'Parameter "embedding" must be supplied if model does not have a base model.'
+
+    # ---------------------------------------------------------------------------------- device plumbing
+    def _device(self) -> torch.device:
+        dev = self.cell_layer.weight.device
+        if dev.type != 'cuda':
+            raise PigeonB200Error("SuperGuessr is on the CPU: call .to('cuda') — the B200 path has no CPU implementation")
+        return dev
+
+    def _packed_head(self) -> Tensor:
+        w = self.cell_layer.weight
+        key = (w.data_ptr(), w._version)
+        if self._w3 is None or self._w3_key != key:
+            self._w3 = ops.head_pack_weight(w.detach())
+            self._w3_key = key
+        return self._w3
+
+    def _classification_loss(self, logits: Tensor, labels: Optional[Tensor], labels_clf: Tensor) -> Tensor:
+        """reference :456,468-474 on the GPU (pg_head_loss)."""
+        B, Cc = logits.shape
+        dev = logits.device
+        per = torch.empty(B, dtype=torch.float64, device=dev)
+        out = torch.empty(1, dtype=torch.float64, device=dev)
+        lib = load()
+        if self.should_smooth_labels:
+            lab = labels.to(device=dev, dtype=torch.float64).contiguous()
+            check(lib.pg_head_loss(ptr(logits), B, Cc, 2, None, None, ptr(lab), ptr(self.lla_geocells.data),
+                                   float(LABEL_SMOOTHING_CONSTANT), ptr(per), ptr(out), current_stream_ptr()), "pg_head_loss")
+            return out[0]                                    # float64, like the reference's promoted soft-target CE
+        if labels_clf.dim() == 0:                            # _to_one_hot (:298-313)
+            labels_clf = labels_clf.reshape(1).expand(B)
+        if labels_clf.dim() == 1:
+            idx = labels_clf.to(device=dev, dtype=torch.int64).contiguous()
+            check(lib.pg_head_loss(ptr(logits), B, Cc, 0, ptr(idx), None, None, None, 0.0, ptr(per), ptr(out),
+                                   current_stream_ptr()), "pg_head_loss")
+        else:
+            soft = labels_clf.to(device=dev, dtype=torch.float32).contiguous()
+            check(lib.pg_head_loss(ptr(logits), B, Cc, 1, None, ptr(soft), None, None, 0.0, ptr(per), ptr(out),
+                                   current_stream_ptr()), "pg_head_loss")
+        return out[0].to(torch.float32)
+
+    # ---------------------------------------------------------------------------------- forward (reference :350-483)
+    def forward(self, pixel_values: Tensor = None, embedding: Tensor = None, heading: Tensor = None,
+                labels: Tensor = None, labels_clf: Tensor = None, labels_multi_task: Tensor = None,
+                labels_climate: Tensor = None, labels_month: Tensor = None, index: Tensor = None) -> ModelOutput:
+        self._assert_requirements(pixel_values, embedding, heading)
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("training forward/backward (fine-tune step) is not built on the B200 path yet; "
+                                      "call .eval() / torch.no_grad() for inference")
+        dev = self._device()
+        with torch.no_grad():
+            # host -> device (reference _move_to_cuda, :193-217)
+            if pixel_values is not None:
+                pixel_values = pixel_values.to(dev, non_blocking=True)
+            if embedding is not None:
+                embedding = embedding.to(dev, non_blocking=True)
+
+            num_samples = None
+            if self.panorama and pixel_values is not None:                      # :386-388
+                num_samples = pixel_values.size(0)
+                s = self.base_model.dims.image_size if self.base_model is not None else 336
+                pixel_values = pixel_values.reshape((num_samples * 4, 3, s, s))
+
+            if self.base_model is not None and pixel_values is not None:        # :391-405
+                if pixel_values.dim() > 4:
+                    pixel_values = pixel_values.squeeze(1)
+                embedding = self.base_model.embed(pixel_values)                 # ViT + token mean, fused
+                if self.panorama:
+                    embedding = embedding.reshape((num_samples, 4, -1))
+
+            layer_input = embedding.to(torch.float32)
+            if self.panorama:                                                   # :437
+                head_in = layer_input if layer_input.dim() == 3 else layer_input.unsqueeze(1)
+            elif layer_input.dim() == 3 and layer_input.size(1) == 4:           # :440-441
+                head_in = layer_input[:, 0].unsqueeze(1)
+            else:
+                head_in = layer_input.unsqueeze(1) if layer_input.dim() == 2 else layer_input
+            head_in = head_in.contiguous()
+
+            h = ops.head_forward(head_in, self._packed_head(), self.cell_layer.bias.detach().float().contiguous(),
+                                 self.lla_geocells.data, self.num_candidates)   # :447-459
+            output, logits = h["pooled"], h["logits"]
+            self.last_pooled = output           # extension: view-averaged embedding, reused by evaluation.predict_batch
+            pred_LLH, geocell_preds = h["pred_lnglat"], h["pred_cell"]
+            geocell_topk = TopK(h["topk_val"], h["topk_idx"])
+
+            preds_mt = preds_climate = preds_month = None
+            loss_reg = loss_climate = loss_month = 0
+            if self.multi_task:                                                 # :315-348 (thin PyTorch, not a kernel target)
+                preds_mt = self.multi_task_head(output)
+                preds_climate = self.climate_layer(output)
+                if not self.yfcc:
+                    preds_month = self.month_layer(output)
+                if not self.serving:
+                    loss_reg = self.loss_fnc_mt(preds_mt, labels_multi_task.to(dev)) * REGRESSION_LOSS_SCALING
+                    loss_climate = self.loss_fnc_climate(preds_climate, labels_climate.to(dev, torch.float32)) * CLIMATE_LOSS_SCALING
+                    if not self.yfcc:
+                        loss_month = self.loss_fnc_month(preds_month, labels_month.to(dev)) * MONTHS_LOSS_SCALING
+
+            if not self.training and self.serving:                              # :462-466
+                if self.multi_task:
+                    return pred_LLH, geocell_topk, preds_mt, embedding
+                return pred_LLH, geocell_topk, embedding
+
+            if labels_clf is None:
+                # the reference dereferences labels_clf unconditionally here (:456 -> _to_one_hot -> .dim())
+                raise AttributeError("'NoneType' object has no attribute 'dim' (labels_clf is required unless serving=True)")
+            loss_clf = self._classification_loss(logits, labels, labels_clf)
+            loss = loss_clf
+            if self.multi_task:
+                loss = loss_clf + loss_reg + loss_climate + loss_month
+            return ModelOutput(loss, loss_clf, loss_reg, loss_climate, loss_month, pred_LLH, geocell_preds, preds_mt,
+                               preds_climate, preds_month, geocell_topk, embedding)
+
+    def __str__(self):
+        rep = 'SuperGuessr(\n'
+        rep += f'\tbase_model\t= {self.base_model is not None}\n'
+        rep += f'\tpanorama\t= {self.panorama}\n'
+        rep += f'\thierarchical\t= {self.hierarchical}\n'
+        rep += f'\tmulti-task\t= {self.multi_task}\n'
+        rep += f'\tyfcc\t\t= {self.yfcc}\n'
+        rep += f'\tembedding_size\t= {self.hidden_size}\n'
+        rep += f'\tinput_dim\t= {self.input_dim}\n'
+        rep += f'\tnum_geocells\t= {self.num_cells}\n'
+        rep += f'\tlabel_smoothing\t= {self.should_smooth_labels}\n'
+        rep += f'\tuses_headings\t= {self.heading}\n'
+        rep += f'\tfreeze_base\t= {self.freeze_base}\n'
+        rep += f'\tserving\t\t= {self.serving}\n'
+        rep += ')'
+        return rep

@@ -1,0 +1,144 @@
+"""Parity of the PUBLIC modules (pigeon_b200.SuperGuessr / CLIPEmbedding / ProtoRefiner -> C ABI -> sm_100a
+kernels) against tests/golden/*.npz, i.e. against outputs of the UNMODIFIED reference modules on the same inputs.
+
+Tolerances: embeddings / logits-derived floats <= 1e-3 relative (BASELINE.json north_star); integer and index
+outputs exact wherever the reference's own decision margin exceeds that floating-point budget."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REL_TOL = 1e-3
+
+
+def load(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=False)
+    return z, (json.loads(str(z["meta"])) if "meta" in z.files else {})
+
+
+def head_weights(C, D, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(C, D, generator=g) * 0.03, torch.randn(C, generator=g) * 0.01
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def _tower(meta, cuda):
+    from pigeon_b200 import CLIPVisionTower, VitDims, synthetic
+    dims = VitDims(**meta["dims"])
+    tower = CLIPVisionTower(dims)
+    sd = synthetic.random_vit_state_dict(dims, seed=meta["sd_seed"], std=meta["std"])
+    missing, unexpected = tower.load_state_dict(sd, strict=True), None
+    return tower, dims
+
+
+def _pixels(meta, dims):
+    g = torch.Generator().manual_seed(meta["px_seed"])
+    ch = 12 if meta["panorama"] else 3
+    return torch.randn(meta["n_samples"], ch, dims.image_size, dims.image_size, generator=g)
+
+
+@pytest.mark.parametrize("name", ["vit_large_single", "vit_large_pano"])
+def test_superguessr_pixels_to_geocells(cuda, name):
+    """cfg1 of BASELINE.json (single 336x336 image, random-init ViT-L/14, 1000 geocells) and its 4-view variant."""
+    from pigeon_b200 import SuperGuessr
+    z, meta = load(name)
+    tower, dims = _tower(meta, cuda)
+    W, b = head_weights(meta["C"], dims.hidden, meta["w_seed"])
+    sg = SuperGuessr(tower, panorama=meta["panorama"], freeze_base=True, num_candidates=50, geocells=z["centroids"])
+    with torch.no_grad():
+        sg.cell_layer.weight.copy_(W)
+        sg.cell_layer.bias.copy_(b)
+    sg.to(cuda).eval()
+    px = _pixels(meta, dims)                                            # host tensor: the module moves it (H2D)
+    out = sg(pixel_values=px, labels=torch.tensor(z["labels"]), labels_clf=torch.tensor(z["labels_clf"]))
+    torch.cuda.synchronize()
+    emb = out.embedding.cpu().numpy()
+    assert emb.shape == z["embedding"].shape
+    e = _rel(emb, z["embedding"])
+    print(f"{name}: embedding rel-L2 vs reference = {e:.3e}")
+    assert e < REL_TOL, e
+    assert np.abs(emb - z["embedding"]).max() / np.abs(z["embedding"]).max() < 5e-3
+    # top-1 geocell identical (the fixtures' top-1/top-2 probability margins are > 10x the error budget)
+    margin = (z["topk_val"][:, 0] - z["topk_val"][:, 1]) / z["topk_val"][:, 0]
+    assert (margin > 20 * REL_TOL).all(), margin
+    assert np.array_equal(out.preds_geocell.cpu().numpy(), z["preds_geocell"])
+    assert np.array_equal(out.preds_LLH.cpu().numpy(), z["preds_LLH"]) and out.preds_LLH.dtype == torch.float64
+    np.testing.assert_allclose(out.top5_geocells.values.cpu().numpy(), z["topk_val"], rtol=5 * REL_TOL)
+    np.testing.assert_allclose(out.loss.item(), z["loss"], rtol=REL_TOL)
+    k_same = (out.top5_geocells.indices.cpu().numpy() == z["topk_idx"]).mean()
+    assert k_same > 0.8, k_same                                         # deep in the top-50 the margins vanish
+
+
+def test_clip_embedding_small_and_large(cuda):
+    from pigeon_b200 import CLIPEmbedding
+    for name in ("vit_small", "vit_large_single"):
+        z, meta = load(name)
+        tower, dims = _tower(meta, cuda)
+        ce = CLIPEmbedding("unused", device="cuda", clip_model=tower)
+        views = _pixels(meta, dims).reshape(-1, 3, dims.image_size, dims.image_size)
+        emb = ce(views).cpu().numpy()
+        assert emb.shape == z["clip_embedding"].shape
+        assert _rel(emb, z["clip_embedding"]) < REL_TOL, (name, _rel(emb, z["clip_embedding"]))
+
+
+@pytest.mark.parametrize("name,panorama,k,smooth,emb_key", [("pano", True, 50, False, "emb4"),
+                                                           ("pano_smooth", True, 5, True, "emb4"),
+                                                           ("single", False, 5, False, "emb1"),
+                                                           ("single_from4", False, 7, False, "emb4")])
+def test_superguessr_on_embeddings(cuda, name, panorama, k, smooth, emb_key):
+    """`-b` not given: base_model=None, the head runs on precomputed embeddings (evaluate.py:36)."""
+    from pigeon_b200 import SuperGuessr
+    z, meta = load("head")
+    W, b = head_weights(meta["C"], meta["D"], meta["w_seed"])
+    sg = SuperGuessr(None, panorama=panorama, num_candidates=k, should_smooth_labels=smooth, geocells=z["centroids"])
+    with torch.no_grad():
+        sg.cell_layer.weight.copy_(W)
+        sg.cell_layer.bias.copy_(b)
+    sg.to(cuda).eval()
+    out = sg(embedding=torch.tensor(z[emb_key]), labels=torch.tensor(z["labels"]), labels_clf=torch.tensor(z["labels_clf"]))
+    assert np.array_equal(out.preds_geocell.cpu().numpy(), z[f"{name}_preds_geocell"])
+    assert np.array_equal(out.preds_LLH.cpu().numpy(), z[f"{name}_preds_LLH"])
+    assert np.array_equal(out.top5_geocells.indices.cpu().numpy(), z[f"{name}_topk_idx"])
+    np.testing.assert_allclose(out.top5_geocells.values.cpu().numpy(), z[f"{name}_topk_val"], rtol=2e-5)
+    np.testing.assert_allclose(out.loss.item(), z[f"{name}_loss"], rtol=2e-5)
+    assert out.loss.dtype == torch.from_numpy(z[f"{name}_loss"]).dtype
+    assert out.embedding.shape == z[emb_key].shape                      # un-averaged (B,4,D) in panorama mode (quirk 10)
+
+
+def test_superguessr_serving_tuple_and_errors(cuda):
+    from pigeon_b200 import SuperGuessr
+    z, meta = load("head")
+    sg = SuperGuessr(None, panorama=True, serving=True, num_candidates=5, geocells=z["centroids"]).to(cuda).eval()
+    pred, topk, emb = sg(embedding=torch.tensor(z["emb4"]))
+    assert pred.shape == (6, 2) and topk.values.shape == (6, 5) and topk.indices.dtype == torch.int64
+    sg2 = SuperGuessr(None, panorama=True, num_candidates=5, geocells=z["centroids"]).to(cuda).eval()
+    with pytest.raises(AttributeError):                                  # quirk 9: labels_clf required unless serving
+        sg2(embedding=torch.tensor(z["emb4"]))
+    with pytest.raises(AssertionError):
+        sg2(pixel_values=None, embedding=None)
+
+
+@pytest.mark.parametrize("name", ["refiner_count1", "refiner_members"])
+def test_protorefiner_matches_reference(cuda, name):
+    from pigeon_b200 import ProtoRefiner
+    z, meta = load(name)
+    bank = {k[5:]: z[k] for k in z.files if k.startswith("bank_")}
+    ref = ProtoRefiner(topk=meta["topk"], max_refinement=meta["maxref"], temperature=meta["T"], protos=bank).eval()
+    args = dict(initial_preds=torch.tensor(z["init"]), candidate_cells=torch.tensor(z["cand"]))
+    loss, ll, cell = ref(torch.tensor(z["emb"]), candidate_probs=torch.tensor(z["probs"]), **args)
+    assert loss is None and ll.dtype == torch.float32 and cell.dtype == torch.int64
+    assert np.array_equal(cell.cpu().numpy(), z["preds_geocell"])
+    assert np.array_equal(ll.cpu().numpy(), z["preds_LLH"])
+    _, ll, cell = ref(torch.tensor(z["emb"]), candidate_probs=None, **args)
+    assert np.array_equal(cell.cpu().numpy(), z["preds_geocell_noprob"])
+    assert np.array_equal(ll.cpu().numpy(), z["preds_LLH_noprob"])
+    with pytest.raises(AssertionError):                                  # proto_refiner.py:135-137
+        ProtoRefiner(topk=99, protos=bank)(torch.tensor(z["emb"]), candidate_probs=None, **args)
