@@ -23,6 +23,7 @@ OBJ_DIR = CSRC / "build"
 SOURCES = [
     "tma_host.cu",
     "gemm_tcgen05.cu",
+    "gemm2_tcgen05.cu",
     "attention_tcgen05.cu",
     "vit_misc.cu",
     "head.cu",

@@ -1,0 +1,261 @@
+// 2-CTA (cta_group::2) persistent tcgen05 GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T (+ epilogue), N % 256 == 0.
+//
+// A CTA pair (cluster of 2 on one TPC) owns a 256 x 256 output tile: CTA r holds rows [256*m + 128*r, +128) of A and
+// rows [256*n + 128*r, +128) of W in its shared memory; ONE thread of the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16) which makes both tensor cores multiply their own A half by
+// BOTH W halves.  Versus the 1-CTA kernel each SM stages and reads half as much W: 8 KB instead of 12 KB of operand
+// reads per 128-cycle MMA and 32 KB instead of 48 KB of TMA writes per k-block, and 6 pipeline stages fit instead of 4.
+//
+//   warp 0      TMA producer (both CTAs; completion bytes land on the LEADER's full barrier)
+//   warp 1      MMA issuer (leader CTA only); tcgen05.commit multicasts to both CTAs' barriers
+//   warp 2      TMEM allocator (both CTAs, cta_group::2)
+//   warps 4..7  epilogue on the CTA's own 128 x 256 accumulator half (gemm_epilogue.cuh)
+#include "gemm.h"
+#include "gemm_epilogue.cuh"
+#include "prof.h"
+#include "ptx.cuh"
+#include "tma_host.h"
+
+namespace pg {
+
+namespace {
+
+constexpr int BLOCK_M_CTA = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_N_CTA = 128;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int kNumThreads = 256;
+constexpr int kEpiWarp0 = 4;
+constexpr int kStages = 6;
+constexpr int kABytes = BLOCK_M_CTA * BLOCK_K * 2;  // 16 KB
+constexpr int kBBytes = BLOCK_N_CTA * BLOCK_K * 2;  // 16 KB
+constexpr int kStageBytes = kABytes + kBBytes;      // per CTA
+constexpr int kTmemCols = 512;                      // two 256-column accumulator stages
+constexpr int kSmemBytes = kStages * kStageBytes + 4 * kStageWarpBytes + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `smem_addr` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_ss_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this smem offset in BOTH CTAs of the pair once the issued MMAs retired
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kABytes;
+  uint8_t* smem_stage = smem + kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + 4 * kStageWarpBytes);
+  uint64_t* full_bar = bars;                       // leader's copy is the live one
+  uint64_t* empty_bar = bars + kStages;            // per CTA
+  uint64_t* tmem_full_bar = bars + 2 * kStages;    // per CTA
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // leader's copy is the live one
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  const int m_blocks = (args.M + 2 * BLOCK_M_CTA - 1) / (2 * BLOCK_M_CTA);
+  const int n_blocks = args.N / BLOCK_N;
+  const int num_tiles = m_blocks * n_blocks;
+  const int num_kb = (args.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 2);   // leader's arrive.expect_tx + peer's remote arrive
+      mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);   // multicast tcgen05.commit
+      mbar_init(&tmem_empty_bar[s], 8);  // 4 epilogue warps x 2 CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_ptr_smem, kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();  // peer barriers initialised and both TMEM allocations done before anything crosses CTAs
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+        const int a_row = m_blk * 2 * BLOCK_M_CTA + rank * BLOCK_M_CTA;
+        const int b_row = n_blk * BLOCK_N + rank * BLOCK_N_CTA;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t full_leader = mapa(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+          else        mbar_arrive_cluster(full_leader);
+          tma_load_2d_2sm(smem_a + stage * kABytes, &tmap_a, full_leader, kb * BLOCK_K, a_row);
+          tma_load_2d_2sm(smem_b + stage * kBBytes, &tmap_b, full_leader, kb * BLOCK_K, b_row);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(2 * BLOCK_M_CTA, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * kBBytes);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t a_desc = make_smem_desc(a_addr + k * UMMA_K * 2, 16, 1024, kLayoutSw128);
+            const uint64_t b_desc = make_smem_desc(b_addr + k * UMMA_K * 2, 16, 1024, kLayoutSw128);
+            umma_ss_2sm(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
+          }
+          tc_commit_2sm(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(&tmem_full_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+    const int q = warp & 3;
+    uint8_t* stage_buf = smem_stage + (warp - kEpiWarp0) * kStageWarpBytes;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N;
+      epilogue_tile<BLOCK_N, EPI>(args, t_row, stage_buf, m_blk * 2 * BLOCK_M_CTA + rank * BLOCK_M_CTA + q * 32,
+                                  n_blk * BLOCK_N, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&tmem_empty_bar[acc]), 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncwarp();        // role lanes rejoin their warp before the aligned cluster barrier
+  cluster_sync_all();  // the pair's MMAs, commits and remote arrives are all done
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, kTmemCols);
+  }
+}
+
+template <int EPI>
+int launch2(const GemmProblem& p, int num_sms, cudaStream_t stream) {
+  constexpr bool f16_out = (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_QGELU);
+  CUtensorMap ta, tb;
+  if (make_tmap_f16_2d(&ta, p.a, p.M, p.K, p.lda, BLOCK_M_CTA, BLOCK_K)) return 1;
+  if (make_tmap_f16_2d(&tb, p.w, p.N, p.K, p.ldw, BLOCK_N_CTA, BLOCK_K)) return 1;
+  auto kern = gemm2_f16_kernel<EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) { set_last_error("gemm2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
+    attr_set = true;
+  }
+  GemmArgs a;
+  a.M = p.M; a.N = p.N; a.K = p.K; a.out = p.out; a.ldo = p.ldo; a.bias = p.bias;
+  a.vec_ok = (p.ldo % (f16_out ? 8 : 4)) == 0;
+  a.rowmap_div = p.rowmap_div > 0 ? p.rowmap_div : 1; a.rowmap_mul = p.rowmap_mul; a.rowmap_add = p.rowmap_add;
+  const int tiles = ((p.M + 255) / 256) * (p.N / BLOCK_N);
+  int pairs = num_sms / 2;
+  if (tiles < pairs) pairs = tiles;
+  static const char* const kNames[] = {"gemm_f16_bias", "gemm_f16_bias_qgelu", "gemm_f32_bias_resid", "gemm_f32_bias",
+                                       "gemm_f32_rowmap"};
+  ProfScope prof(kNames[EPI], stream);
+  kern<<<2 * pairs, kNumThreads, kSmemBytes, stream>>>(ta, tb, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_last_error("gemm2 launch: %s", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
+}  // namespace
+
+int gemm2_f16(const GemmProblem& p, int num_sms, cudaStream_t stream) {
+  switch (p.epi) {
+    case EPI_F16_BIAS:       return launch2<EPI_F16_BIAS>(p, num_sms, stream);
+    case EPI_F16_BIAS_QGELU: return launch2<EPI_F16_BIAS_QGELU>(p, num_sms, stream);
+    case EPI_F32_BIAS_RESID: return launch2<EPI_F32_BIAS_RESID>(p, num_sms, stream);
+    case EPI_F32_BIAS:       return launch2<EPI_F32_BIAS>(p, num_sms, stream);
+    case EPI_F32_ROWMAP:     return launch2<EPI_F32_ROWMAP>(p, num_sms, stream);
+    default: set_last_error("gemm2: unknown epilogue %d", p.epi); return 1;
+  }
+}
+
+}  // namespace pg

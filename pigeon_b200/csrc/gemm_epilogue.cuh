@@ -1,0 +1,141 @@
+// Shared epilogue of the tcgen05 GEMM kernels (1-CTA and 2-CTA): TMEM accumulator tile (128 rows x BLOCK_N fp32
+// columns per CTA) -> bias / activation / residual -> global.  Included by gemm_tcgen05.cu and gemm2_tcgen05.cu.
+#pragma once
+#include "gemm.h"
+#include "ptx.cuh"
+
+namespace pg {
+
+constexpr int kStagePitch = 144;                    // 128 B row + 16 B pad
+constexpr int kStageWarpBytes = 32 * kStagePitch;   // 4608 B per epilogue warp
+
+struct GemmArgs {
+  int M, N, K;
+  void* out;          // fp16 or fp32 [M, ldo]
+  int ldo;
+  const float* bias;  // [N] or nullptr
+  // EPI_F32_ROWMAP: output row = rowmap_mul * (row / rowmap_div) + row % rowmap_div + rowmap_add
+  int rowmap_div, rowmap_mul, rowmap_add;
+  int vec_ok;  // output rows are 16-byte aligned -> vector stores allowed
+};
+
+__device__ __forceinline__ float quick_gelu(float v) {
+  // HF "quick_gelu": x * sigmoid(1.702 x) = x / (1 + 2^(-1.702 log2(e) x)); ex2.approx + rcp.approx (2 MUFU / element)
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.4554669595930157f * v));
+  return __fdividef(v, 1.0f + e);
+}
+
+// One epilogue warp's share of one output tile: rows [warp_row0, warp_row0 + 32), columns [tile_col0, tile_col0 + BLOCK_N).
+//   t_row  : TMEM address of this warp's lane quarter at the accumulator stage's first column
+//   stage  : this warp's private staging buffer (kStageWarpBytes)
+// Per chunk of CHUNK columns (128 bytes of output per row): TMEM -> registers (thread = row) -> bias / activation ->
+// smem staging (32 rows x 128 B, 144 B pitch: conflict-free both ways) -> coalesced global phase in which 8 lanes cover
+// one 128-byte row segment (4 rows per instruction).
+template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_row, uint8_t* stage, int warp_row0,
+                                              int tile_col0, int lane) {
+  constexpr bool kF16Out = (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_QGELU);
+  constexpr int CHUNK = kF16Out ? 64 : 32;
+  constexpr int kElt = kF16Out ? 2 : 4;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK) {
+    const int col0 = tile_col0 + c0;
+    if (col0 >= args.N) break;  // warp-uniform: the rest of this tile is past N
+    uint32_t r[CHUNK];
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < CHUNK / 32; ++h) tmem_ld32(t_row + c0 + 32 * h, *reinterpret_cast<uint32_t(*)[32]>(&r[32 * h]));
+    tmem_ld_wait();
+    const bool in_n = (col0 + CHUNK <= args.N);
+    float v[CHUNK];
+#pragma unroll
+    for (int i = 0; i < CHUNK; ++i) v[i] = __uint_as_float(r[i]);
+    if (args.bias != nullptr) {
+      if (in_n) {
+        const float4* b4 = reinterpret_cast<const float4*>(args.bias + col0);
+#pragma unroll
+        for (int i = 0; i < CHUNK / 4; ++i) {
+          const float4 b = __ldg(b4 + i);
+          v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < CHUNK; ++i)
+          if (col0 + i < args.N) v[i] += __ldg(args.bias + col0 + i);
+      }
+    }
+    if (EPI == EPI_F16_BIAS_QGELU) {
+#pragma unroll
+      for (int i = 0; i < CHUNK; ++i) v[i] = quick_gelu(v[i]);
+    }
+    if (in_n && args.vec_ok) {
+      // ---- stage this thread's row (128 bytes)
+      uint4* srow = reinterpret_cast<uint4*>(stage + lane * kStagePitch);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 pk;
+        if (kF16Out) {
+          pk.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
+          pk.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+          pk.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+          pk.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+        } else {
+          pk.x = __float_as_uint(v[4 * j + 0]);
+          pk.y = __float_as_uint(v[4 * j + 1]);
+          pk.z = __float_as_uint(v[4 * j + 2]);
+          pk.w = __float_as_uint(v[4 * j + 3]);
+        }
+        srow[j] = pk;
+      }
+      __syncwarp();
+      // ---- coalesced global phase
+      const int sub = lane >> 3, c16 = lane & 7;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + sub;
+        const int grow = warp_row0 + rr;
+        if (grow < args.M) {
+          uint4 val = *reinterpret_cast<const uint4*>(stage + rr * kStagePitch + c16 * 16);
+          long orow = grow;
+          if (EPI == EPI_F32_ROWMAP)
+            orow = (long)args.rowmap_mul * (grow / args.rowmap_div) + (grow % args.rowmap_div) + args.rowmap_add;
+          uint8_t* gp = reinterpret_cast<uint8_t*>(args.out) + (orow * args.ldo + col0) * kElt + c16 * 16;
+          if (EPI == EPI_F32_BIAS_RESID) {
+            const float4 res = *reinterpret_cast<const float4*>(gp);
+            val.x = __float_as_uint(__uint_as_float(val.x) + res.x);
+            val.y = __float_as_uint(__uint_as_float(val.y) + res.y);
+            val.z = __float_as_uint(__uint_as_float(val.z) + res.z);
+            val.w = __float_as_uint(__uint_as_float(val.w) + res.w);
+          }
+          *reinterpret_cast<uint4*>(gp) = val;
+        }
+      }
+    } else {
+      // ---- ragged N tail / unaligned rows: per-thread scalar stores
+      const int row = warp_row0 + lane;
+      if (row < args.M) {
+        long orow = row;
+        if (EPI == EPI_F32_ROWMAP)
+          orow = (long)args.rowmap_mul * (row / args.rowmap_div) + (row % args.rowmap_div) + args.rowmap_add;
+        if (kF16Out) {
+          __half* o = reinterpret_cast<__half*>(args.out) + orow * args.ldo + col0;
+#pragma unroll
+          for (int i = 0; i < CHUNK; ++i)
+            if (col0 + i < args.N) o[i] = __float2half_rn(v[i]);
+        } else {
+          float* o = reinterpret_cast<float*>(args.out) + orow * args.ldo + col0;
+#pragma unroll
+          for (int i = 0; i < CHUNK; ++i)
+            if (col0 + i < args.N) {
+              float x = v[i];
+              if (EPI == EPI_F32_BIAS_RESID) x += o[i];
+              o[i] = x;
+            }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace pg

@@ -15,9 +15,12 @@
 //   warps 4..7  epilogue: tcgen05.ld -> registers -> bias/activation/residual -> global
 // Two TMEM accumulator stages (2 x BLOCK_N columns) so tile i's epilogue overlaps tile i+1's MMAs.
 #include "gemm.h"
+#include "gemm_epilogue.cuh"
 #include "ptx.cuh"
 #include "prof.h"
 #include "tma_host.h"
+
+#include <stdlib.h>
 
 namespace pg {
 
@@ -36,23 +39,8 @@ struct GemmCfg {
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 512 or 256: powers of two
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 4 * kStageWarpBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
-
-struct GemmArgs {
-  int M, N, K;
-  void* out;          // fp16 or fp32 [M, ldo]
-  int ldo;
-  const float* bias;  // [N] or nullptr
-  // EPI_F32_ROWMAP: output row = rowmap_mul * (row / rowmap_div) + row % rowmap_div + rowmap_add
-  int rowmap_div, rowmap_mul, rowmap_add;
-  int vec_ok;  // output rows are 16-byte aligned -> vector stores allowed
-};
-
-__device__ __forceinline__ float quick_gelu(float v) {
-  // HF "quick_gelu": x * sigmoid(1.702 x)
-  return v / (1.0f + __expf(-1.702f * v));
-}
 
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -64,7 +52,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* smem_stage = smem + Cfg::kStages * Cfg::kStageBytes;  // epilogue staging, 4 warps
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + 4 * kStageWarpBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::kStages;
   uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
@@ -151,95 +140,17 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ------------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------------ epilogue (gemm_epilogue.cuh)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint8_t* stage = smem_stage + (warp - kEpiWarp0) * kStageWarpBytes;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * BLOCK_M + q * 32 + lane;
-      const bool row_ok = row < args.M;
-      long out_row = row;
-      if (EPI == EPI_F32_ROWMAP) {
-        out_row = (long)args.rowmap_mul * (row / args.rowmap_div) + (row % args.rowmap_div) + args.rowmap_add;
-      }
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld32(t_row + c0, r);
-        tmem_ld_wait();
-        const int col0 = n_blk * BLOCK_N + c0;
-        if (col0 >= args.N) break;  // warp-uniform: the rest of this tile is past N
-        const bool full = args.vec_ok && (col0 + 32 <= args.N);
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (args.bias != nullptr) {
-          if (col0 + 32 <= args.N) {
-            const float4* b4 = reinterpret_cast<const float4*>(args.bias + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b = __ldg(b4 + i);
-              v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < args.N) v[i] += __ldg(args.bias + col0 + i);
-          }
-        }
-        if (EPI == EPI_F16_BIAS_QGELU) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
-        }
-        if (!row_ok) {
-          // rows past M (TMA zero-filled): nothing to store
-        } else if (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_QGELU) {
-          __half* o = reinterpret_cast<__half*>(args.out) + out_row * args.ldo + col0;
-          if (full) {
-            uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 pk;
-              pk.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
-              pk.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
-              pk.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
-              pk.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
-              o4[i] = pk;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < args.N) o[i] = __float2half_rn(v[i]);
-          }
-        } else {
-          float* o = reinterpret_cast<float*>(args.out) + out_row * args.ldo + col0;
-          if (full) {
-            float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 x = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-              if (EPI == EPI_F32_BIAS_RESID) {
-                const float4 res = o4[i];
-                x.x += res.x; x.y += res.y; x.z += res.z; x.w += res.w;
-              }
-              o4[i] = x;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < args.N) {
-                float x = v[i];
-                if (EPI == EPI_F32_BIAS_RESID) x += o[i];
-                o[i] = x;
-              }
-          }
-        }
-      }
+      epilogue_tile<BLOCK_N, EPI>(args, t_row, stage, m_blk * BLOCK_M + q * 32, n_blk * BLOCK_N, lane);
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -287,6 +198,17 @@ int launch(const GemmProblem& p, int num_sms, cudaStream_t stream) {
 
 }  // namespace
 
+int gemm2_f16(const GemmProblem& p, int num_sms, cudaStream_t stream);  // gemm2_tcgen05.cu
+
+static bool use_2cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PG_GEMM_1CTA");  // debugging / A-B switch: force the single-CTA kernel
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int gemm_f16(const GemmProblem& p, int num_sms, cudaStream_t stream) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return 0;
   if ((p.lda % 8) || (p.ldw % 8)) { set_last_error("gemm: lda/ldw must be multiples of 8 halves (TMA 16B stride)"); return 1; }
@@ -296,6 +218,7 @@ int gemm_f16(const GemmProblem& p, int num_sms, cudaStream_t stream) {
   }
   // Wide tiles when N is a multiple of 256 (all ViT-L projections); 128-wide otherwise (head, small tests).
   const bool wide = (p.N % 256 == 0);
+  if (wide && p.M > 128 && num_sms >= 2 && use_2cta()) return gemm2_f16(p, num_sms, stream);
   switch (p.epi) {
     case EPI_F16_BIAS:       return wide ? launch<256, EPI_F16_BIAS>(p, num_sms, stream)       : launch<128, EPI_F16_BIAS>(p, num_sms, stream);
     case EPI_F16_BIAS_QGELU: return wide ? launch<256, EPI_F16_BIAS_QGELU>(p, num_sms, stream) : launch<128, EPI_F16_BIAS_QGELU>(p, num_sms, stream);
