@@ -9,17 +9,20 @@
 // Input  qkv : fp16 [n_views * S, 3 * hidden]   row = (view, token); cols = [q | k | v], head-major inside
 // Output out : fp16 [n_views * S, hidden]
 //
-// One CTA per (q-tile of 128 rows, head, view); 192 threads; two CTAs co-reside per SM so one CTA's
-// softmax overlaps the other's MMAs.
-//   warp 0     TMA producer: Q tile once, then K/V tiles (128 x 64 halves, 128B swizzle) through a 4-slot ring
+// One CTA per (q-tile of 128 rows, head, view); 192 threads; two CTAs co-reside per SM (64 KB smem, 256 TMEM columns).
+//   warp 0     TMA producer: Q tile once, then K/V tiles (64 x 64 halves, 128B swizzle) through a 6-slot ring
 //   warp 1     TMEM allocator + MMA issuer (tcgen05.mma cta_group::1, M = 128)
 //   warps 2-5  softmax, one TMEM lane (= one query row) per thread
-// Exact two-pass softmax: pass 1 forms S = Q K^T block by block to get the row max; pass 2 re-forms S,
-// writes P = exp2(S*c - max*c) as fp16 over the S columns in TMEM and issues O += P V with P as the
-// TMEM A-operand and V as an MN-major smem B-operand.  No online rescale, O stays in TMEM until the end.
+//
+// Single pass, flash-style, KV blocks of 64:  S_j = Q K_j^T lands in one of TWO TMEM buffers so that the MMAs of block
+// j+1 run while the softmax warps work on block j.  The softmax warps keep a running row maximum m and row sum l,
+// write P_j = exp2(S_j*c - m*c) as packed fp16 over the S_j columns, and the MMA warp accumulates O += P_j V_j with P
+// as the TMEM A operand and V as an MN-major smem B operand.  m is only raised (and O, l rescaled in TMEM) when the
+// block maximum exceeds it by more than 2^8 in the exponent domain ("lazy rescale"): P then stays <= 256, exact in fp16
+// range, and the rescale path is rare.  Final O / l -> fp16.
 #include "attention.h"
-#include "ptx.cuh"
 #include "prof.h"
+#include "ptx.cuh"
 #include "tma_host.h"
 
 namespace pg {
@@ -28,13 +31,15 @@ namespace {
 
 constexpr int kHeadDim = 64;
 constexpr int kBlockQ = 128;
-constexpr int kBlockKV = 128;
-constexpr int kSlots = 4;
-constexpr int kTileBytes = kBlockKV * kHeadDim * 2;  // 16 KB
+constexpr int kBlockKV = 64;
+constexpr int kSlots = 6;
+constexpr int kQBytes = kBlockQ * kHeadDim * 2;       // 16 KB
+constexpr int kTileBytes = kBlockKV * kHeadDim * 2;   // 8 KB
 constexpr int kThreads = 192;
-constexpr int kTmemCols = 256;  // S/P: [0,128)  O: [128,192)
+constexpr int kTmemCols = 256;                        // S0 [0,64)  S1 [64,128)  O [128,192)
 constexpr int kOCol = 128;
-constexpr int kSmemBytes = (1 + kSlots) * kTileBytes + 1024 + 256;
+constexpr int kSmemBytes = kQBytes + kSlots * kTileBytes + 1024 + 256;
+constexpr float kRescaleThreshold = 8.0f;             // log2 domain
 
 struct AttnArgs {
   int seq;      // tokens per view (577)
@@ -63,29 +68,41 @@ __device__ __forceinline__ void tmem_st8_(uint32_t taddr, const uint32_t* r) {
                "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st32_(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 
 __global__ void __launch_bounds__(kThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;
-  uint8_t* smem_kv = smem + kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + kSlots) * kTileBytes);
-  uint64_t* full_bar = bars;             // [kSlots]
-  uint64_t* empty_bar = bars + kSlots;   // [kSlots]
+  uint8_t* smem_kv = smem + kQBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kQBytes + kSlots * kTileBytes);
+  uint64_t* full_bar = bars;             // [kSlots]  TMA -> MMA
+  uint64_t* empty_bar = bars + kSlots;   // [kSlots]  MMA -> TMA
   uint64_t* q_full = bars + 2 * kSlots;
-  uint64_t* s_full = q_full + 1;         // MMA -> softmax : an S block is complete in TMEM
-  uint64_t* sm_done = q_full + 2;        // softmax -> MMA : S consumed (pass 1) / P written (pass 2)
-  uint64_t* o_full = q_full + 3;         // MMA -> softmax : O complete
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(q_full + 4);
+  uint64_t* s_full = q_full + 1;         // [2] MMA -> softmax : S block complete in TMEM buffer b
+  uint64_t* p_ready = q_full + 3;        // [2] softmax -> MMA : P written over buffer b (4 warps arrive)
+  uint64_t* pv_done = q_full + 5;        // MMA -> softmax : one phase per P V product (O is quiescent after it)
+  uint64_t* o_full = q_full + 6;         // MMA -> softmax : the last P V retired, O complete
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(q_full + 7);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x, head = blockIdx.y, view = blockIdx.z;
   const int S = args.seq;
-  const int nb = (S + kBlockKV - 1) / kBlockKV;                 // KV blocks (5 for S = 577)
-  const int last_valid = S - (nb - 1) * kBlockKV;               // valid kv columns in the last block (65)
-  const int last_n = (last_valid + 15) & ~15;                   // MMA N / K extent of the last block (80)
+  const int nb = (S + kBlockKV - 1) / kBlockKV;                 // KV blocks (10 for S = 577)
+  const int last_valid = S - (nb - 1) * kBlockKV;               // valid kv columns in the last block (1)
+  const int last_n = (last_valid + 15) & ~15;                   // MMA N / K extent of the last block (16)
   const int row0 = view * S;                                    // first row of this view in qkv / out
   const int q_col = head * kHeadDim, k_col = args.hidden + q_col, v_col = 2 * args.hidden + q_col;
 
@@ -96,8 +113,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(q_full, 1);
-    mbar_init(s_full, 1);
-    mbar_init(sm_done, 4);
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(&p_ready[0], 4);
+    mbar_init(&p_ready[1], 4);
+    mbar_init(pv_done, 1);
     mbar_init(o_full, 1);
     fence_mbar_init();
   }
@@ -113,8 +133,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kTileBytes);
+      mbar_arrive_expect_tx(q_full, kQBytes);
       tma_load_2d(smem_q, &tmap_qkv, q_full, q_col, row0 + q_tile * kBlockQ);
+      tma_load_2d(smem_q + kTileBytes, &tmap_qkv, q_full, q_col, row0 + q_tile * kBlockQ + kBlockKV);
       int slot = 0;
       uint32_t phase = 0;
       auto load = [&](int col, int blk) {
@@ -123,10 +144,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
         tma_load_2d(smem_kv + slot * kTileBytes, &tmap_qkv, &full_bar[slot], col, row0 + blk * kBlockKV);
         if (++slot == kSlots) { slot = 0; phase ^= 1; }
       };
-      for (int j = 0; j < nb; ++j) load(k_col, j);  // pass 1: K only
-      for (int j = 0; j < nb; ++j) {                // pass 2: K_j then V_j
-        load(k_col, j);
+      // consumption order of the MMA warp: K0, K1, then (V_j, K_{j+2}) for j = 0..
+      load(k_col, 0);
+      if (nb > 1) load(k_col, 1);
+      for (int j = 0; j < nb; ++j) {
         load(v_col, j);
+        if (j + 2 < nb) load(k_col, j + 2);
       }
     }
   } else if (warp == 1) {
@@ -134,8 +157,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
     if (lane == 0) {
       int slot = 0;
       uint32_t phase = 0;
-      uint32_t sm_phase = 0;
-      const uint32_t s_tmem = tmem_base;          // S (fp32) and P (fp16, aliased from column 0)
       const uint32_t o_tmem = tmem_base + kOCol;
       const uint32_t q_addr = smem_u32(smem_q);
       mbar_wait(q_full, 0);
@@ -144,6 +165,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
       auto issue_s = [&](int j) {
         const int n = (j == nb - 1) ? last_n : kBlockKV;
         const uint32_t idesc = make_idesc_f16(kBlockQ, n, 0, 0);
+        const uint32_t s_tmem = tmem_base + (j & 1) * kBlockKV;
         mbar_wait(&full_bar[slot], phase);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(smem_kv + slot * kTileBytes);
@@ -154,118 +176,160 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
           umma_ss(s_tmem, a_desc, b_desc, idesc, k != 0);
         }
         tc_commit(&empty_bar[slot]);
-        tc_commit(s_full);
+        tc_commit(&s_full[j & 1]);
         if (++slot == kSlots) { slot = 0; phase ^= 1; }
       };
       auto issue_pv = [&](int j) {
-        const int kext = (j == nb - 1) ? last_n : kBlockKV;  // contraction extent = kv rows of this block
+        const int kext = (j == nb - 1) ? last_n : kBlockKV;              // contraction extent = kv rows of this block
         const uint32_t idesc = make_idesc_f16(kBlockQ, kHeadDim, 0, 1);  // B (= V) is MN-major
+        const uint32_t p_tmem = tmem_base + (j & 1) * kBlockKV;          // P aliases the S buffer, fp16 pairs
         mbar_wait(&full_bar[slot], phase);
         tc_fence_after();
         const uint32_t v_addr = smem_u32(smem_kv + slot * kTileBytes);
         for (int k = 0; k < kext / 16; ++k) {
           // V tile: row = kv index (128 B each, 64 halves of head_dim), 8-row groups 1024 B apart.
           const uint64_t b_desc = make_smem_desc(v_addr + k * 16 * 128, 1024, 1024, kLayoutSw128);
-          umma_ts(o_tmem, s_tmem + k * 8, b_desc, idesc, (j | k) != 0);
+          umma_ts(o_tmem, p_tmem + k * 8, b_desc, idesc, (j | k) != 0);
         }
         tc_commit(&empty_bar[slot]);
+        tc_commit(pv_done);
         if (++slot == kSlots) { slot = 0; phase ^= 1; }
       };
 
-      const int total = 2 * nb;
-      for (int b = 0; b < total; ++b) {
-        if (b > 0) {
-          mbar_wait(sm_done, sm_phase);
-          sm_phase ^= 1;
-          tc_fence_after();
-          if (b - 1 >= nb) issue_pv(b - 1 - nb);
-        }
-        issue_s(b < nb ? b : b - nb);
+      issue_s(0);
+      if (nb > 1) issue_s(1);
+      for (int j = 0; j < nb; ++j) {
+        mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        issue_pv(j);
+        if (j + 2 < nb) issue_s(j + 2);  // overwrites P_j only after P_j V_j (in-order tensor pipe)
       }
-      mbar_wait(sm_done, sm_phase);
-      tc_fence_after();
-      issue_pv(nb - 1);
       tc_commit(o_full);
     }
   } else {
     // ---------------------------------------------------------------- softmax warps
     const int q = warp & 3;
     const uint32_t lane_base = uint32_t(q * 32) << 16;
-    const uint32_t s_tmem = tmem_base + lane_base;
     const uint32_t o_tmem = tmem_base + lane_base + kOCol;
     const int q_row = q_tile * kBlockQ + q * 32 + lane;  // token index inside the view
-    uint32_t s_phase = 0;
     const float c = args.scale_log2;
 
-    // pass 1: row max
-    float m = -INFINITY;
-    for (int j = 0; j < nb; ++j) {
-      const int ncols = (j == nb - 1) ? last_n : kBlockKV;
-      const int nvalid = (j == nb - 1) ? last_valid : kBlockKV;
-      mbar_wait(s_full, s_phase);
-      s_phase ^= 1;
-      tc_fence_after();
-      for (int c0 = 0; c0 < ncols; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16_(s_tmem + c0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (c0 + i < nvalid) m = fmaxf(m, __uint_as_float(r[i]));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sm_done);
-    }
+    float m = -INFINITY;   // reference maximum currently used in the exponent (raw logit units)
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 
-    // pass 2: P = exp2(S*c - m*c), row sum, P -> TMEM (fp16 pairs)
-    const float mc = m * c;
-    float l = 0.f;
     for (int j = 0; j < nb; ++j) {
-      const int ncols = (j == nb - 1) ? last_n : kBlockKV;
-      const int nvalid = (j == nb - 1) ? last_valid : kBlockKV;
-      mbar_wait(s_full, s_phase);
-      s_phase ^= 1;
+      const uint32_t s_tmem = tmem_base + lane_base + (j & 1) * kBlockKV;
+      const bool tail = (j == nb - 1) && (last_valid < kBlockKV);
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      for (int c0 = 0; c0 < ncols; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16_(s_tmem + c0, r);
+
+      uint32_t r[kBlockKV];
+      float bm = -INFINITY;
+      if (!tail) {
+        tmem_ld32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        tmem_ld32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
         tmem_ld_wait();
-        uint32_t pk[8];
+        float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          float p0 = (c0 + i < nvalid) ? ex2(fmaf(__uint_as_float(r[i]), c, -mc)) : 0.f;
-          float p1 = (c0 + i + 1 < nvalid) ? ex2(fmaf(__uint_as_float(r[i + 1]), c, -mc)) : 0.f;
-          l += p0 + p1;
-          pk[i >> 1] = pack_half2(p0, p1);
+        for (int i = 0; i < kBlockKV; i += 4) {
+          b0 = fmaxf(b0, __uint_as_float(r[i]));
+          b1 = fmaxf(b1, __uint_as_float(r[i + 1]));
+          b2 = fmaxf(b2, __uint_as_float(r[i + 2]));
+          b3 = fmaxf(b3, __uint_as_float(r[i + 3]));
         }
-        tmem_st8_(s_tmem + (c0 >> 1), pk);  // P overwrites S columns already consumed by this thread
+        bm = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
+      } else {
+        for (int c0 = 0; c0 < last_n; c0 += 16) {   // sweep 1 of the ragged block: maximum over the valid columns
+          uint32_t t[16];
+          tmem_ld16_(s_tmem + c0, t);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < last_valid) bm = fmaxf(bm, __uint_as_float(t[i]));
+        }
+      }
+
+      // running maximum with lazy rescale
+      const float m_new = fmaxf(m, bm);
+      if (j == 0) {
+        m = m_new;
+      } else {
+        const bool need = (m_new - m) * c > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          // rare: raise m for every row of this warp and rescale its O rows and l.  O is quiescent once P_{j-1} V_{j-1}
+          // retired, and P_j V_j cannot be issued before this warp reports p_ready.
+          mbar_wait(pv_done, (j - 1) & 1);
+          tc_fence_after();
+          const float alpha = ex2((m - m_new) * c);
+          uint32_t o[32];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tmem_ld32(o_tmem + 32 * h, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32_(o_tmem + 32 * h, o);
+          }
+          tmem_st_wait();
+          l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
+          m = m_new;
+        }
+      }
+      const float mc = m * c;
+
+      if (!tail) {
+        uint32_t pk[kBlockKV / 2];
+#pragma unroll
+        for (int i = 0; i < kBlockKV; i += 4) {
+          const float p0 = ex2(fmaf(__uint_as_float(r[i]), c, -mc));
+          const float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), c, -mc));
+          const float p2 = ex2(fmaf(__uint_as_float(r[i + 2]), c, -mc));
+          const float p3 = ex2(fmaf(__uint_as_float(r[i + 3]), c, -mc));
+          l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+          pk[i >> 1] = pack_half2(p0, p1);
+          pk[(i >> 1) + 1] = pack_half2(p2, p3);
+        }
+        tmem_st32_(s_tmem, pk);  // P overwrites S columns already held in registers by this thread
+      } else {
+        for (int c0 = 0; c0 < last_n; c0 += 16) {   // sweep 2: reload the chunk (P of earlier chunks never reaches it)
+          uint32_t t[16], pk[8];
+          tmem_ld16_(s_tmem + c0, t);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float p0 = (c0 + i < last_valid) ? ex2(fmaf(__uint_as_float(t[i]), c, -mc)) : 0.f;
+            const float p1 = (c0 + i + 1 < last_valid) ? ex2(fmaf(__uint_as_float(t[i + 1]), c, -mc)) : 0.f;
+            l0 += p0; l1 += p1;
+            pk[i >> 1] = pack_half2(p0, p1);
+          }
+          tmem_st8_(s_tmem + (c0 >> 1), pk);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(sm_done);
+      if (lane == 0) mbar_arrive(&p_ready[j & 1]);
     }
 
     // epilogue: O / l -> fp16 -> global
     mbar_wait(o_full, 0);
     tc_fence_after();
-    const float inv_l = 1.0f / l;
+    const float inv_l = 1.0f / ((l0 + l1) + (l2 + l3));
     __half* orow = args.out + (size_t)(row0 + q_row) * args.hidden + q_col;
 #pragma unroll
     for (int c0 = 0; c0 < kHeadDim; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(o_tmem + c0, r);
+      uint32_t o[32];
+      tmem_ld32(o_tmem + c0, o);
       tmem_ld_wait();
       if (q_row < S) {
         uint4* o4 = reinterpret_cast<uint4*>(orow + c0);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 v;
-          v.x = pack_half2(__uint_as_float(r[8 * i + 0]) * inv_l, __uint_as_float(r[8 * i + 1]) * inv_l);
-          v.y = pack_half2(__uint_as_float(r[8 * i + 2]) * inv_l, __uint_as_float(r[8 * i + 3]) * inv_l);
-          v.z = pack_half2(__uint_as_float(r[8 * i + 4]) * inv_l, __uint_as_float(r[8 * i + 5]) * inv_l);
-          v.w = pack_half2(__uint_as_float(r[8 * i + 6]) * inv_l, __uint_as_float(r[8 * i + 7]) * inv_l);
+          v.x = pack_half2(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
+          v.y = pack_half2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
+          v.z = pack_half2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
+          v.w = pack_half2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
           o4[i] = v;
         }
       }

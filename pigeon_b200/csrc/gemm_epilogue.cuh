@@ -42,12 +42,27 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
   for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK) {
     const int col0 = tile_col0 + c0;
     if (col0 >= args.N) break;  // warp-uniform: the rest of this tile is past N
+    const bool in_n = (col0 + CHUNK <= args.N);
+    const bool fast = in_n && args.vec_ok;
+    const int sub = lane >> 3, c16 = lane & 7;
+    // residual prefetch: the 8 coalesced 16-byte pieces this lane will update, requested before the TMEM load so that
+    // their L2/HBM latency overlaps it (and is not serialised behind the stores, which may alias for the compiler)
+    float4 res[8];
+    if (EPI == EPI_F32_BIAS_RESID && fast) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int grow = warp_row0 + i * 4 + sub;
+        res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (grow < args.M)
+          res[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(args.out) +
+                                                    ((long)grow * args.ldo + col0) * kElt + c16 * 16);
+      }
+    }
     uint32_t r[CHUNK];
     __syncwarp();
 #pragma unroll
     for (int h = 0; h < CHUNK / 32; ++h) tmem_ld32(t_row + c0 + 32 * h, *reinterpret_cast<uint32_t(*)[32]>(&r[32 * h]));
     tmem_ld_wait();
-    const bool in_n = (col0 + CHUNK <= args.N);
     float v[CHUNK];
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) v[i] = __uint_as_float(r[i]);
@@ -69,7 +84,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
 #pragma unroll
       for (int i = 0; i < CHUNK; ++i) v[i] = quick_gelu(v[i]);
     }
-    if (in_n && args.vec_ok) {
+    if (fast) {
       // ---- stage this thread's row (128 bytes)
       uint4* srow = reinterpret_cast<uint4*>(stage + lane * kStagePitch);
 #pragma unroll
@@ -90,7 +105,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
       }
       __syncwarp();
       // ---- coalesced global phase
-      const int sub = lane >> 3, c16 = lane & 7;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + sub;
@@ -102,11 +116,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
             orow = (long)args.rowmap_mul * (grow / args.rowmap_div) + (grow % args.rowmap_div) + args.rowmap_add;
           uint8_t* gp = reinterpret_cast<uint8_t*>(args.out) + (orow * args.ldo + col0) * kElt + c16 * 16;
           if (EPI == EPI_F32_BIAS_RESID) {
-            const float4 res = *reinterpret_cast<const float4*>(gp);
-            val.x = __float_as_uint(__uint_as_float(val.x) + res.x);
-            val.y = __float_as_uint(__uint_as_float(val.y) + res.y);
-            val.z = __float_as_uint(__uint_as_float(val.z) + res.z);
-            val.w = __float_as_uint(__uint_as_float(val.w) + res.w);
+            val.x = __float_as_uint(__uint_as_float(val.x) + res[i].x);
+            val.y = __float_as_uint(__uint_as_float(val.y) + res[i].y);
+            val.z = __float_as_uint(__uint_as_float(val.z) + res[i].z);
+            val.w = __float_as_uint(__uint_as_float(val.w) + res[i].w);
           }
           *reinterpret_cast<uint4*>(gp) = val;
         }

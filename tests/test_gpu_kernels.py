@@ -97,6 +97,27 @@ def test_attention(cuda, n_views, seq, heads):
     assert torch.isfinite(out.float()).all()
 
 
+def test_attention_growing_logits_exercise_rescale(cuda):
+    """Key norms grow along the sequence so that later KV blocks raise the row maximum by far more than 2^8:
+    the lazy-rescale path (O and l rescaled in TMEM) must give the same answer as an exact softmax."""
+    from pigeon_b200 import ops
+    n_views, seq, heads = 2, 577, 2
+    g = torch.Generator(device="cpu").manual_seed(77)
+    hidden = heads * 64
+    x = torch.randn(n_views, seq, 3, heads, 64, generator=g)
+    ramp = (0.25 + 6.0 * torch.arange(seq) / seq).view(1, seq, 1, 1)
+    x[:, :, 1] *= ramp                                   # k
+    qkv = x.reshape(n_views * seq, 3 * hidden).half().to(cuda)
+    out = ops.attention_f16(qkv, n_views, seq, heads)
+    xf = qkv.float().view(n_views, seq, 3, heads, 64)
+    q, k, v = (xf[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    logits = q @ k.transpose(-1, -2) * 0.125
+    assert (logits.max(-1).values - logits[..., :64].max(-1).values).max() * 1.4427 > 16, "test must trigger rescales"
+    ref = (torch.softmax(logits, dim=-1) @ v).permute(0, 2, 1, 3).reshape(n_views * seq, hidden)
+    err = _rel(out.float(), ref)
+    assert torch.isfinite(out.float()).all() and err < 2e-3, err
+
+
 # ------------------------------------------------------------------------------------------------ head
 @pytest.mark.parametrize("B,V,D,C,k", [(8, 4, 1024, 1000, 50), (3, 1, 1024, 2076, 5), (256, 4, 1024, 1000, 50),
                                        (5, 4, 256, 331, 7)])
