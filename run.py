@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Entry points of the hot path with the reference's CLI (run.py:21-93): `embed` and `evaluate`.
+
+    python run.py evaluate HEAD.model -l DATASET_DIR [-b BASE.model] [--yfcc]
+    python run.py embed CLIP.model -l DATASET_DIR
+
+`pretrain` / `finetune` (training) are outside the B200 inference path and raise NotImplementedError, like the
+reference does for its unsupported resume modes (run.py:166-173,189).  Datasets are HF `DatasetDict`s on disk, as in the
+reference (run.py:143-162); none are shipped with either repository.
+"""
+import argparse
+import logging
+
+import torch
+
+from pigeon_b200 import CLIPEmbedding, ProtoRefiner, SuperGuessr
+from pigeon_b200 import config as cfg
+from pigeon_b200.loops import embed_images, evaluate_model
+
+logger = logging.getLogger('run')
+
+
+def evaluate(model: str, dataset, yfcc: bool, landmarks: bool = False, base_model: str = None, heading: bool = False,
+             refine: bool = True, metrics=None):
+    """reference evaluation/evaluate.py:10-86."""
+    embed_model = None
+    if base_model is not None:
+        from transformers import CLIPVisionModel
+        embed_model = CLIPVisionModel.from_pretrained(cfg.CLIP_MODEL)                      # :36
+        if base_model != cfg.CLIP_MODEL:
+            from pigeon_b200 import load_state_dict
+            load_state_dict(embed_model, torch.load(base_model, map_location='cpu'))       # :37-40
+    full_model = SuperGuessr(embed_model, panorama=True, hierarchical=False, multi_task=False, heading=heading,
+                             freeze_base=True, yfcc=yfcc, num_candidates=50)               # :42-44
+    full_model.to('cuda')
+    full_model.load_state(model)                                                           # :45-46
+    refiner = None
+    if refine:                                                                             # :50-80
+        proto_model_path = cfg.PROTO_MODEL_YFCC_PATH if yfcc else cfg.PROTO_MODEL_PATH
+        proto_path = cfg.PROTO_PATH_YFCC if yfcc else cfg.PROTO_PATH
+        dataset_path = cfg.DATASET_PATH_YFCC if yfcc else cfg.DATASET_PATH
+        protos = None
+        try:
+            protos = torch.load(proto_model_path, map_location='cpu', weights_only=False).protos
+        except FileNotFoundError:
+            pass
+        if protos is None:
+            refiner = ProtoRefiner(20, False, 10000, proto_path=proto_path, dataset_path=dataset_path, temperature=1)
+            torch.save(refiner, proto_model_path)
+        else:
+            refiner = ProtoRefiner(40, False, 100000, proto_path=proto_path, dataset_path=dataset_path, protos=protos,
+                                   temperature=0.6, verbose=False)
+        print(refiner)
+    return evaluate_model(full_model, dataset, metrics, None, refiner)
+
+
+def main():
+    p = argparse.ArgumentParser(description='PIGEON hot path on B200 (embed / evaluate)')
+    p.add_argument('mode', choices=['pretrain', 'finetune', 'embed', 'evaluate'])
+    p.add_argument('name', help='model / prediction-head path')
+    p.add_argument('-l', '--load', default=None, help='comma-separated HF dataset directories')
+    p.add_argument('-b', '--base', default=None, help='base (vision tower) checkpoint')
+    p.add_argument('-r', '--refine', action='store_true', default=True)
+    p.add_argument('--yfcc', action='store_true')
+    p.add_argument('--landmarks', action='store_true')
+    p.add_argument('--heading', action='store_true')
+    args = p.parse_args()
+    if args.mode in ('pretrain', 'finetune'):
+        raise NotImplementedError(f'"{args.mode}" (training) is outside the B200 inference hot path')
+    if args.load is None:
+        raise NotImplementedError('A dataset must be given with -l (the reference regenerates it from un-shipped raw data).')
+    from datasets import DatasetDict
+    dataset = DatasetDict.load_from_disk(args.load.split(',')[0])
+    if args.mode == 'embed':
+        model = CLIPEmbedding(args.name, load_checkpoint=True, panorama=not args.yfcc)    # run.py:126-129
+        embed_images(model, dataset)
+    else:
+        split = dataset['test'] if 'test' in dataset else dataset[list(dataset.keys())[-1]]
+        print(evaluate(args.name, split.with_format('torch'), args.yfcc, args.landmarks, base_model=args.base,
+                       heading=args.heading, refine=args.refine))
+
+
+if __name__ == '__main__':
+    torch.multiprocessing.set_start_method('spawn', force=True)                           # run.py:192
+    main()

@@ -142,3 +142,43 @@ def test_protorefiner_matches_reference(cuda, name):
     assert np.array_equal(ll.cpu().numpy(), z["preds_LLH_noprob"])
     with pytest.raises(AssertionError):                                  # proto_refiner.py:135-137
         ProtoRefiner(topk=99, protos=bank)(torch.tensor(z["emb"]), candidate_probs=None, **args)
+
+
+def test_evaluate_model_loop_matches_direct_calls(cuda):
+    """loops.evaluate_model (mirror of training/train_eval_loop.py:35-161) == per-batch direct calls."""
+    from pigeon_b200 import ProtoRefiner, SuperGuessr
+    from pigeon_b200.loops import evaluate_model
+    z, meta = load("refiner_count1")
+    zh, mh = load("head")
+    bank = {k[5:]: z[k] for k in z.files if k.startswith("bank_")}
+    D, C = bank["proto_emb"].shape[1], int(bank["cell_off"].shape[0]) - 1
+    g = torch.Generator().manual_seed(5)
+    n = 37
+    emb = torch.randn(n, 4, D, generator=g) * 0.3
+    labels = torch.rand(n, 2, generator=g, dtype=torch.float64) * 90
+    labels_clf = torch.randint(0, C, (n,), generator=g)
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return n
+
+        def __getitem__(self, i):
+            if isinstance(i, str):
+                return {"labels": labels.numpy(), "labels_clf": labels_clf.numpy()}[i]
+            return dict(embedding=emb[i], labels=labels[i], labels_clf=labels_clf[i])
+
+    cells = np.stack([np.linspace(-170, 170, C), np.linspace(-80, 80, C)], 1)
+    sg = SuperGuessr(None, panorama=True, num_candidates=10, embed_dim=D, geocells=cells).to(cuda).eval()
+    ref = ProtoRefiner(topk=5, max_refinement=1e6, temperature=1.6, protos=bank).eval()
+
+    class Args:
+        per_device_eval_batch_size = 16
+
+    res = evaluate_model(sg, DS(), None, Args(), ref)
+    out = sg(embedding=emb, labels=labels, labels_clf=labels_clf)
+    _, ll, cell = ref(out.embedding, initial_preds=out.preds_LLH, candidate_cells=out.top5_geocells.indices,
+                      candidate_probs=out.top5_geocells.values)
+    assert np.array_equal(res["preds"], ll.cpu().numpy())
+    assert np.array_equal(res["preds_geocell"], out.preds_geocell.cpu().numpy())
+    assert np.array_equal(res["top_geocells"], out.top5_geocells.indices.cpu().numpy())
+    np.testing.assert_allclose(res["loss"], out.loss.item(), rtol=1e-5)
