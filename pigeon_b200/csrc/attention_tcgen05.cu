@@ -9,8 +9,10 @@
 // Input  qkv : fp16 [n_views * S, 3 * hidden]   row = (view, token); cols = [q | k | v], head-major inside
 // Output out : fp16 [n_views * S, hidden]
 //
-// One CTA per (q-tile of 128 rows, head, view); 192 threads; two CTAs co-reside per SM (64 KB smem, 256 TMEM columns).
-//   warp 0     TMA producer: Q tile once, then K/V tiles (64 x 64 halves, 128B swizzle) through a 6-slot ring
+// Persistent: 2 CTAs per SM (80 KB smem, 256 TMEM columns each), each looping over work items
+// (q-tile of 128 rows, head, view) with every pipeline (TMA ring, S/P buffers, O buffers, Q buffers) running ACROSS
+// tile boundaries, so the next tile's loads and first QK^T products overlap the current tile's tail.  192 threads:
+//   warp 0     TMA producer: Q tiles (double-buffered), K/V tiles (64 x 64 halves, 128B swizzle) through a 6-slot ring
 //   warp 1     TMEM allocator + MMA issuer (tcgen05.mma cta_group::1, M = 128)
 //   warps 2-5  softmax, one TMEM lane (= one query row) per thread
 //
@@ -36,12 +38,13 @@ constexpr int kSlots = 6;
 constexpr int kQBytes = kBlockQ * kHeadDim * 2;       // 16 KB
 constexpr int kTileBytes = kBlockKV * kHeadDim * 2;   // 8 KB
 constexpr int kThreads = 192;
-constexpr int kTmemCols = 256;                        // S0 [0,64)  S1 [64,128)  O [128,192)
+constexpr int kTmemCols = 256;                        // S0 [0,64)  S1 [64,128)  O0 [128,192)  O1 [192,256)
 constexpr int kOCol = 128;
-constexpr int kSmemBytes = kQBytes + kSlots * kTileBytes + 1024 + 256;
+constexpr int kSmemBytes = 2 * kQBytes + kSlots * kTileBytes + 1024 + 256;
 constexpr float kRescaleThreshold = 8.0f;             // log2 domain
 
 struct AttnArgs {
+  int n_views, heads, q_tiles;
   int seq;      // tokens per view (577)
   int hidden;   // heads * 64
   __half* out;  // [n_views*seq, hidden]
@@ -80,31 +83,45 @@ __device__ __forceinline__ void tmem_st32_(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
+// Work item `w` -> (view, head, q_tile); q_tile fastest so that co-scheduled CTAs share the K/V of one (view, head).
+struct Tile {
+  int view, head, qt;
+};
+__device__ __forceinline__ Tile decode_tile(int w, const AttnArgs& a) {
+  Tile t;
+  t.qt = w % a.q_tiles;
+  const int vh = w / a.q_tiles;
+  t.head = vh % a.heads;
+  t.view = vh / a.heads;
+  return t;
+}
+
 __global__ void __launch_bounds__(kThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_q = smem;
-  uint8_t* smem_kv = smem + kQBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kQBytes + kSlots * kTileBytes);
+  uint8_t* smem_q = smem;                       // 2 x 16 KB
+  uint8_t* smem_kv = smem + 2 * kQBytes;        // kSlots x 8 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kQBytes + kSlots * kTileBytes);
   uint64_t* full_bar = bars;             // [kSlots]  TMA -> MMA
   uint64_t* empty_bar = bars + kSlots;   // [kSlots]  MMA -> TMA
-  uint64_t* q_full = bars + 2 * kSlots;
-  uint64_t* s_full = q_full + 1;         // [2] MMA -> softmax : S block complete in TMEM buffer b
-  uint64_t* p_ready = q_full + 3;        // [2] softmax -> MMA : P written over buffer b (4 warps arrive)
-  uint64_t* pv_done = q_full + 5;        // MMA -> softmax : one phase per P V product (O is quiescent after it)
-  uint64_t* o_full = q_full + 6;         // MMA -> softmax : the last P V retired, O complete
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(q_full + 7);
+  uint64_t* q_full = bars + 2 * kSlots;  // [2] TMA -> MMA : Q tile landed
+  uint64_t* q_empty = q_full + 2;        // [2] MMA -> TMA : every QK^T of the tile retired
+  uint64_t* s_full = q_full + 4;         // [2] MMA -> softmax : S block complete in TMEM buffer b
+  uint64_t* p_ready = q_full + 6;        // [2] softmax -> MMA : P written over buffer b (4 warps arrive)
+  uint64_t* pv_done = q_full + 8;        // MMA -> softmax : one phase per P V product (O is quiescent after it)
+  uint64_t* o_full = q_full + 9;         // [2] MMA -> softmax : last P V of the tile retired, O buffer complete
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(q_full + 11);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x, head = blockIdx.y, view = blockIdx.z;
   const int S = args.seq;
-  const int nb = (S + kBlockKV - 1) / kBlockKV;                 // KV blocks (10 for S = 577)
+  const int nb = (S + kBlockKV - 1) / kBlockKV;                 // KV blocks per tile (10 for S = 577)
   const int last_valid = S - (nb - 1) * kBlockKV;               // valid kv columns in the last block (1)
   const int last_n = (last_valid + 15) & ~15;                   // MMA N / K extent of the last block (16)
-  const int row0 = view * S;                                    // first row of this view in qkv / out
-  const int q_col = head * kHeadDim, k_col = args.hidden + q_col, v_col = 2 * args.hidden + q_col;
+  const int total = args.n_views * args.heads * args.q_tiles;
+  const int my_tiles = (total > (int)blockIdx.x) ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int G = my_tiles * nb;                                  // KV blocks this CTA will process, globally numbered
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
@@ -112,13 +129,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(q_full, 1);
-    mbar_init(&s_full[0], 1);
-    mbar_init(&s_full[1], 1);
-    mbar_init(&p_ready[0], 4);
-    mbar_init(&p_ready[1], 4);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&q_full[b], 1);
+      mbar_init(&q_empty[b], 1);
+      mbar_init(&s_full[b], 1);
+      mbar_init(&p_ready[b], 4);
+      mbar_init(&o_full[b], 1);
+    }
     mbar_init(pv_done, 1);
-    mbar_init(o_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -132,40 +150,52 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kQBytes);
-      tma_load_2d(smem_q, &tmap_qkv, q_full, q_col, row0 + q_tile * kBlockQ);
-      tma_load_2d(smem_q + kTileBytes, &tmap_qkv, q_full, q_col, row0 + q_tile * kBlockQ + kBlockKV);
+    // Load order = consumption order of the MMA warp over the GLOBAL block index g = tile_i * nb + j:
+    //   K(0), K(1), then for g = 0, 1, ...: V(g), K(g+2);  the Q tile of a tile goes right before its K(., 0).
+    if (lane == 0 && G > 0) {
       int slot = 0;
       uint32_t phase = 0;
-      auto load = [&](int col, int blk) {
+      auto load_kv = [&](int g, bool is_v) {
+        const int ti = g / nb, j = g - ti * nb;
+        const Tile t = decode_tile(blockIdx.x + ti * gridDim.x, args);
+        const int row0 = t.view * S;
+        const int q_col = t.head * kHeadDim;
+        if (!is_v && j == 0) {  // first block of a tile: its Q tile (two 64-row boxes) into Q buffer ti & 1
+          mbar_wait(&q_empty[ti & 1], ((ti >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&q_full[ti & 1], kQBytes);
+          uint8_t* qb = smem_q + (ti & 1) * kQBytes;
+          tma_load_2d(qb, &tmap_qkv, &q_full[ti & 1], q_col, row0 + t.qt * kBlockQ);
+          tma_load_2d(qb + kTileBytes, &tmap_qkv, &q_full[ti & 1], q_col, row0 + t.qt * kBlockQ + kBlockKV);
+        }
         mbar_wait(&empty_bar[slot], phase ^ 1);
         mbar_arrive_expect_tx(&full_bar[slot], kTileBytes);
-        tma_load_2d(smem_kv + slot * kTileBytes, &tmap_qkv, &full_bar[slot], col, row0 + blk * kBlockKV);
+        tma_load_2d(smem_kv + slot * kTileBytes, &tmap_qkv, &full_bar[slot],
+                    (is_v ? 2 * args.hidden : args.hidden) + q_col, row0 + j * kBlockKV);
         if (++slot == kSlots) { slot = 0; phase ^= 1; }
       };
-      // consumption order of the MMA warp: K0, K1, then (V_j, K_{j+2}) for j = 0..
-      load(k_col, 0);
-      if (nb > 1) load(k_col, 1);
-      for (int j = 0; j < nb; ++j) {
-        load(v_col, j);
-        if (j + 2 < nb) load(k_col, j + 2);
+      load_kv(0, false);
+      if (G > 1) load_kv(1, false);
+      for (int g = 0; g < G; ++g) {
+        load_kv(g, true);
+        if (g + 2 < G) load_kv(g + 2, false);
       }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && G > 0) {
       int slot = 0;
       uint32_t phase = 0;
-      const uint32_t o_tmem = tmem_base + kOCol;
-      const uint32_t q_addr = smem_u32(smem_q);
-      mbar_wait(q_full, 0);
-      tc_fence_after();
 
-      auto issue_s = [&](int j) {
+      auto issue_s = [&](int g) {
+        const int ti = g / nb, j = g - ti * nb;
         const int n = (j == nb - 1) ? last_n : kBlockKV;
         const uint32_t idesc = make_idesc_f16(kBlockQ, n, 0, 0);
-        const uint32_t s_tmem = tmem_base + (j & 1) * kBlockKV;
+        const uint32_t s_tmem = tmem_base + (g & 1) * kBlockKV;
+        if (j == 0) {
+          mbar_wait(&q_full[ti & 1], (ti >> 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t q_addr = smem_u32(smem_q + (ti & 1) * kQBytes);
         mbar_wait(&full_bar[slot], phase);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(smem_kv + slot * kTileBytes);
@@ -176,13 +206,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
           umma_ss(s_tmem, a_desc, b_desc, idesc, k != 0);
         }
         tc_commit(&empty_bar[slot]);
-        tc_commit(&s_full[j & 1]);
+        tc_commit(&s_full[g & 1]);
+        if (j == nb - 1) tc_commit(&q_empty[ti & 1]);  // the tile's last read of its Q buffer
         if (++slot == kSlots) { slot = 0; phase ^= 1; }
       };
-      auto issue_pv = [&](int j) {
+      auto issue_pv = [&](int g) {
+        const int ti = g / nb, j = g - ti * nb;
         const int kext = (j == nb - 1) ? last_n : kBlockKV;              // contraction extent = kv rows of this block
         const uint32_t idesc = make_idesc_f16(kBlockQ, kHeadDim, 0, 1);  // B (= V) is MN-major
-        const uint32_t p_tmem = tmem_base + (j & 1) * kBlockKV;          // P aliases the S buffer, fp16 pairs
+        const uint32_t p_tmem = tmem_base + (g & 1) * kBlockKV;          // P aliases the S buffer, fp16 pairs
+        const uint32_t o_tmem = tmem_base + kOCol + (ti & 1) * kHeadDim;
         mbar_wait(&full_bar[slot], phase);
         tc_fence_after();
         const uint32_t v_addr = smem_u32(smem_kv + slot * kTileBytes);
@@ -193,147 +226,156 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
         }
         tc_commit(&empty_bar[slot]);
         tc_commit(pv_done);
+        if (j == nb - 1) tc_commit(&o_full[ti & 1]);
         if (++slot == kSlots) { slot = 0; phase ^= 1; }
       };
 
       issue_s(0);
-      if (nb > 1) issue_s(1);
-      for (int j = 0; j < nb; ++j) {
-        mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
+      if (G > 1) issue_s(1);
+      for (int g = 0; g < G; ++g) {
+        mbar_wait(&p_ready[g & 1], (g >> 1) & 1);
         tc_fence_after();
-        issue_pv(j);
-        if (j + 2 < nb) issue_s(j + 2);  // overwrites P_j only after P_j V_j (in-order tensor pipe)
+        issue_pv(g);
+        if (g + 2 < G) issue_s(g + 2);  // overwrites P_g only after P_g V_g (in-order tensor pipe)
       }
-      tc_commit(o_full);
     }
   } else {
     // ---------------------------------------------------------------- softmax warps
     const int q = warp & 3;
     const uint32_t lane_base = uint32_t(q * 32) << 16;
-    const uint32_t o_tmem = tmem_base + lane_base + kOCol;
-    const int q_row = q_tile * kBlockQ + q * 32 + lane;  // token index inside the view
     const float c = args.scale_log2;
 
-    float m = -INFINITY;   // reference maximum currently used in the exponent (raw logit units)
-    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const Tile t = decode_tile(blockIdx.x + ti * gridDim.x, args);
+      const int row0 = t.view * S;
+      const int q_row = t.qt * kBlockQ + q * 32 + lane;  // token index inside the view
+      const uint32_t o_tmem = tmem_base + lane_base + kOCol + (ti & 1) * kHeadDim;
 
-    for (int j = 0; j < nb; ++j) {
-      const uint32_t s_tmem = tmem_base + lane_base + (j & 1) * kBlockKV;
-      const bool tail = (j == nb - 1) && (last_valid < kBlockKV);
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
+      float m = -INFINITY;   // reference maximum currently used in the exponent (raw logit units)
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 
-      uint32_t r[kBlockKV];
-      float bm = -INFINITY;
-      if (!tail) {
-        tmem_ld32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-        tmem_ld32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-        tmem_ld_wait();
-        float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < kBlockKV; i += 4) {
-          b0 = fmaxf(b0, __uint_as_float(r[i]));
-          b1 = fmaxf(b1, __uint_as_float(r[i + 1]));
-          b2 = fmaxf(b2, __uint_as_float(r[i + 2]));
-          b3 = fmaxf(b3, __uint_as_float(r[i + 3]));
-        }
-        bm = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
-      } else {
-        for (int c0 = 0; c0 < last_n; c0 += 16) {   // sweep 1 of the ragged block: maximum over the valid columns
-          uint32_t t[16];
-          tmem_ld16_(s_tmem + c0, t);
+      for (int j = 0; j < nb; ++j) {
+        const int g = ti * nb + j;
+        const uint32_t s_tmem = tmem_base + lane_base + (g & 1) * kBlockKV;
+        const bool tail = (j == nb - 1) && (last_valid < kBlockKV);
+        mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+        tc_fence_after();
+
+        uint32_t r[kBlockKV];
+        float bm = -INFINITY;
+        if (!tail) {
+          tmem_ld32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+          tmem_ld32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
           tmem_ld_wait();
+          float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c0 + i < last_valid) bm = fmaxf(bm, __uint_as_float(t[i]));
-        }
-      }
-
-      // running maximum with lazy rescale
-      const float m_new = fmaxf(m, bm);
-      if (j == 0) {
-        m = m_new;
-      } else {
-        const bool need = (m_new - m) * c > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) {
-          // rare: raise m for every row of this warp and rescale its O rows and l.  O is quiescent once P_{j-1} V_{j-1}
-          // retired, and P_j V_j cannot be issued before this warp reports p_ready.
-          mbar_wait(pv_done, (j - 1) & 1);
-          tc_fence_after();
-          const float alpha = ex2((m - m_new) * c);
-          uint32_t o[32];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            tmem_ld32(o_tmem + 32 * h, o);
+          for (int i = 0; i < kBlockKV; i += 4) {
+            b0 = fmaxf(b0, __uint_as_float(r[i]));
+            b1 = fmaxf(b1, __uint_as_float(r[i + 1]));
+            b2 = fmaxf(b2, __uint_as_float(r[i + 2]));
+            b3 = fmaxf(b3, __uint_as_float(r[i + 3]));
+          }
+          bm = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
+        } else {
+          for (int c0 = 0; c0 < last_n; c0 += 16) {   // sweep 1 of the ragged block: maximum over the valid columns
+            uint32_t tt[16];
+            tmem_ld16_(s_tmem + c0, tt);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32_(o_tmem + 32 * h, o);
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < last_valid) bm = fmaxf(bm, __uint_as_float(tt[i]));
           }
-          tmem_st_wait();
-          l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
+        }
+
+        // running maximum with lazy rescale
+        const float m_new = fmaxf(m, bm);
+        if (j == 0) {
           m = m_new;
-        }
-      }
-      const float mc = m * c;
-
-      if (!tail) {
-        uint32_t pk[kBlockKV / 2];
+        } else {
+          const bool need = (m_new - m) * c > kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) {
+            // rare: raise m for every row of this warp and rescale its O rows and l.  O is quiescent once
+            // P_{g-1} V_{g-1} retired (S_g complete => every product before g-1 retired, so the parity wait below
+            // cannot alias an older phase), and P_g V_g cannot be issued before this warp reports p_ready.
+            mbar_wait(pv_done, (g - 1) & 1);
+            tc_fence_after();
+            const float alpha = ex2((m - m_new) * c);
+            uint32_t o[32];
 #pragma unroll
-        for (int i = 0; i < kBlockKV; i += 4) {
-          const float p0 = ex2(fmaf(__uint_as_float(r[i]), c, -mc));
-          const float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), c, -mc));
-          const float p2 = ex2(fmaf(__uint_as_float(r[i + 2]), c, -mc));
-          const float p3 = ex2(fmaf(__uint_as_float(r[i + 3]), c, -mc));
-          l0 += p0; l1 += p1; l2 += p2; l3 += p3;
-          pk[i >> 1] = pack_half2(p0, p1);
-          pk[(i >> 1) + 1] = pack_half2(p2, p3);
-        }
-        tmem_st32_(s_tmem, pk);  // P overwrites S columns already held in registers by this thread
-      } else {
-        for (int c0 = 0; c0 < last_n; c0 += 16) {   // sweep 2: reload the chunk (P of earlier chunks never reaches it)
-          uint32_t t[16], pk[8];
-          tmem_ld16_(s_tmem + c0, t);
-          tmem_ld_wait();
+            for (int h = 0; h < 2; ++h) {
+              tmem_ld32(o_tmem + 32 * h, o);
+              tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const float p0 = (c0 + i < last_valid) ? ex2(fmaf(__uint_as_float(t[i]), c, -mc)) : 0.f;
-            const float p1 = (c0 + i + 1 < last_valid) ? ex2(fmaf(__uint_as_float(t[i + 1]), c, -mc)) : 0.f;
-            l0 += p0; l1 += p1;
-            pk[i >> 1] = pack_half2(p0, p1);
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32_(o_tmem + 32 * h, o);
+            }
+            tmem_st_wait();
+            l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
+            m = m_new;
           }
-          tmem_st8_(s_tmem + (c0 >> 1), pk);
         }
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[j & 1]);
-    }
+        const float mc = m * c;
 
-    // epilogue: O / l -> fp16 -> global
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    const float inv_l = 1.0f / ((l0 + l1) + (l2 + l3));
-    __half* orow = args.out + (size_t)(row0 + q_row) * args.hidden + q_col;
+        if (!tail) {
+          uint32_t pk[kBlockKV / 2];
 #pragma unroll
-    for (int c0 = 0; c0 < kHeadDim; c0 += 32) {
-      uint32_t o[32];
-      tmem_ld32(o_tmem + c0, o);
-      tmem_ld_wait();
-      if (q_row < S) {
-        uint4* o4 = reinterpret_cast<uint4*>(orow + c0);
+          for (int i = 0; i < kBlockKV; i += 4) {
+            const float p0 = ex2(fmaf(__uint_as_float(r[i]), c, -mc));
+            const float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), c, -mc));
+            const float p2 = ex2(fmaf(__uint_as_float(r[i + 2]), c, -mc));
+            const float p3 = ex2(fmaf(__uint_as_float(r[i + 3]), c, -mc));
+            l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+            pk[i >> 1] = pack_half2(p0, p1);
+            pk[(i >> 1) + 1] = pack_half2(p2, p3);
+          }
+          tmem_st32_(s_tmem, pk);  // P overwrites S columns already held in registers by this thread
+        } else {
+          for (int c0 = 0; c0 < last_n; c0 += 16) {   // sweep 2: reload the chunk (P of earlier chunks never reaches it)
+            uint32_t tt[16], pk[8];
+            tmem_ld16_(s_tmem + c0, tt);
+            tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 v;
-          v.x = pack_half2(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
-          v.y = pack_half2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
-          v.z = pack_half2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
-          v.w = pack_half2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
-          o4[i] = v;
+            for (int i = 0; i < 16; i += 2) {
+              const float p0 = (c0 + i < last_valid) ? ex2(fmaf(__uint_as_float(tt[i]), c, -mc)) : 0.f;
+              const float p1 = (c0 + i + 1 < last_valid) ? ex2(fmaf(__uint_as_float(tt[i + 1]), c, -mc)) : 0.f;
+              l0 += p0; l1 += p1;
+              pk[i >> 1] = pack_half2(p0, p1);
+            }
+            tmem_st8_(s_tmem + (c0 >> 1), pk);
+          }
         }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[g & 1]);
       }
-      __syncwarp();
+
+      // tile epilogue: O / l -> fp16 -> global.  The O buffer of tile ti is only rewritten by tile ti + 2, whose
+      // first P V needs this warp's p_ready, i.e. comes after this read.
+      mbar_wait(&o_full[ti & 1], (ti >> 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.0f / ((l0 + l1) + (l2 + l3));
+      __half* orow = args.out + (size_t)(row0 + q_row) * args.hidden + t.head * kHeadDim;
+#pragma unroll
+      for (int c0 = 0; c0 < kHeadDim; c0 += 32) {
+        uint32_t o[32];
+        tmem_ld32(o_tmem + c0, o);
+        tmem_ld_wait();
+        if (q_row < S) {
+          uint4* o4 = reinterpret_cast<uint4*>(orow + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 v;
+            v.x = pack_half2(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
+            v.y = pack_half2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
+            v.z = pack_half2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
+            v.w = pack_half2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
+            o4[i] = v;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();  // order this tile's TMEM reads before the barrier arrivals of the next tile
     }
   }
 
@@ -359,13 +401,21 @@ int attention_f16(const void* qkv, void* out, int n_views, int seq, int heads, c
     attr_set = true;
   }
   AttnArgs a;
+  a.n_views = n_views;
+  a.heads = heads;
+  a.q_tiles = (seq + kBlockQ - 1) / kBlockQ;
   a.seq = seq;
   a.hidden = hidden;
   a.out = reinterpret_cast<__half*>(out);
   a.scale_log2 = 0.125f * 1.4426950408889634f;
-  dim3 grid((seq + kBlockQ - 1) / kBlockQ, heads, n_views);
+  const long total = (long)n_views * heads * a.q_tiles;
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long grid = 2L * (sms > 0 ? sms : 148);   // persistent: two co-resident CTAs per SM
+  if (grid > total) grid = total;
   ProfScope prof("attention", stream);
-  attention_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tm, a);
+  attention_kernel<<<(unsigned)grid, kThreads, kSmemBytes, stream>>>(tm, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_last_error("attention launch: %s", cudaGetErrorString(e)); return 1; }
   return 0;

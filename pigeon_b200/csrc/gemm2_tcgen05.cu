@@ -9,7 +9,8 @@
 //   warp 0      TMA producer (both CTAs; completion bytes land on the LEADER's full barrier)
 //   warp 1      MMA issuer (leader CTA only); tcgen05.commit multicasts to both CTAs' barriers
 //   warp 2      TMEM allocator (both CTAs, cta_group::2)
-//   warps 4..7  epilogue on the CTA's own 128 x 256 accumulator half (gemm_epilogue.cuh)
+//   warps 4..11 epilogue on the CTA's own 128 x 256 accumulator half: two warps per TMEM lane quarter, each taking
+//               128 of the 256 columns (gemm_epilogue.cuh)
 #include "gemm.h"
 #include "gemm_epilogue.cuh"
 #include "prof.h"
@@ -25,14 +26,15 @@ constexpr int BLOCK_N = 256;
 constexpr int BLOCK_N_CTA = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int kNumThreads = 256;
+constexpr int kNumThreads = 384;   // 4 role warps + 8 epilogue warps
+constexpr int kNumEpiWarps = 8;
 constexpr int kEpiWarp0 = 4;
 constexpr int kStages = 6;
 constexpr int kABytes = BLOCK_M_CTA * BLOCK_K * 2;  // 16 KB
 constexpr int kBBytes = BLOCK_N_CTA * BLOCK_K * 2;  // 16 KB
 constexpr int kStageBytes = kABytes + kBBytes;      // per CTA
 constexpr int kTmemCols = 512;                      // two 256-column accumulator stages
-constexpr int kSmemBytes = kStages * kStageBytes + 4 * kStageWarpBytes + 1024 + 256;
+constexpr int kSmemBytes = kStages * kStageBytes + kNumEpiWarps * kStageWarpBytes + 1024 + 256;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -100,7 +102,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
   uint8_t* smem_stage = smem + kStages * kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + 4 * kStageWarpBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + kNumEpiWarps * kStageWarpBytes);
   uint64_t* full_bar = bars;                       // leader's copy is the live one
   uint64_t* empty_bar = bars + kStages;            // per CTA
   uint64_t* tmem_full_bar = bars + 2 * kStages;    // per CTA
@@ -129,7 +131,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);   // multicast tcgen05.commit
-      mbar_init(&tmem_empty_bar[s], 8);  // 4 epilogue warps x 2 CTAs
+      mbar_init(&tmem_empty_bar[s], 2 * kNumEpiWarps);  // 8 epilogue warps x 2 CTAs
     }
     fence_mbar_init();
   }
@@ -200,8 +202,10 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N;
-      epilogue_tile<BLOCK_N, EPI>(args, t_row, stage_buf, m_blk * 2 * BLOCK_M_CTA + rank * BLOCK_M_CTA + q * 32,
-                                  n_blk * BLOCK_N, lane);
+      // warps 4-7 take tile columns [0,128), warps 8-11 take [128,256) of the same lane quarters
+      const int c_begin = (warp - kEpiWarp0) >= 4 ? BLOCK_N / 2 : 0;
+      epilogue_tile<EPI>(args, t_row, stage_buf, m_blk * 2 * BLOCK_M_CTA + rank * BLOCK_M_CTA + q * 32, n_blk * BLOCK_N,
+                         c_begin, c_begin + BLOCK_N / 2, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&tmem_empty_bar[acc]), 0));

@@ -6,8 +6,7 @@
 
 namespace pg {
 
-constexpr int kStagePitch = 144;                    // 128 B row + 16 B pad
-constexpr int kStageWarpBytes = 32 * kStagePitch;   // 4608 B per epilogue warp
+constexpr int kStageWarpBytes = 32 * 128;   // per epilogue warp: 32 rows x 128 B, 16-byte pieces XOR-swizzled by (row & 7)
 
 struct GemmArgs {
   int M, N, K;
@@ -26,37 +25,55 @@ __device__ __forceinline__ float quick_gelu(float v) {
   return __fdividef(v, 1.0f + e);
 }
 
-// One epilogue warp's share of one output tile: rows [warp_row0, warp_row0 + 32), columns [tile_col0, tile_col0 + BLOCK_N).
+// One epilogue warp's share of one output tile: rows [warp_row0, warp_row0 + 32), tile columns [c_begin, c_end).
 //   t_row  : TMEM address of this warp's lane quarter at the accumulator stage's first column
 //   stage  : this warp's private staging buffer (kStageWarpBytes)
 // Per chunk of CHUNK columns (128 bytes of output per row): TMEM -> registers (thread = row) -> bias / activation ->
-// smem staging (32 rows x 128 B, 144 B pitch: conflict-free both ways) -> coalesced global phase in which 8 lanes cover
-// one 128-byte row segment (4 rows per instruction).
-template <int BLOCK_N, int EPI>
+// smem staging (32 rows x 128 B, pieces swizzled: conflict-free both ways) -> coalesced global phase in which 8 lanes
+// cover one 128-byte row segment (4 rows per instruction).  For the residual epilogue the 16-byte pieces a lane will
+// update are fetched ONE CHUNK AHEAD so that their HBM latency hides behind the current chunk's work.
+template <int EPI>
+struct EpiTraits {
+  static constexpr bool kF16Out = (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_QGELU);
+  static constexpr int CHUNK = kF16Out ? 64 : 32;
+  static constexpr int kElt = kF16Out ? 2 : 4;
+};
+
+template <int EPI>
+__device__ __forceinline__ void load_residual(const GemmArgs& args, float4 (&res)[8], int warp_row0, int col0, int lane) {
+  const int sub = lane >> 3, c16 = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int grow = warp_row0 + i * 4 + sub;
+    res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (grow < args.M)
+      res[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(args.out) +
+                                                ((long)grow * args.ldo + col0) * 4 + c16 * 16);
+  }
+}
+
+template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_row, uint8_t* stage, int warp_row0,
-                                              int tile_col0, int lane) {
-  constexpr bool kF16Out = (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_QGELU);
-  constexpr int CHUNK = kF16Out ? 64 : 32;
-  constexpr int kElt = kF16Out ? 2 : 4;
+                                              int tile_col0, int c_begin, int c_end, int lane) {
+  constexpr bool kF16Out = EpiTraits<EPI>::kF16Out;
+  constexpr int CHUNK = EpiTraits<EPI>::CHUNK;
+  constexpr int kElt = EpiTraits<EPI>::kElt;
+  constexpr bool kResid = (EPI == EPI_F32_BIAS_RESID);
+  const int sub = lane >> 3, c16 = lane & 7;
+  float4 res[8], res_next[8];
+  {
+    const int col0 = tile_col0 + c_begin;
+    if (kResid && args.vec_ok && col0 + CHUNK <= args.N) load_residual<EPI>(args, res, warp_row0, col0, lane);
+  }
 #pragma unroll 1
-  for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK) {
+  for (int c0 = c_begin; c0 < c_end; c0 += CHUNK) {
     const int col0 = tile_col0 + c0;
     if (col0 >= args.N) break;  // warp-uniform: the rest of this tile is past N
     const bool in_n = (col0 + CHUNK <= args.N);
     const bool fast = in_n && args.vec_ok;
-    const int sub = lane >> 3, c16 = lane & 7;
-    // residual prefetch: the 8 coalesced 16-byte pieces this lane will update, requested before the TMEM load so that
-    // their L2/HBM latency overlaps it (and is not serialised behind the stores, which may alias for the compiler)
-    float4 res[8];
-    if (EPI == EPI_F32_BIAS_RESID && fast) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int grow = warp_row0 + i * 4 + sub;
-        res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (grow < args.M)
-          res[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(args.out) +
-                                                    ((long)grow * args.ldo + col0) * kElt + c16 * 16);
-      }
+    if (kResid) {  // prefetch the next chunk's residual pieces
+      const int ncol0 = col0 + CHUNK;
+      if (c0 + CHUNK < c_end && args.vec_ok && ncol0 + CHUNK <= args.N) load_residual<EPI>(args, res_next, warp_row0, ncol0, lane);
     }
     uint32_t r[CHUNK];
     __syncwarp();
@@ -85,8 +102,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
       for (int i = 0; i < CHUNK; ++i) v[i] = quick_gelu(v[i]);
     }
     if (fast) {
-      // ---- stage this thread's row (128 bytes)
-      uint4* srow = reinterpret_cast<uint4*>(stage + lane * kStagePitch);
+      // ---- stage this thread's row (128 bytes); 16-byte piece j of row `lane` lives at piece slot j ^ (lane & 7)
+      uint8_t* srow = stage + lane * 128;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         uint4 pk;
@@ -101,7 +118,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
           pk.z = __float_as_uint(v[4 * j + 2]);
           pk.w = __float_as_uint(v[4 * j + 3]);
         }
-        srow[j] = pk;
+        *reinterpret_cast<uint4*>(srow + ((j ^ (lane & 7)) << 4)) = pk;
       }
       __syncwarp();
       // ---- coalesced global phase
@@ -110,12 +127,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
         const int rr = i * 4 + sub;
         const int grow = warp_row0 + rr;
         if (grow < args.M) {
-          uint4 val = *reinterpret_cast<const uint4*>(stage + rr * kStagePitch + c16 * 16);
+          uint4 val = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((c16 ^ (rr & 7)) << 4));
           long orow = grow;
           if (EPI == EPI_F32_ROWMAP)
             orow = (long)args.rowmap_mul * (grow / args.rowmap_div) + (grow % args.rowmap_div) + args.rowmap_add;
           uint8_t* gp = reinterpret_cast<uint8_t*>(args.out) + (orow * args.ldo + col0) * kElt + c16 * 16;
-          if (EPI == EPI_F32_BIAS_RESID) {
+          if (kResid) {
             val.x = __float_as_uint(__uint_as_float(val.x) + res[i].x);
             val.y = __float_as_uint(__uint_as_float(val.y) + res[i].y);
             val.z = __float_as_uint(__uint_as_float(val.z) + res[i].z);
@@ -142,11 +159,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
           for (int i = 0; i < CHUNK; ++i)
             if (col0 + i < args.N) {
               float x = v[i];
-              if (EPI == EPI_F32_BIAS_RESID) x += o[i];
+              if (kResid) x += o[i];
               o[i] = x;
             }
         }
       }
+    }
+    if (kResid) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) res[i] = res_next[i];
     }
   }
 }

@@ -150,7 +150,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N;
-      epilogue_tile<BLOCK_N, EPI>(args, t_row, stage, m_blk * BLOCK_M + q * 32, n_blk * BLOCK_N, lane);
+      epilogue_tile<EPI>(args, t_row, stage, m_blk * BLOCK_M + q * 32, n_blk * BLOCK_N, 0, BLOCK_N, lane);
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
