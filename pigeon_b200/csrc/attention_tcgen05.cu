@@ -14,7 +14,7 @@
 // tile boundaries, so the next tile's loads and first QK^T products overlap the current tile's tail.  192 threads:
 //   warp 0     TMA producer: Q tiles (double-buffered), K/V tiles (64 x 64 halves, 128B swizzle) through a 6-slot ring
 //   warp 1     TMEM allocator + MMA issuer (tcgen05.mma cta_group::1, M = 128)
-//   warps 2-5  softmax, one TMEM lane (= one query row) per thread
+//   warps 2-9  softmax: two warps per TMEM lane quarter, each thread owns half (32 columns) of one query row's block
 //
 // Single pass, flash-style, KV blocks of 64:  S_j = Q K_j^T lands in one of TWO TMEM buffers so that the MMAs of block
 // j+1 run while the softmax warps work on block j.  The softmax warps keep a running row maximum m and row sum l,
@@ -37,10 +37,11 @@ constexpr int kBlockKV = 64;
 constexpr int kSlots = 6;
 constexpr int kQBytes = kBlockQ * kHeadDim * 2;       // 16 KB
 constexpr int kTileBytes = kBlockKV * kHeadDim * 2;   // 8 KB
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                         // TMA warp + MMA warp + 8 softmax warps
 constexpr int kTmemCols = 256;                        // S0 [0,64)  S1 [64,128)  O0 [128,192)  O1 [192,256)
 constexpr int kOCol = 128;
-constexpr int kSmemBytes = 2 * kQBytes + kSlots * kTileBytes + 1024 + 256;
+constexpr int kXchgBytes = (2 * 4 * 64 + 4 * 64) * 4;  // half-row maxima (double-buffered) + row sums
+constexpr int kSmemBytes = 2 * kQBytes + kSlots * kTileBytes + kXchgBytes + 1024 + 256;
 constexpr float kRescaleThreshold = 8.0f;             // log2 domain
 
 struct AttnArgs {
@@ -102,7 +103,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;                       // 2 x 16 KB
   uint8_t* smem_kv = smem + 2 * kQBytes;        // kSlots x 8 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kQBytes + kSlots * kTileBytes);
+  float* xchg_max = reinterpret_cast<float*>(smem + 2 * kQBytes + kSlots * kTileBytes);  // [2][4][2][32]
+  float* xchg_sum = xchg_max + 2 * 4 * 64;                                                // [4][2][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kQBytes + kSlots * kTileBytes + kXchgBytes);
   uint64_t* full_bar = bars;             // [kSlots]  TMA -> MMA
   uint64_t* empty_bar = bars + kSlots;   // [kSlots]  MMA -> TMA
   uint64_t* q_full = bars + 2 * kSlots;  // [2] TMA -> MMA : Q tile landed
@@ -133,7 +136,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
       mbar_init(&q_full[b], 1);
       mbar_init(&q_empty[b], 1);
       mbar_init(&s_full[b], 1);
-      mbar_init(&p_ready[b], 4);
+      mbar_init(&p_ready[b], 8);
       mbar_init(&o_full[b], 1);
     }
     mbar_init(pv_done, 1);
@@ -240,36 +243,45 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
       }
     }
   } else {
-    // ---------------------------------------------------------------- softmax warps
+    // ---------------------------------------------------------------- softmax warps (8 per CTA)
+    // Two warps share each TMEM lane quarter (= 32 query rows): warp "half 0" owns S/P/O columns [0,32), "half 1"
+    // owns [32,64).  Per block they exchange their half-row maxima through shared memory and a 64-thread named
+    // barrier, so both take identical rescale decisions; row sums are combined once per tile.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const uint32_t lane_base = uint32_t(q * 32) << 16;
     const float c = args.scale_log2;
+    const float2 c2 = make_float2(c, c);
+    const int bar_id = 1 + q;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); };
 
     for (int ti = 0; ti < my_tiles; ++ti) {
       const Tile t = decode_tile(blockIdx.x + ti * gridDim.x, args);
       const int row0 = t.view * S;
       const int q_row = t.qt * kBlockQ + q * 32 + lane;  // token index inside the view
-      const uint32_t o_tmem = tmem_base + lane_base + kOCol + (ti & 1) * kHeadDim;
+      const uint32_t o_tmem = tmem_base + lane_base + kOCol + (ti & 1) * kHeadDim + half * 32;
 
       float m = -INFINITY;   // reference maximum currently used in the exponent (raw logit units)
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      float2 l01 = make_float2(0.f, 0.f), l23 = make_float2(0.f, 0.f);
 
       for (int j = 0; j < nb; ++j) {
         const int g = ti * nb + j;
-        const uint32_t s_tmem = tmem_base + lane_base + (g & 1) * kBlockKV;
+        const uint32_t s_tmem = tmem_base + lane_base + (g & 1) * kBlockKV + half * 32;
+        const uint32_t p_tmem = tmem_base + lane_base + (g & 1) * kBlockKV + half * 16;
         const bool tail = (j == nb - 1) && (last_valid < kBlockKV);
+        // columns of the ragged last block owned by this half: [t_lo, t_hi), valid up to last_valid
+        const int t_lo = half * 32, t_hi = (last_n < half * 32 + 32) ? last_n : half * 32 + 32;
         mbar_wait(&s_full[g & 1], (g >> 1) & 1);
         tc_fence_after();
 
-        uint32_t r[kBlockKV];
+        uint32_t r[32];
         float bm = -INFINITY;
         if (!tail) {
-          tmem_ld32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-          tmem_ld32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+          tmem_ld32(s_tmem, r);
           tmem_ld_wait();
           float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < kBlockKV; i += 4) {
+          for (int i = 0; i < 32; i += 4) {
             b0 = fmaxf(b0, __uint_as_float(r[i]));
             b1 = fmaxf(b1, __uint_as_float(r[i + 1]));
             b2 = fmaxf(b2, __uint_as_float(r[i + 2]));
@@ -277,71 +289,74 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
           }
           bm = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
         } else {
-          for (int c0 = 0; c0 < last_n; c0 += 16) {   // sweep 1 of the ragged block: maximum over the valid columns
+          for (int c0 = t_lo; c0 < t_hi; c0 += 16) {   // sweep 1 of the ragged block: maximum over the valid columns
             uint32_t tt[16];
-            tmem_ld16_(s_tmem + c0, tt);
+            tmem_ld16_(tmem_base + lane_base + (g & 1) * kBlockKV + c0, tt);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               if (c0 + i < last_valid) bm = fmaxf(bm, __uint_as_float(tt[i]));
           }
         }
+        // exchange half-row maxima with the partner warp (also orders both warps' S loads before any P store)
+        xchg_max[((g & 1) * 4 + q) * 64 + half * 32 + lane] = bm;
+        pair_sync();
+        bm = fmaxf(bm, xchg_max[((g & 1) * 4 + q) * 64 + (half ^ 1) * 32 + lane]);
 
-        // running maximum with lazy rescale
+        // running maximum with lazy rescale (identical decision in both warps of the pair)
         const float m_new = fmaxf(m, bm);
         if (j == 0) {
           m = m_new;
         } else {
           const bool need = (m_new - m) * c > kRescaleThreshold;
           if (__any_sync(0xffffffffu, need)) {
-            // rare: raise m for every row of this warp and rescale its O rows and l.  O is quiescent once
+            // rare: raise m for every row of this warp and rescale its half of the O rows and l.  O is quiescent once
             // P_{g-1} V_{g-1} retired (S_g complete => every product before g-1 retired, so the parity wait below
             // cannot alias an older phase), and P_g V_g cannot be issued before this warp reports p_ready.
             mbar_wait(pv_done, (g - 1) & 1);
             tc_fence_after();
             const float alpha = ex2((m - m_new) * c);
             uint32_t o[32];
+            tmem_ld32(o_tmem, o);
+            tmem_ld_wait();
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              tmem_ld32(o_tmem + 32 * h, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st32_(o_tmem + 32 * h, o);
-            }
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32_(o_tmem, o);
             tmem_st_wait();
-            l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
+            l01.x *= alpha; l01.y *= alpha; l23.x *= alpha; l23.y *= alpha;
             m = m_new;
           }
         }
         const float mc = m * c;
+        const float2 nmc2 = make_float2(-mc, -mc);
 
         if (!tail) {
-          uint32_t pk[kBlockKV / 2];
+          uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < kBlockKV; i += 4) {
-            const float p0 = ex2(fmaf(__uint_as_float(r[i]), c, -mc));
-            const float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), c, -mc));
-            const float p2 = ex2(fmaf(__uint_as_float(r[i + 2]), c, -mc));
-            const float p3 = ex2(fmaf(__uint_as_float(r[i + 3]), c, -mc));
-            l0 += p0; l1 += p1; l2 += p2; l3 += p3;
-            pk[i >> 1] = pack_half2(p0, p1);
-            pk[(i >> 1) + 1] = pack_half2(p2, p3);
+          for (int i = 0; i < 32; i += 4) {
+            const float2 x01 = ffma2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), c2, nmc2);
+            const float2 x23 = ffma2(make_float2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), c2, nmc2);
+            const float2 p01 = make_float2(ex2(x01.x), ex2(x01.y));
+            const float2 p23 = make_float2(ex2(x23.x), ex2(x23.y));
+            l01 = fadd2(l01, p01);
+            l23 = fadd2(l23, p23);
+            pk[i >> 1] = pack_half2(p01.x, p01.y);
+            pk[(i >> 1) + 1] = pack_half2(p23.x, p23.y);
           }
-          tmem_st32_(s_tmem, pk);  // P overwrites S columns already held in registers by this thread
+          tmem_st16(p_tmem, pk);  // P over S columns that both warps of the pair already hold in registers
         } else {
-          for (int c0 = 0; c0 < last_n; c0 += 16) {   // sweep 2: reload the chunk (P of earlier chunks never reaches it)
+          for (int c0 = t_lo; c0 < t_hi; c0 += 16) {   // sweep 2: reload the chunk (P of earlier chunks never reaches it)
             uint32_t tt[16], pk[8];
-            tmem_ld16_(s_tmem + c0, tt);
+            tmem_ld16_(tmem_base + lane_base + (g & 1) * kBlockKV + c0, tt);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
               const float p0 = (c0 + i < last_valid) ? ex2(fmaf(__uint_as_float(tt[i]), c, -mc)) : 0.f;
               const float p1 = (c0 + i + 1 < last_valid) ? ex2(fmaf(__uint_as_float(tt[i + 1]), c, -mc)) : 0.f;
-              l0 += p0; l1 += p1;
+              l01.x += p0; l01.y += p1;
               pk[i >> 1] = pack_half2(p0, p1);
             }
-            tmem_st8_(s_tmem + (c0 >> 1), pk);
+            tmem_st8_(tmem_base + lane_base + (g & 1) * kBlockKV + (c0 >> 1), pk);
           }
         }
         tmem_st_wait();
@@ -352,17 +367,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
 
       // tile epilogue: O / l -> fp16 -> global.  The O buffer of tile ti is only rewritten by tile ti + 2, whose
       // first P V needs this warp's p_ready, i.e. comes after this read.
+      const float l_own = (l01.x + l01.y) + (l23.x + l23.y);
+      xchg_sum[q * 64 + half * 32 + lane] = l_own;
+      pair_sync();
+      const float l_tot = l_own + xchg_sum[q * 64 + (half ^ 1) * 32 + lane];
       mbar_wait(&o_full[ti & 1], (ti >> 1) & 1);
       tc_fence_after();
-      const float inv_l = 1.0f / ((l0 + l1) + (l2 + l3));
-      __half* orow = args.out + (size_t)(row0 + q_row) * args.hidden + t.head * kHeadDim;
-#pragma unroll
-      for (int c0 = 0; c0 < kHeadDim; c0 += 32) {
+      const float inv_l = 1.0f / l_tot;
+      __half* orow = args.out + (size_t)(row0 + q_row) * args.hidden + t.head * kHeadDim + half * 32;
+      {
         uint32_t o[32];
-        tmem_ld32(o_tmem + c0, o);
+        tmem_ld32(o_tmem, o);
         tmem_ld_wait();
         if (q_row < S) {
-          uint4* o4 = reinterpret_cast<uint4*>(orow + c0);
+          uint4* o4 = reinterpret_cast<uint4*>(orow);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 v;
