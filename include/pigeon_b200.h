@@ -122,7 +122,7 @@ typedef struct pg_refiner_bank {
   const float* data_lnglat;    /* [Ntrain, 2] */
 } pg_refiner_bank;
 
-size_t pg_refiner_workspace_bytes(int64_t B, int32_t topk, int32_t D);
+size_t pg_refiner_workspace_bytes(int64_t B, int32_t topk, int32_t D, int32_t num_cells);
 /* emb f32 [B, V, D]; init_lnglat f64 [B, 2]; cand_idx i64 [B, cand_stride]; cand_prob f32 [B, cand_stride];
  * only the first `topk` candidates of each row are used (topk <= cand_stride).
  *   -> out_lnglat f32 [B, 2], out_cell i64 [B]   (ProtoRefiner.forward's preds_LLH, preds_geocell)

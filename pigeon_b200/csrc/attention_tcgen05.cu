@@ -58,20 +58,6 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__device__ __forceinline__ void tmem_ld16_(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st8_(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
-               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
 __device__ __forceinline__ void tmem_st32_(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -247,6 +233,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
     // Two warps share each TMEM lane quarter (= 32 query rows): warp "half 0" owns S/P/O columns [0,32), "half 1"
     // owns [32,64).  Per block they exchange their half-row maxima through shared memory and a 64-thread named
     // barrier, so both take identical rescale decisions; row sums are combined once per tile.
+    // Software pipeline over the global block index g: while the exponentials of block g are being evaluated the
+    // TMEM load of block g+1 is already in flight, and its row maxima are reduced while the P store of block g drains.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const uint32_t lane_base = uint32_t(q * 32) << 16;
@@ -255,127 +243,137 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
     const int bar_id = 1 + q;
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); };
 
-    for (int ti = 0; ti < my_tiles; ++ti) {
-      const Tile t = decode_tile(blockIdx.x + ti * gridDim.x, args);
-      const int row0 = t.view * S;
-      const int q_row = t.qt * kBlockQ + q * 32 + lane;  // token index inside the view
+    // per-tile state
+    int ti = 0, j = 0;
+    Tile t = decode_tile(blockIdx.x, args);
+    float m = -INFINITY;   // reference maximum currently used in the exponent (raw logit units)
+    float2 l01 = make_float2(0.f, 0.f), l23 = make_float2(0.f, 0.f);
+    float bm = -INFINITY;  // row maximum of the block about to be processed (both halves)
+
+    // masked maximum of this thread's 32 columns of block index jj
+    auto block_max = [&](const uint32_t (&r)[32], int jj) -> float {
+      float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
+      if (jj == nb - 1 && last_valid < kBlockKV) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const int col = half * 32 + i;
+          b0 = fmaxf(b0, col + 0 < last_valid ? __uint_as_float(r[i]) : -INFINITY);
+          b1 = fmaxf(b1, col + 1 < last_valid ? __uint_as_float(r[i + 1]) : -INFINITY);
+          b2 = fmaxf(b2, col + 2 < last_valid ? __uint_as_float(r[i + 2]) : -INFINITY);
+          b3 = fmaxf(b3, col + 3 < last_valid ? __uint_as_float(r[i + 3]) : -INFINITY);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          b0 = fmaxf(b0, __uint_as_float(r[i]));
+          b1 = fmaxf(b1, __uint_as_float(r[i + 1]));
+          b2 = fmaxf(b2, __uint_as_float(r[i + 2]));
+          b3 = fmaxf(b3, __uint_as_float(r[i + 3]));
+        }
+      }
+      return fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
+    };
+    // asynchronous TMEM loads of this thread's 32 columns of block g, in two 16-column halves (the second half is issued
+    // once the registers of the block being consumed are free); both complete at the next tmem_ld_wait()
+    auto fetch_lo = [&](uint32_t (&r)[32], int g) {
+      mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+      tc_fence_after();
+      tmem_ld16(tmem_base + lane_base + (g & 1) * kBlockKV + half * 32, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+    };
+    auto fetch_hi = [&](uint32_t (&r)[32], int g) {
+      tmem_ld16(tmem_base + lane_base + (g & 1) * kBlockKV + half * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+    };
+    auto exchange_max = [&](float mine, int g) -> float {   // all 64 threads of the pair
+      float* slot = xchg_max + ((g & 1) * 4 + q) * 64;
+      slot[half * 32 + lane] = mine;
+      pair_sync();
+      return fmaxf(mine, slot[(half ^ 1) * 32 + lane]);
+    };
+
+    // one pipeline step: consume block g from `cur`, prefetch block g+1 into `nxt`
+    auto step = [&](uint32_t (&cur)[32], uint32_t (&nxt)[32], int g) {
+      const uint32_t p_tmem = tmem_base + lane_base + (g & 1) * kBlockKV + half * 16;
       const uint32_t o_tmem = tmem_base + lane_base + kOCol + (ti & 1) * kHeadDim + half * 32;
+      const bool tail = (j == nb - 1) && (last_valid < kBlockKV);
+      const bool more = (g + 1 < G);
 
-      float m = -INFINITY;   // reference maximum currently used in the exponent (raw logit units)
-      float2 l01 = make_float2(0.f, 0.f), l23 = make_float2(0.f, 0.f);
-
-      for (int j = 0; j < nb; ++j) {
-        const int g = ti * nb + j;
-        const uint32_t s_tmem = tmem_base + lane_base + (g & 1) * kBlockKV + half * 32;
-        const uint32_t p_tmem = tmem_base + lane_base + (g & 1) * kBlockKV + half * 16;
-        const bool tail = (j == nb - 1) && (last_valid < kBlockKV);
-        // columns of the ragged last block owned by this half: [t_lo, t_hi), valid up to last_valid
-        const int t_lo = half * 32, t_hi = (last_n < half * 32 + 32) ? last_n : half * 32 + 32;
-        mbar_wait(&s_full[g & 1], (g >> 1) & 1);
-        tc_fence_after();
-
-        uint32_t r[32];
-        float bm = -INFINITY;
-        if (!tail) {
-          tmem_ld32(s_tmem, r);
-          tmem_ld_wait();
-          float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            b0 = fmaxf(b0, __uint_as_float(r[i]));
-            b1 = fmaxf(b1, __uint_as_float(r[i + 1]));
-            b2 = fmaxf(b2, __uint_as_float(r[i + 2]));
-            b3 = fmaxf(b3, __uint_as_float(r[i + 3]));
-          }
-          bm = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
-        } else {
-          for (int c0 = t_lo; c0 < t_hi; c0 += 16) {   // sweep 1 of the ragged block: maximum over the valid columns
-            uint32_t tt[16];
-            tmem_ld16_(tmem_base + lane_base + (g & 1) * kBlockKV + c0, tt);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c0 + i < last_valid) bm = fmaxf(bm, __uint_as_float(tt[i]));
-          }
-        }
-        // exchange half-row maxima with the partner warp (also orders both warps' S loads before any P store)
-        xchg_max[((g & 1) * 4 + q) * 64 + half * 32 + lane] = bm;
-        pair_sync();
-        bm = fmaxf(bm, xchg_max[((g & 1) * 4 + q) * 64 + (half ^ 1) * 32 + lane]);
-
-        // running maximum with lazy rescale (identical decision in both warps of the pair)
+      // running maximum with lazy rescale (identical decision in both warps of the pair)
+      if (j == 0) {
+        m = bm;
+        l01 = make_float2(0.f, 0.f);
+        l23 = make_float2(0.f, 0.f);
+      } else {
         const float m_new = fmaxf(m, bm);
-        if (j == 0) {
+        const bool need = (m_new - m) * c > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          // rare: raise m for every row of this warp and rescale its half of the O rows and l.  O is quiescent once
+          // P_{g-1} V_{g-1} retired (S_g complete => every product before g-1 retired, so the parity wait below
+          // cannot alias an older phase), and P_g V_g cannot be issued before this warp reports p_ready.
+          mbar_wait(pv_done, (g - 1) & 1);
+          tc_fence_after();
+          const float alpha = ex2((m - m_new) * c);
+          uint32_t o[32];
+          tmem_ld32(o_tmem, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32_(o_tmem, o);
+          tmem_st_wait();
+          l01.x *= alpha; l01.y *= alpha; l23.x *= alpha; l23.y *= alpha;
           m = m_new;
-        } else {
-          const bool need = (m_new - m) * c > kRescaleThreshold;
-          if (__any_sync(0xffffffffu, need)) {
-            // rare: raise m for every row of this warp and rescale its half of the O rows and l.  O is quiescent once
-            // P_{g-1} V_{g-1} retired (S_g complete => every product before g-1 retired, so the parity wait below
-            // cannot alias an older phase), and P_g V_g cannot be issued before this warp reports p_ready.
-            mbar_wait(pv_done, (g - 1) & 1);
-            tc_fence_after();
-            const float alpha = ex2((m - m_new) * c);
-            uint32_t o[32];
-            tmem_ld32(o_tmem, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32_(o_tmem, o);
-            tmem_st_wait();
-            l01.x *= alpha; l01.y *= alpha; l23.x *= alpha; l23.y *= alpha;
-            m = m_new;
-          }
         }
-        const float mc = m * c;
-        const float2 nmc2 = make_float2(-mc, -mc);
+      }
+      const float mc = m * c;
+      const float2 nmc2 = make_float2(-mc, -mc);
 
-        if (!tail) {
-          uint32_t pk[16];
+      // P is packed in place: columns i..i+3 are consumed before cur[i/2], cur[i/2+1] (<= i) are overwritten
+      auto exps = [&](int i0) {   // 16 columns starting at i0
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float2 x01 = ffma2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), c2, nmc2);
-            const float2 x23 = ffma2(make_float2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), c2, nmc2);
-            const float2 p01 = make_float2(ex2(x01.x), ex2(x01.y));
-            const float2 p23 = make_float2(ex2(x23.x), ex2(x23.y));
-            l01 = fadd2(l01, p01);
-            l23 = fadd2(l23, p23);
-            pk[i >> 1] = pack_half2(p01.x, p01.y);
-            pk[(i >> 1) + 1] = pack_half2(p23.x, p23.y);
+        for (int i = i0; i < i0 + 16; i += 4) {
+          const float2 x01 = ffma2(make_float2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), c2, nmc2);
+          const float2 x23 = ffma2(make_float2(__uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3])), c2, nmc2);
+          float2 p01 = make_float2(ex2(x01.x), ex2(x01.y));
+          float2 p23 = make_float2(ex2(x23.x), ex2(x23.y));
+          if (tail) {
+            const int col = half * 32 + i;
+            if (col + 0 >= last_valid) p01.x = 0.f;
+            if (col + 1 >= last_valid) p01.y = 0.f;
+            if (col + 2 >= last_valid) p23.x = 0.f;
+            if (col + 3 >= last_valid) p23.y = 0.f;
           }
-          tmem_st16(p_tmem, pk);  // P over S columns that both warps of the pair already hold in registers
-        } else {
-          for (int c0 = t_lo; c0 < t_hi; c0 += 16) {   // sweep 2: reload the chunk (P of earlier chunks never reaches it)
-            uint32_t tt[16], pk[8];
-            tmem_ld16_(tmem_base + lane_base + (g & 1) * kBlockKV + c0, tt);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-              const float p0 = (c0 + i < last_valid) ? ex2(fmaf(__uint_as_float(tt[i]), c, -mc)) : 0.f;
-              const float p1 = (c0 + i + 1 < last_valid) ? ex2(fmaf(__uint_as_float(tt[i + 1]), c, -mc)) : 0.f;
-              l01.x += p0; l01.y += p1;
-              pk[i >> 1] = pack_half2(p0, p1);
-            }
-            tmem_st8_(tmem_base + lane_base + (g & 1) * kBlockKV + (c0 >> 1), pk);
-          }
+          l01 = fadd2(l01, p01);
+          l23 = fadd2(l23, p23);
+          cur[i >> 1] = pack_half2(p01.x, p01.y);
+          cur[(i >> 1) + 1] = pack_half2(p23.x, p23.y);
         }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_ready[g & 1]);
+      };
+      exps(0);
+      if (more) fetch_lo(nxt, g + 1);  // S_{g+1} is normally complete by now: its load overlaps the second half
+      exps(16);
+      if (more) fetch_hi(nxt, g + 1);
+      tmem_st16(p_tmem, *reinterpret_cast<uint32_t(*)[16]>(&cur[0]));  // P over S columns both warps of the pair hold in registers
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[g & 1]);
+      if (more) {
+        tmem_ld_wait();
+        // the exchange also orders both warps' S_{g+1} loads before any P_{g+1} store
+        bm = exchange_max(block_max(nxt, (j + 1 == nb) ? 0 : j + 1), g + 1);
       }
 
-      // tile epilogue: O / l -> fp16 -> global.  The O buffer of tile ti is only rewritten by tile ti + 2, whose
-      // first P V needs this warp's p_ready, i.e. comes after this read.
-      const float l_own = (l01.x + l01.y) + (l23.x + l23.y);
-      xchg_sum[q * 64 + half * 32 + lane] = l_own;
-      pair_sync();
-      const float l_tot = l_own + xchg_sum[q * 64 + (half ^ 1) * 32 + lane];
-      mbar_wait(&o_full[ti & 1], (ti >> 1) & 1);
-      tc_fence_after();
-      const float inv_l = 1.0f / l_tot;
-      __half* orow = args.out + (size_t)(row0 + q_row) * args.hidden + t.head * kHeadDim + half * 32;
-      {
+      if (j == nb - 1) {
+        // tile epilogue: O / l -> fp16 -> global.  The O buffer of tile ti is only rewritten by tile ti + 2, whose
+        // first P V needs this warp's p_ready, i.e. comes after this read.
+        const float l_own = (l01.x + l01.y) + (l23.x + l23.y);
+        xchg_sum[q * 64 + half * 32 + lane] = l_own;
+        pair_sync();
+        const float l_tot = l_own + xchg_sum[q * 64 + (half ^ 1) * 32 + lane];
+        mbar_wait(&o_full[ti & 1], (ti >> 1) & 1);
+        tc_fence_after();
+        const float inv_l = 1.0f / l_tot;
+        const int q_row = t.qt * kBlockQ + q * 32 + lane;  // token index inside the view
+        __half* orow = args.out + (size_t)(t.view * S + q_row) * args.hidden + t.head * kHeadDim + half * 32;
         uint32_t o[32];
         tmem_ld32(o_tmem, o);
         tmem_ld_wait();
@@ -392,8 +390,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
           }
         }
         __syncwarp();
+        tc_fence_before();  // order this tile's TMEM reads before the barrier arrivals of the next tile
+        ++ti;
+        j = 0;
+        if (more) t = decode_tile(blockIdx.x + ti * gridDim.x, args);
+      } else {
+        ++j;
       }
-      tc_fence_before();  // order this tile's TMEM reads before the barrier arrivals of the next tile
+    };
+
+    if (G > 0) {
+      uint32_t ra[32], rb[32];
+      fetch_lo(ra, 0);
+      fetch_hi(ra, 0);
+      tmem_ld_wait();
+      bm = exchange_max(block_max(ra, 0), 0);
+      for (int g = 0; g < G; g += 2) {
+        step(ra, rb, g);
+        if (g + 1 < G) step(rb, ra, g + 1);
+      }
     }
   }
 

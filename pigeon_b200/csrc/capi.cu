@@ -4,6 +4,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+
 #include <new>
 #include <vector>
 
@@ -208,14 +210,20 @@ int pg_head_loss(const float* logits, int32_t B, int32_t C, int32_t mode, const 
 }
 
 // ---------------------------------------------------------------------------------------------- refiner
-size_t pg_refiner_workspace_bytes(int64_t B, int32_t topk, int32_t D) {
-  if (B <= 0 || topk <= 0 || D <= 0) return 0;
+size_t pg_refiner_workspace_bytes(int64_t B, int32_t topk, int32_t D, int32_t num_cells) {
+  if (B <= 0 || topk <= 0 || D <= 0 || num_cells <= 0) return 0;
   Carver c(nullptr);
   c.take((size_t)B * D * 4);         // pooled queries
   c.take((size_t)B * topk * 4);      // best_logit
   c.take((size_t)B * topk * 2 * 4);  // best_lnglat
   c.take((size_t)B * topk * 4);      // best_proto
+  c.take(refiner_sort_workspace_bytes(num_cells, (long)B * topk));  // counting sort of the pairs by geocell
   return c.off;
+}
+
+static bool refiner_query_major_forced() {
+  const char* e = getenv("PG_REFINER_QUERY_MAJOR");  // debugging / A-B switch, read per call
+  return e && e[0] == '1';
 }
 
 int pg_refiner_forward(const pg_refiner_bank* bank, const float* emb, int64_t B, int32_t V, const double* init_lnglat,
@@ -230,7 +238,7 @@ int pg_refiner_forward(const pg_refiner_bank* bank, const float* emb, int64_t B,
   // mirrors the reference assert at models/proto_refiner.py:135-137
   if (topk <= 0 || topk > cand_stride) { set_last_error("pg_refiner_forward: \"topk\" (%d) must be <= number of candidates (%d)", topk, cand_stride); return 1; }
   if (V <= 0 || bank->dim % 128 || bank->dim > 1024) { set_last_error("pg_refiner_forward: bad V=%d / dim=%d", V, bank->dim); return 1; }
-  if (workspace_bytes < pg_refiner_workspace_bytes(B, topk, bank->dim)) { set_last_error("pg_refiner_forward: workspace too small"); return 1; }
+  if (workspace_bytes < pg_refiner_workspace_bytes(B, topk, bank->dim, bank->num_cells)) { set_last_error("pg_refiner_forward: workspace too small"); return 1; }
   const int sms = sm_count();
   if (sms < 0) return 1;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -239,6 +247,7 @@ int pg_refiner_forward(const pg_refiner_bank* bank, const float* emb, int64_t B,
   float* bl = reinterpret_cast<float*>(c.take((size_t)B * topk * 4));
   float* bll = reinterpret_cast<float*>(c.take((size_t)B * topk * 2 * 4));
   int* bp = reinterpret_cast<int*>(c.take((size_t)B * topk * 4));
+  void* sort_ws = c.take(refiner_sort_workspace_bytes(bank->num_cells, (long)B * topk));
   if (best_logit) bl = best_logit;
   if (best_lnglat) bll = best_lnglat;
   if (best_proto) bp = best_proto;
@@ -250,7 +259,15 @@ int pg_refiner_forward(const pg_refiner_bank* bank, const float* emb, int64_t B,
   rb.member_idx = reinterpret_cast<const long long*>(bank->member_idx);
   rb.data_emb = bank->data_emb; rb.data_lnglat = bank->data_lnglat;
   if (refiner_pool(emb, q, B, V, bank->dim, stream)) return 1;
-  if (refiner_scan(rb, q, reinterpret_cast<const long long*>(cand_idx), cand_stride, B, topk, bl, bll, bp, sms, stream)) return 1;
+  // cell-major (each touched prototype segment read once) as soon as cells are shared by several pairs on average;
+  // the query-major kernel (one warp per pair) for small batches where the sort would dominate
+  const bool cell_major = !refiner_query_major_forced() && (long)B * topk >= 2L * bank->num_cells;
+  if (cell_major) {
+    if (refiner_scan_cell_major(rb, q, reinterpret_cast<const long long*>(cand_idx), cand_stride, B, topk, sort_ws, bl,
+                                bll, bp, sms, stream)) return 1;
+  } else {
+    if (refiner_scan(rb, q, reinterpret_cast<const long long*>(cand_idx), cand_stride, B, topk, bl, bll, bp, sms, stream)) return 1;
+  }
   return refiner_finalize(bl, bll, reinterpret_cast<const long long*>(cand_idx), cand_prob, cand_stride, init_lnglat, B,
                           topk, temperature, max_refinement_km, out_lnglat, reinterpret_cast<long long*>(out_cell),
                           choice, stream);

@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "prof.h"
+#include "ptx.cuh"
 #include "tma_host.h"
 
 namespace pg {
@@ -113,6 +114,234 @@ scan_kernel(const RefinerBank bank, const float* __restrict__ q, const long long
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cell-major scan (v2).  (query, candidate) pairs are counting-sorted by geocell; one CTA per geocell then reads
+// that cell's prototype segment from HBM ONCE (re-reads per 8-query chunk come from L2) and scores every pair of the
+// cell against it.  Per warp a 4-prototype x 8-query register tile: prototype rows stay in registers, the 8 query
+// rows sit in shared memory interleaved in pairs so that one FSUB2 + one FFMA2 (packed fp32) advance two queries.
+// Algorithmic bytes: sum over touched cells of P_c * D * 4, each once.
+// ------------------------------------------------------------------------------------------------
+constexpr int kQT = 8;  // queries per chunk
+constexpr int kPT = 4;  // prototypes per warp register tile
+
+__global__ void pair_hist_kernel(const RefinerBank bank, const long long* __restrict__ cand, int cand_stride, long B,
+                                 int topk, int* __restrict__ cell_cnt, float* __restrict__ best_logit,
+                                 float* __restrict__ best_lnglat, int* __restrict__ best_proto) {
+  const long pairs = B * topk;
+  for (long pair = (long)blockIdx.x * blockDim.x + threadIdx.x; pair < pairs; pair += (long)gridDim.x * blockDim.x) {
+    const long b = pair / topk;
+    const int j = pair % topk;
+    const long long cell = cand[b * cand_stride + j];
+    bool live = false;
+    if (cell >= 0 && cell < bank.num_cells) live = bank.cell_off[cell + 1] > bank.cell_off[cell];
+    if (live) {
+      atomicAdd(&cell_cnt[cell], 1);
+    } else {  // reference: protos[cell] is None -> logit -100000, prediction [0., 0.]   (proto_refiner.py:168-174)
+      best_logit[pair] = -100000.f;
+      best_lnglat[2 * pair] = 0.f;
+      best_lnglat[2 * pair + 1] = 0.f;
+      best_proto[pair] = -1;
+    }
+  }
+}
+
+// exclusive scan of cell_cnt[0..C) -> cell_start[0..C]; also zeroes the cursors. Single block.
+__global__ void cell_scan_offsets_kernel(const int* __restrict__ cell_cnt, int* __restrict__ cell_start,
+                                         int* __restrict__ cursor, int C) {
+  __shared__ int carry;
+  __shared__ int warp_tot[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < C; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = (i < C) ? cell_cnt[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int t = (threadIdx.x < (blockDim.x >> 5)) ? warp_tot[threadIdx.x] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (threadIdx.x >= o) t += y;
+      }
+      warp_tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+    const int warp_off = (threadIdx.x >> 5) ? warp_tot[(threadIdx.x >> 5) - 1] : 0;
+    if (i < C) {
+      cell_start[i] = carry + warp_off + x - v;
+      cursor[i] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry += warp_off + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cell_start[C] = carry;
+}
+
+__global__ void pair_scatter_kernel(const RefinerBank bank, const long long* __restrict__ cand, int cand_stride, long B,
+                                    int topk, const int* __restrict__ cell_start, int* __restrict__ cursor,
+                                    int* __restrict__ order) {
+  const long pairs = B * topk;
+  for (long pair = (long)blockIdx.x * blockDim.x + threadIdx.x; pair < pairs; pair += (long)gridDim.x * blockDim.x) {
+    const long b = pair / topk;
+    const int j = pair % topk;
+    const long long cell = cand[b * cand_stride + j];
+    if (cell >= 0 && cell < bank.num_cells && bank.cell_off[cell + 1] > bank.cell_off[cell])
+      order[cell_start[cell] + atomicAdd(&cursor[cell], 1)] = (int)pair;
+  }
+}
+
+template <int NV4>
+__global__ void __launch_bounds__(256, 1)
+cell_major_scan_kernel(const RefinerBank bank, const float* __restrict__ q, const int* __restrict__ cell_start,
+                       const int* __restrict__ order, int topk, float* __restrict__ best_logit,
+                       float* __restrict__ best_lnglat, int* __restrict__ best_proto) {
+  constexpr int D = NV4 * 128;
+  extern __shared__ float4 qs[];                 // [D/4 * kQT/2 ... ] layout: (chunk i, lane, query-pair, 2 halves)
+  __shared__ float wbest_d[8][kQT];
+  __shared__ long wbest_p[8][kQT];
+  const int cell = blockIdx.x;
+  const int n_pairs = cell_start[cell + 1] - cell_start[cell];
+  if (n_pairs == 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long lo = bank.cell_off[cell], hi = bank.cell_off[cell + 1];
+  const int* my_order = order + cell_start[cell];
+
+  for (int c0 = 0; c0 < n_pairs; c0 += kQT) {
+    const int nq = min(kQT, n_pairs - c0);
+    __syncthreads();
+    // stage the chunk's queries, two queries interleaved per float4:
+    //   qs[((i * (kQT/2) + qp) * 2 + h) * 32 + lane] = for h = 0: (q_{2qp}[4c], q_{2qp+1}[4c], q_{2qp}[4c+1], q_{2qp+1}[4c+1])
+    //                                                  for h = 1: the same for elements 4c+2, 4c+3;  c = lane + 32 i
+    for (int idx = threadIdx.x; idx < NV4 * 32 * (kQT / 2); idx += blockDim.x) {
+      const int ln = idx & 31;
+      const int qp = (idx >> 5) % (kQT / 2);
+      const int i = (idx >> 5) / (kQT / 2);
+      const int col4 = i * 32 + ln;      // float4 column index
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (2 * qp < nq) a = reinterpret_cast<const float4*>(q + (long)(my_order[c0 + 2 * qp] / topk) * D)[col4];
+      if (2 * qp + 1 < nq) b = reinterpret_cast<const float4*>(q + (long)(my_order[c0 + 2 * qp + 1] / topk) * D)[col4];
+      const size_t base = (size_t)((i * (kQT / 2) + qp) * 2) * 32 + ln;   // lanes contiguous: conflict-free LDS.128
+      qs[base] = make_float4(a.x, b.x, a.y, b.y);
+      qs[base + 32] = make_float4(a.z, b.z, a.w, b.w);
+    }
+    __syncthreads();
+
+    float run_d[kQT];
+    long run_p[kQT];
+#pragma unroll
+    for (int i = 0; i < kQT; ++i) { run_d[i] = INFINITY; run_p[i] = hi; }
+
+    for (long p0 = lo + warp * kPT; p0 < hi; p0 += 8 * kPT) {
+      float2 acc[kPT][kQT / 2];
+#pragma unroll
+      for (int a = 0; a < kPT; ++a)
+#pragma unroll
+        for (int b = 0; b < kQT / 2; ++b) acc[a][b] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
+        float4 pr[kPT];
+#pragma unroll
+        for (int a = 0; a < kPT; ++a) {
+          const long p = (p0 + a < hi) ? p0 + a : hi - 1;   // clamp: duplicates are discarded below
+          pr[a] = __ldg(reinterpret_cast<const float4*>(bank.proto_emb + p * D) + lane + 32 * i);
+        }
+        const float4* qrow = qs + (size_t)(i * (kQT / 2) * 2) * 32 + lane;
+#pragma unroll
+        for (int b = 0; b < kQT / 2; ++b) {
+          const float4 q01 = qrow[(2 * b) * 32], q23 = qrow[(2 * b + 1) * 32];
+#pragma unroll
+          for (int a = 0; a < kPT; ++a) {
+            float2 d;
+            d = fsub2(make_float2(pr[a].x, pr[a].x), make_float2(q01.x, q01.y)); acc[a][b] = ffma2(d, d, acc[a][b]);
+            d = fsub2(make_float2(pr[a].y, pr[a].y), make_float2(q01.z, q01.w)); acc[a][b] = ffma2(d, d, acc[a][b]);
+            d = fsub2(make_float2(pr[a].z, pr[a].z), make_float2(q23.x, q23.y)); acc[a][b] = ffma2(d, d, acc[a][b]);
+            d = fsub2(make_float2(pr[a].w, pr[a].w), make_float2(q23.z, q23.w)); acc[a][b] = ffma2(d, d, acc[a][b]);
+          }
+        }
+      }
+      // 32 partial sums (index = proto a * 8 + query) -> lane L ends with the warp total of index L
+      float v[32];
+#pragma unroll
+      for (int a = 0; a < kPT; ++a)
+#pragma unroll
+        for (int b = 0; b < kQT / 2; ++b) { v[a * kQT + 2 * b] = acc[a][b].x; v[a * kQT + 2 * b + 1] = acc[a][b].y; }
+#pragma unroll
+      for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+#pragma unroll
+        for (int k = 0; k < n; ++k) {
+          const float send = (lane & off) ? v[k] : v[k + n];
+          const float keep = (lane & off) ? v[k + n] : v[k];
+          v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      // lane L: squared distance of prototype p0 + (L >> 3) to query (L & 7); min over the 4 prototypes, first index wins
+      float d2 = v[0];
+      long pp = p0 + (lane >> 3);
+      if (pp >= hi) d2 = INFINITY;
+#pragma unroll
+      for (int off = 8; off <= 16; off <<= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, d2, off);
+        const long op = __shfl_xor_sync(0xffffffffu, pp, off);
+        if (od < d2 || (od == d2 && op < pp)) { d2 = od; pp = op; }
+      }
+      // lanes 0..7 now hold the group's best for query `lane`; keep running best per query in lanes 0..7
+#pragma unroll
+      for (int i = 0; i < kQT; ++i) {
+        const float gd = __shfl_sync(0xffffffffu, d2, i);
+        const long gp = __shfl_sync(0xffffffffu, pp, i);
+        if (gd < run_d[i] || (gd == run_d[i] && gp < run_p[i])) { run_d[i] = gd; run_p[i] = gp; }
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < kQT; ++i) { wbest_d[warp][i] = run_d[i]; wbest_p[warp][i] = run_p[i]; }
+    }
+    __syncthreads();
+    // warp w finishes query w of the chunk: cross-warp arg-min, then the farthest-member pick, then the outputs
+    if (warp < nq) {
+      float bd = wbest_d[0][warp];
+      long bp = wbest_p[0][warp];
+      for (int w = 1; w < 8; ++w) {
+        const float od = wbest_d[w][warp];
+        const long op = wbest_p[w][warp];
+        if (od < bd || (od == bd && op < bp)) { bd = od; bp = op; }
+      }
+      const long pair = my_order[c0 + warp];
+      const long b = pair / topk;
+      float lng = bank.proto_lnglat[2 * bp], lat = bank.proto_lnglat[2 * bp + 1];
+      if (bank.proto_count[bp] != 1) {
+        float4 qv[NV4];
+        const float4* q4 = reinterpret_cast<const float4*>(q + b * D);
+#pragma unroll
+        for (int i = 0; i < NV4; ++i) qv[i] = q4[lane + 32 * i];
+        const long mlo = bank.member_off[bp], mhi = bank.member_off[bp + 1];
+        float far = -INFINITY;
+        long bm = -1;
+        for (long mi = mlo; mi < mhi; ++mi) {
+          const long idx = bank.member_idx[mi];
+          const float dd = sqdist<NV4>(qv, bank.data_emb + idx * D, lane);
+          if (dd > far) { far = dd; bm = idx; }
+        }
+        if (bm >= 0) { lng = bank.data_lnglat[2 * bm]; lat = bank.data_lnglat[2 * bm + 1]; }
+      }
+      if (lane == 0) {
+        best_logit[pair] = -sqrtf(bd);
+        best_lnglat[2 * pair] = lng;
+        best_lnglat[2 * pair + 1] = lat;
+        best_proto[pair] = (int)bp;
+      }
+    }
+  }
+}
+
 // NaN ranks above everything, first index wins ties (torch.argmax).
 __device__ __forceinline__ bool better(float v, float bv) {
   const bool vn = isnan(v), bn = isnan(bv);
@@ -206,6 +435,51 @@ int refiner_scan(const RefinerBank& bank, const float* q, const long long* cand,
   }
   if (bank.dim % 128) { set_last_error("refiner: embedding dim %d not a multiple of 128", bank.dim); return 1; }
   return check_launch("refiner_scan");
+}
+
+size_t refiner_sort_workspace_bytes(int num_cells, long pairs) {
+  return (size_t)(3 * (num_cells + 1) + pairs) * sizeof(int) + 1024;
+}
+
+int refiner_scan_cell_major(const RefinerBank& bank, const float* q, const long long* cand, int cand_stride, long B,
+                            int topk, void* sort_ws, float* best_logit, float* best_lnglat, int* best_proto,
+                            int num_sms, cudaStream_t stream) {
+  const long pairs = B * topk;
+  if (pairs == 0) return 0;
+  if (bank.dim % 128) { set_last_error("refiner: embedding dim %d not a multiple of 128", bank.dim); return 1; }
+  const int C = bank.num_cells;
+  int* cell_cnt = reinterpret_cast<int*>(sort_ws);
+  int* cell_start = cell_cnt + (C + 1);
+  int* cursor = cell_start + (C + 1);
+  int* order = cursor + (C + 1);
+  cudaError_t e = cudaMemsetAsync(cell_cnt, 0, (size_t)(C + 1) * sizeof(int), stream);
+  if (e != cudaSuccess) { set_last_error("refiner: memset: %s", cudaGetErrorString(e)); return 1; }
+  long blocks = (pairs + 255) / 256;
+  if (blocks > (long)num_sms * 8) blocks = (long)num_sms * 8;
+  {
+    ProfScope prof("refiner_sort", stream);
+    pair_hist_kernel<<<(int)blocks, 256, 0, stream>>>(bank, cand, cand_stride, B, topk, cell_cnt, best_logit, best_lnglat, best_proto);
+    cell_scan_offsets_kernel<<<1, 1024, 0, stream>>>(cell_cnt, cell_start, cursor, C);
+    pair_scatter_kernel<<<(int)blocks, 256, 0, stream>>>(bank, cand, cand_stride, B, topk, cell_start, cursor, order);
+  }
+  if (check_launch("refiner_sort")) return 1;
+  const size_t smem = (size_t)bank.dim * kQT * sizeof(float);
+  ProfScope prof("refiner_scan", stream);
+  switch (bank.dim / 128) {
+#define PG_CASE(N)                                                                                                   \
+  case N: {                                                                                                          \
+    auto kern = cell_major_scan_kernel<N>;                                                                           \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    kern<<<C, 256, smem, stream>>>(bank, q, cell_start, order, topk, best_logit, best_lnglat, best_proto);           \
+    break;                                                                                                           \
+  }
+    PG_CASE(1) PG_CASE(2) PG_CASE(4) PG_CASE(6) PG_CASE(8)
+#undef PG_CASE
+    default:
+      set_last_error("refiner: embedding dim %d unsupported (need 128*{1,2,4,6,8})", bank.dim);
+      return 1;
+  }
+  return check_launch("refiner_scan_cell_major");
 }
 
 int refiner_finalize(const float* best_logit, const float* best_lnglat, const long long* cand, const float* cand_prob,

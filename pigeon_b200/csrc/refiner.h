@@ -22,6 +22,11 @@ struct RefinerBank {
 int refiner_pool(const float* emb, float* q, long B, int V, int D, cudaStream_t stream);
 int refiner_scan(const RefinerBank& bank, const float* q, const long long* cand, int cand_stride, long B, int topk,
                  float* best_logit, float* best_lnglat, int* best_proto, int num_sms, cudaStream_t stream);
+// Cell-major variant of refiner_scan: pairs counting-sorted by geocell, each touched prototype segment read once.
+size_t refiner_sort_workspace_bytes(int num_cells, long pairs);
+int refiner_scan_cell_major(const RefinerBank& bank, const float* q, const long long* cand, int cand_stride, long B,
+                            int topk, void* sort_ws, float* best_logit, float* best_lnglat, int* best_proto,
+                            int num_sms, cudaStream_t stream);
 int refiner_finalize(const float* best_logit, const float* best_lnglat, const long long* cand, const float* cand_prob,
                      int cand_stride, const double* init_lnglat, long B, int topk, float temperature,
                      double max_refinement, float* out_lnglat, long long* out_cell, int* out_choice,

@@ -128,7 +128,7 @@ def refiner_forward(bank: DeviceBank, emb: torch.Tensor, init_lnglat: torch.Tens
     stride = cand_idx.shape[1]
     dev = emb.device
     lib = load()
-    ws = torch.empty(lib.pg_refiner_workspace_bytes(B, topk, D), dtype=torch.uint8, device=dev)
+    ws = torch.empty(lib.pg_refiner_workspace_bytes(B, topk, D, bank.num_cells), dtype=torch.uint8, device=dev)
     out_ll = torch.empty((B, 2), dtype=torch.float32, device=dev)
     out_cell = torch.empty((B,), dtype=torch.int64, device=dev)
     dbg = None

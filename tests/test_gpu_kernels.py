@@ -184,3 +184,30 @@ def test_refiner_vs_oracle(cuda, C, P, D, B, kc, topk, members, T, maxref):
     assert (info["choice"] != 0).any(), "test data must exercise a refinement that changes the geocell"
     assert torch.equal(ocell.cpu()[row_ok], cell[row_ok])
     assert torch.equal(oll.cpu()[row_ok], ll[row_ok])
+
+
+@pytest.mark.parametrize("C,P,D,B,kc,topk,members", [(30, 900, 1024, 256, 8, 8, 4.0), (64, 4000, 768, 512, 10, 5, 0.0),
+                                                     (20, 150, 128, 3, 4, 4, 3.0)])
+def test_refiner_cell_major_equals_query_major(cuda, C, P, D, B, kc, topk, members, monkeypatch):
+    """The cell-major scan (pairs counting-sorted by geocell, register-tiled 4 prototypes x 8 queries) and the
+    query-major scan (one warp per pair) are two schedules of the same arithmetic: same winners, same outputs."""
+    import numpy as np
+    from pigeon_b200 import ops, synthetic
+    bank = synthetic.synthetic_bank(C, P, D, seed=12, members_mean=members, empty_cells=2)
+    cand, probs = synthetic.synthetic_candidates(B, kc, C, seed=13)
+    emb = torch.from_numpy(synthetic.synthetic_queries(bank, cand, views=1, seed=14)).to(cuda)
+    init = torch.from_numpy(synthetic.synthetic_geocells(B, seed=15)).to(cuda)
+    dbank = ops.DeviceBank(cuda, **bank)
+    args = (dbank, emb, init, torch.from_numpy(cand).to(cuda), torch.from_numpy(probs).to(cuda), topk, 1.6, 1e6)
+    monkeypatch.setenv("PG_REFINER_QUERY_MAJOR", "1")
+    ll_q, cell_q, dq = ops.refiner_forward(*args, debug=True)
+    monkeypatch.setenv("PG_REFINER_QUERY_MAJOR", "0")
+    ll_c, cell_c, dc = ops.refiner_forward(*args, debug=True)
+    torch.cuda.synchronize()
+    # identical winners except where two prototypes tie to within fp32 summation-order noise
+    same = (dq["best_proto"] == dc["best_proto"])
+    assert same.float().mean() > 0.995
+    assert torch.allclose(dq["best_logit"], dc["best_logit"], rtol=1e-5, atol=1e-6)
+    assert torch.equal(dq["best_lnglat"][same], dc["best_lnglat"][same])
+    rows = same.all(dim=1)
+    assert torch.equal(cell_q[rows], cell_c[rows]) and torch.equal(ll_q[rows], ll_c[rows])
