@@ -200,6 +200,8 @@ def run_ours(args):
                                      "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": a_ach / peaks["tflops_sustained"],
                                      "share_of_step": attn_ms / prof["total_ms"]}
         out["kernel_ms_per_step"] = {k: round(v, 3) for k, v in prof.items() if k.endswith("_ms")}
+        out["gpu_launches"] = prof["launches"] * args.steps     # counted by the library's launch hooks, per step
+        out["launches_by_family_per_step"] = prof["families"]
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(sample_images=args.cpu_sample)
     if rank == 0:
@@ -234,7 +236,8 @@ def profile_step(model, refiner, px_dev, labels, labels_clf):
     lib.pg_profile_read(names, ms, counts, n)
     d = {names[i].decode(): (ms[i], counts[i]) for i in range(n)}
     gemm = [v for k, v in d.items() if k.startswith("gemm")]
-    return {"gemm_ms": sum(v[0] for v in gemm), "gemm_launches": sum(v[1] for v in gemm),
+    return {"launches": sum(v[1] for v in d.values()), "families": {k: v[1] for k, v in d.items()},
+            "gemm_ms": sum(v[0] for v in gemm), "gemm_launches": sum(v[1] for v in gemm),
             "attention_ms": d.get("attention", (0.0, 0))[0], "layernorm_ms": d.get("layernorm", (0.0, 0))[0],
             "other_ms": sum(v[0] for k, v in d.items() if not k.startswith("gemm") and k not in ("attention", "layernorm")),
             "total_ms": e0.elapsed_time(e1)}

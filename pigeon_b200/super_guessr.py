@@ -138,11 +138,11 @@ class CLIPVisionTower(nn.Module):
     @torch.no_grad()
     def embed(self, pixel_values: Tensor) -> Tensor:
         """Token mean of last_hidden_state, fused path (last_hidden_state is not returned)."""
-        return self.engine().forward(pixel_values.to(next(self.parameters()).device))
+        return self.engine().forward(pixel_values)
 
     @torch.no_grad()
     def forward(self, pixel_values: Tensor = None, **kwargs):
-        emb, hidden = self.engine().forward(pixel_values.to(next(self.parameters()).device), return_hidden=True)
+        emb, hidden = self.engine().forward(pixel_values, return_hidden=True)
         return SimpleNamespace(last_hidden_state=hidden, pooler_output=None, token_mean=emb)
 
 
@@ -306,8 +306,7 @@ class SuperGuessr(nn.Module):
         dev = self._device()
         with torch.no_grad():
             # host -> device (reference _move_to_cuda, :193-217)
-            if pixel_values is not None:
-                pixel_values = pixel_values.to(dev, non_blocking=True)
+            # host pixel_values stay on the host here: VitEngine overlaps their H2D copy with compute, chunk by chunk
             if embedding is not None:
                 embedding = embedding.to(dev, non_blocking=True)
 

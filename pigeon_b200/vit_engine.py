@@ -146,7 +146,7 @@ class VitEngine:
         (and last_hidden_state [N, tokens, hidden] fp32 when `return_hidden`)."""
         d = self.dims
         if not pixel_values.is_cuda:
-            raise PigeonB200Error("pixel_values must be a CUDA tensor (the module moves host tensors first)")
+            return self._forward_from_host(pixel_values, return_hidden)
         if pixel_values.dim() != 4 or tuple(pixel_values.shape[1:]) != (3, d.image_size, d.image_size):
             raise ValueError(f"Input image size ({tuple(pixel_values.shape[1:])}) doesn't match model "
                              f"(3, {d.image_size}, {d.image_size}).")
@@ -164,6 +164,58 @@ class VitEngine:
             check(self._lib.pg_vit_forward(self._handle, ptr(pixel_values[s:e]), int(pixel_values.dtype == torch.float16),
                                            e - s, ptr(ws), ws.numel(), ptr(emb[s:e]),
                                            ptr(hidden[s:e]) if hidden is not None else None, stream), "pg_vit_forward")
+        return (emb, hidden) if return_hidden else emb
+
+    @torch.no_grad()
+    def _forward_from_host(self, pixel_values: torch.Tensor, return_hidden: bool, host_chunk: int = 256):
+        """Host (ideally pinned) pixels: the H2D copy of chunk i+1 runs on a side stream while chunk i computes,
+        through two device staging buffers (the reference copies the whole batch up front, super_guessr.py:193-217)."""
+        d = self.dims
+        if pixel_values.dim() != 4 or tuple(pixel_values.shape[1:]) != (3, d.image_size, d.image_size):
+            raise ValueError(f"Input image size ({tuple(pixel_values.shape[1:])}) doesn't match model "
+                             f"(3, {d.image_size}, {d.image_size}).")
+        if pixel_values.dtype not in (torch.float32, torch.float16):
+            pixel_values = pixel_values.float()
+        pixel_values = pixel_values.contiguous()
+        n = pixel_values.shape[0]
+        step = max(1, min(host_chunk, self.max_views_per_pass, n))
+        emb = torch.empty((n, d.hidden), dtype=torch.float32, device=self.device)
+        hidden = torch.empty((n, d.tokens, d.hidden), dtype=torch.float32, device=self.device) if return_hidden else None
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        key = (step, pixel_values.dtype)
+        if getattr(self, "_stage_key", None) != key:
+            self._stage = [torch.empty((step,) + tuple(pixel_values.shape[1:]), dtype=pixel_values.dtype, device=self.device)
+                           for _ in range(2)]
+            self._stage_key = key
+        ws = self._workspace(step)
+        main = torch.cuda.current_stream(self.device)
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        chunks = list(range(0, n, step))
+
+        def start_copy(i):
+            s0, b = chunks[i], i & 1
+            e0 = min(n, s0 + step)
+            with torch.cuda.stream(self._copy_stream):
+                if i >= 2:
+                    self._copy_stream.wait_event(consumed[b])      # staging buffer b free again
+                else:
+                    self._copy_stream.wait_stream(main)            # order after earlier users of the staging buffers
+                self._stage[b][: e0 - s0].copy_(pixel_values[s0:e0], non_blocking=True)
+                copied[b].record(self._copy_stream)
+
+        start_copy(0)
+        for i, s0 in enumerate(chunks):
+            e0, b = min(n, s0 + step), i & 1
+            if i + 1 < len(chunks):
+                start_copy(i + 1)
+            main.wait_event(copied[b])
+            check(self._lib.pg_vit_forward(self._handle, ptr(self._stage[b]), int(pixel_values.dtype == torch.float16),
+                                           e0 - s0, ptr(ws), ws.numel(), ptr(emb[s0:e0]),
+                                           ptr(hidden[s0:e0]) if hidden is not None else None, main.cuda_stream),
+                  "pg_vit_forward")
+            consumed[b].record(main)
         return (emb, hidden) if return_hidden else emb
 
     __call__ = forward

@@ -11,9 +11,10 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 548 -c 190 --csv --log-file gpurun_out/launches_$R.csv \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_stdout.log 2>&1
   tail -2 gpurun_out/ncu_launches_stdout.log
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_f16_kernel -s 9 -c 4 -o gpurun_out/prof_gemm_$R -f \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm2_f16_kernel -s 5 -c 4 -o gpurun_out/prof_gemm_$R -f \
       python tools/ncu_target.py 64 2 > gpurun_out/ncu_gemm_stdout.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_kernel -s 2 -c 1 -o gpurun_out/prof_attn_$R -f \
       python tools/ncu_target.py 64 2 > gpurun_out/ncu_attn_stdout.log 2>&1
   ls -la gpurun_out/*.ncu-rep
 fi
+timeout 900 python tools/refiner_bench.py > gpurun_out/refiner_bench.log 2>&1; tail -8 gpurun_out/refiner_bench.log
