@@ -118,7 +118,7 @@ scan_kernel(const RefinerBank bank, const float* __restrict__ q, const long long
 // Cell-major scan (v2).  (query, candidate) pairs are counting-sorted by geocell; one CTA per geocell then reads
 // that cell's prototype segment from HBM ONCE (re-reads per 8-query chunk come from L2) and scores every pair of the
 // cell against it.  Per warp a 4-prototype x 8-query register tile: prototype rows stay in registers, the 8 query
-// rows sit in shared memory interleaved in pairs so that one FSUB2 + one FFMA2 (packed fp32) advance two queries.
+// rows sit in shared memory interleaved in pairs so that one FFMA2 (packed fp32) advances two queries' dot products.
 // Algorithmic bytes: sum over touched cells of P_c * D * 4, each once.
 // ------------------------------------------------------------------------------------------------
 constexpr int kQT = 8;  // queries per chunk
@@ -199,7 +199,7 @@ __global__ void pair_scatter_kernel(const RefinerBank bank, const long long* __r
 }
 
 template <int NV4>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 cell_major_scan_kernel(const RefinerBank bank, const float* __restrict__ q, const int* __restrict__ cell_start,
                        const int* __restrict__ order, int topk, float* __restrict__ best_logit,
                        float* __restrict__ best_lnglat, int* __restrict__ best_proto) {
@@ -207,6 +207,7 @@ cell_major_scan_kernel(const RefinerBank bank, const float* __restrict__ q, cons
   extern __shared__ float4 qs[];                 // [D/4 * kQT/2 ... ] layout: (chunk i, lane, query-pair, 2 halves)
   __shared__ float wbest_d[8][kQT];
   __shared__ long wbest_p[8][kQT];
+  __shared__ float q_sqnorm[kQT];
   const int cell = blockIdx.x;
   const int n_pairs = cell_start[cell + 1] - cell_start[cell];
   if (n_pairs == 0) return;
@@ -232,6 +233,20 @@ cell_major_scan_kernel(const RefinerBank bank, const float* __restrict__ q, cons
       qs[base] = make_float4(a.x, b.x, a.y, b.y);
       qs[base + 32] = make_float4(a.z, b.z, a.w, b.w);
     }
+    {  // |q|^2 of the chunk's queries: warp w owns query w
+      float acc_q = 0.f;
+      if (warp < nq) {
+        const float4* q4 = reinterpret_cast<const float4*>(q + (long)(my_order[c0 + warp] / topk) * D);
+#pragma unroll
+        for (int i = 0; i < NV4; ++i) {
+          const float4 t = q4[lane + 32 * i];
+          acc_q = fmaf(t.x, t.x, acc_q); acc_q = fmaf(t.y, t.y, acc_q);
+          acc_q = fmaf(t.z, t.z, acc_q); acc_q = fmaf(t.w, t.w, acc_q);
+        }
+      }
+      acc_q = warp_sum(acc_q);
+      if (lane == 0) q_sqnorm[warp] = acc_q;
+    }
     __syncthreads();
 
     float run_d[kQT];
@@ -245,28 +260,42 @@ cell_major_scan_kernel(const RefinerBank bank, const float* __restrict__ q, cons
       for (int a = 0; a < kPT; ++a)
 #pragma unroll
         for (int b = 0; b < kQT / 2; ++b) acc[a][b] = make_float2(0.f, 0.f);
+      // d^2 = |p|^2 + |q|^2 - 2 p.q (the form torch.cdist itself uses beyond 25 rows): one FFMA2 per two (p, q) element
+      // pairs; |p|^2 is accumulated from the same registers.
+      float pn[kPT];
+#pragma unroll
+      for (int a = 0; a < kPT; ++a) pn[a] = 0.f;
+      float4 pr[NV4][kPT];
 #pragma unroll
       for (int i = 0; i < NV4; ++i) {
-        float4 pr[kPT];
 #pragma unroll
         for (int a = 0; a < kPT; ++a) {
           const long p = (p0 + a < hi) ? p0 + a : hi - 1;   // clamp: duplicates are discarded below
-          pr[a] = __ldg(reinterpret_cast<const float4*>(bank.proto_emb + p * D) + lane + 32 * i);
+          pr[i][a] = __ldg(reinterpret_cast<const float4*>(bank.proto_emb + p * D) + lane + 32 * i);
         }
+      }
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
         const float4* qrow = qs + (size_t)(i * (kQT / 2) * 2) * 32 + lane;
+#pragma unroll
+        for (int a = 0; a < kPT; ++a) {
+          pn[a] = fmaf(pr[i][a].x, pr[i][a].x, pn[a]); pn[a] = fmaf(pr[i][a].y, pr[i][a].y, pn[a]);
+          pn[a] = fmaf(pr[i][a].z, pr[i][a].z, pn[a]); pn[a] = fmaf(pr[i][a].w, pr[i][a].w, pn[a]);
+        }
 #pragma unroll
         for (int b = 0; b < kQT / 2; ++b) {
           const float4 q01 = qrow[(2 * b) * 32], q23 = qrow[(2 * b + 1) * 32];
 #pragma unroll
           for (int a = 0; a < kPT; ++a) {
-            float2 d;
-            d = fsub2(make_float2(pr[a].x, pr[a].x), make_float2(q01.x, q01.y)); acc[a][b] = ffma2(d, d, acc[a][b]);
-            d = fsub2(make_float2(pr[a].y, pr[a].y), make_float2(q01.z, q01.w)); acc[a][b] = ffma2(d, d, acc[a][b]);
-            d = fsub2(make_float2(pr[a].z, pr[a].z), make_float2(q23.x, q23.y)); acc[a][b] = ffma2(d, d, acc[a][b]);
-            d = fsub2(make_float2(pr[a].w, pr[a].w), make_float2(q23.z, q23.w)); acc[a][b] = ffma2(d, d, acc[a][b]);
+            acc[a][b] = ffma2(make_float2(pr[i][a].x, pr[i][a].x), make_float2(q01.x, q01.y), acc[a][b]);
+            acc[a][b] = ffma2(make_float2(pr[i][a].y, pr[i][a].y), make_float2(q01.z, q01.w), acc[a][b]);
+            acc[a][b] = ffma2(make_float2(pr[i][a].z, pr[i][a].z), make_float2(q23.x, q23.y), acc[a][b]);
+            acc[a][b] = ffma2(make_float2(pr[i][a].w, pr[i][a].w), make_float2(q23.z, q23.w), acc[a][b]);
           }
         }
       }
+#pragma unroll
+      for (int a = 0; a < kPT; ++a) pn[a] = warp_sum(pn[a]);
       // 32 partial sums (index = proto a * 8 + query) -> lane L ends with the warp total of index L
       float v[32];
 #pragma unroll
@@ -282,8 +311,9 @@ cell_major_scan_kernel(const RefinerBank bank, const float* __restrict__ q, cons
           v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
         }
       }
-      // lane L: squared distance of prototype p0 + (L >> 3) to query (L & 7); min over the 4 prototypes, first index wins
-      float d2 = v[0];
+      // lane L: prototype p0 + (L >> 3) against query (L & 7); min over the 4 prototypes, first index wins
+      const float pn_mine = (lane >> 3) == 0 ? pn[0] : (lane >> 3) == 1 ? pn[1] : (lane >> 3) == 2 ? pn[2] : pn[3];
+      float d2 = fmaxf(pn_mine + q_sqnorm[lane & 7] - 2.f * v[0], 0.f);
       long pp = p0 + (lane >> 3);
       if (pp >= hi) d2 = INFINITY;
 #pragma unroll

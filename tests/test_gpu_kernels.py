@@ -178,7 +178,7 @@ def test_refiner_vs_oracle(cuda, C, P, D, B, kc, topk, members, T, maxref):
     row_ok = pair_ok.all(axis=1) & (info["margin"] > 1e-4)
     assert pair_ok.mean() > 0.95 and row_ok.mean() > 0.8
     assert np.array_equal(dbg["best_proto"].cpu().numpy()[pair_ok], info["best_proto"][pair_ok])
-    np.testing.assert_allclose(dbg["best_logit"].cpu().numpy(), info["best_logit"], rtol=2e-5)
+    np.testing.assert_allclose(dbg["best_logit"].cpu().numpy(), info["best_logit"], rtol=5e-5)
     assert np.array_equal(dbg["best_lnglat"].cpu().numpy()[pair_ok], info["best_lnglat"][pair_ok])
     assert np.array_equal(dbg["choice"].cpu().numpy()[row_ok], info["choice"][row_ok])
     assert (info["choice"] != 0).any(), "test data must exercise a refinement that changes the geocell"
@@ -207,7 +207,7 @@ def test_refiner_cell_major_equals_query_major(cuda, C, P, D, B, kc, topk, membe
     # identical winners except where two prototypes tie to within fp32 summation-order noise
     same = (dq["best_proto"] == dc["best_proto"])
     assert same.float().mean() > 0.995
-    assert torch.allclose(dq["best_logit"], dc["best_logit"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(dq["best_logit"], dc["best_logit"], rtol=5e-5, atol=1e-5)   # direct differences vs |p|^2+|q|^2-2pq
     assert torch.equal(dq["best_lnglat"][same], dc["best_lnglat"][same])
     rows = same.all(dim=1)
     assert torch.equal(cell_q[rows], cell_c[rows]) and torch.equal(ll_q[rows], ll_c[rows])
