@@ -25,21 +25,32 @@
 #include "ptx.cuh"
 #include "tma_host.h"
 
+#include <stdlib.h>
+
 namespace pg {
 
 namespace {
 
 constexpr int kHeadDim = 64;
 constexpr int kBlockQ = 128;
-constexpr int kBlockKV = 64;
-constexpr int kSlots = 6;
 constexpr int kQBytes = kBlockQ * kHeadDim * 2;       // 16 KB
-constexpr int kTileBytes = kBlockKV * kHeadDim * 2;   // 8 KB
 constexpr int kThreads = 192;
-constexpr int kNumSBuf = 3;                           // S/P ring in TMEM: the MMA warp runs two blocks ahead
-constexpr int kTmemCols = 256;                        // S0 [0,64)  S1 [64,128)  S2 [128,192)  O [192,256)
-constexpr int kOCol = kNumSBuf * kBlockKV;
-constexpr int kSmemBytes = kQBytes + kSlots * kTileBytes + 1024 + 256;
+
+// Two tilings of the same kernel:
+//   <64, 3, 2>  KV blocks of 64, three S buffers, 256 TMEM columns, 2 CTAs / SM   (S0 S1 S2 [0,192)  O [192,256))
+//   <32, 2, 4>  KV blocks of 32, two S buffers, 128 TMEM columns, 4 CTAs / SM     (S0 S1 [0,64)      O [64,128))
+template <int KV, int NBUF, int CTAS>
+struct AttnCfg {
+  static constexpr int kBlockKV = KV;
+  static constexpr int kNumSBuf = NBUF;
+  static constexpr int kCtasPerSm = CTAS;
+  static constexpr int kSlots = 6;
+  static constexpr int kTileBytes = KV * kHeadDim * 2;
+  static constexpr int kOCol = NBUF * KV;
+  static constexpr int kTmemCols = (NBUF * KV + kHeadDim <= 128) ? 128 : 256;
+  static constexpr int kSmemBytes = kQBytes + kSlots * kTileBytes + 1024 + 256;
+  static_assert(NBUF * KV + kHeadDim <= kTmemCols, "TMEM budget");
+};
 constexpr float kRescaleThreshold = 8.0f;             // log2 domain
 
 struct AttnArgs {
@@ -81,8 +92,11 @@ __device__ __forceinline__ void tmem_st32_(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+template <class Cfg>
+__global__ void __launch_bounds__(kThreads, Cfg::kCtasPerSm)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs args) {
+  constexpr int kBlockKV = Cfg::kBlockKV, kNumSBuf = Cfg::kNumSBuf, kSlots = Cfg::kSlots, kTileBytes = Cfg::kTileBytes;
+  constexpr int kOCol = Cfg::kOCol, kTmemCols = Cfg::kTmemCols;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;
@@ -135,8 +149,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, kQBytes);
-      tma_load_2d(smem_q, &tmap_qkv, q_full, q_col, row0 + q_tile * kBlockQ);
-      tma_load_2d(smem_q + kTileBytes, &tmap_qkv, q_full, q_col, row0 + q_tile * kBlockQ + kBlockKV);
+#pragma unroll
+      for (int part = 0; part < kBlockQ / kBlockKV; ++part)   // the tensor map's box is one KV tile (kBlockKV rows)
+        tma_load_2d(smem_q + part * kTileBytes, &tmap_qkv, q_full, q_col, row0 + q_tile * kBlockQ + part * kBlockKV);
       int slot = 0;
       uint32_t phase = 0;
       auto load = [&](int col, int blk) {
@@ -225,8 +240,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
       uint32_t r[kBlockKV];
       float bm = -INFINITY;
       if (!tail) {
-        tmem_ld32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-        tmem_ld32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+#pragma unroll
+        for (int h = 0; h < kBlockKV / 32; ++h) tmem_ld32(s_tmem + 32 * h, *reinterpret_cast<uint32_t(*)[32]>(&r[32 * h]));
         tmem_ld_wait();
         float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
 #pragma unroll
@@ -292,7 +307,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
           r[(i >> 1) + 1] = pack_half2(p23.x, p23.y);
         }
         l0 = l01.x; l1 = l01.y; l2 = l23.x; l3 = l23.y;
-        tmem_st32_(s_tmem, r);  // P overwrites S columns already held in registers by this thread
+        // P overwrites S columns already held in registers by this thread
+        if constexpr (kBlockKV == 64) tmem_st32_(s_tmem, r);
+        else tmem_st16(s_tmem, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
       } else {
         for (int c0 = 0; c0 < last_n; c0 += 16) {   // sweep 2: reload the chunk (P of earlier chunks never reaches it)
           uint32_t t[16], pk[8];
@@ -348,16 +365,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
   }
 }
 
-}  // namespace
-
-int attention_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream) {
-  if (n_views <= 0) return 0;
+template <class Cfg>
+int launch_attention(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream) {
   const int hidden = heads * kHeadDim;
   CUtensorMap tm;
-  if (make_tmap_f16_2d(&tm, qkv, (uint64_t)n_views * seq, 3 * hidden, 3 * hidden, kBlockKV, kHeadDim)) return 1;
+  if (make_tmap_f16_2d(&tm, qkv, (uint64_t)n_views * seq, 3 * hidden, 3 * hidden, Cfg::kBlockKV, kHeadDim)) return 1;
+  auto kern = attention_kernel<Cfg>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { set_last_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
     attr_set = true;
   }
@@ -368,10 +384,19 @@ int attention_f16(const void* qkv, void* out, int n_views, int seq, int heads, c
   a.scale_log2 = 0.125f * 1.4426950408889634f;
   dim3 grid((seq + kBlockQ - 1) / kBlockQ, heads, n_views);
   ProfScope prof("attention", stream);
-  attention_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tm, a);
+  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tm, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_last_error("attention launch: %s", cudaGetErrorString(e)); return 1; }
   return 0;
+}
+
+}  // namespace
+
+int attention_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream) {
+  if (n_views <= 0) return 0;
+  const char* v = getenv("PG_ATTN_VARIANT");   // A/B switch: "32" = KV blocks of 32, 4 CTAs/SM
+  if (v && v[0] == '3' && v[1] == '2') return launch_attention<AttnCfg<32, 2, 4>>(qkv, out, n_views, seq, heads, stream);
+  return launch_attention<AttnCfg<64, 3, 2>>(qkv, out, n_views, seq, heads, stream);
 }
 
 }  // namespace pg
