@@ -157,8 +157,11 @@ def run_ours(args):
     ms_e2e, _ = timed(step_e2e, max(2, min(args.steps, 5)), 1)
     e2e_steps = max(2, min(args.steps, 5))
 
-    # per-kernel-family device time of ONE step (CUDA events recorded by the library on the launch stream)
-    prof = profile_step(model, refiner, px_dev, labels, labels_clf) if rank == 0 else None
+    # per-kernel-family device time of ONE step (CUDA events recorded by the library on the launch stream).
+    # Every rank runs it (the step contains the all-gather); only rank 0 reports.
+    prof = profile_step(model, refiner, px_dev, labels, labels_clf)
+    if rank != 0:
+        prof = None
 
     images = B * world
     value = images * args.steps / (ms / 1e3)
