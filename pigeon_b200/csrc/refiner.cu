@@ -198,16 +198,21 @@ __global__ void pair_scatter_kernel(const RefinerBank bank, const long long* __r
   }
 }
 
+// Shared-memory budget of the staged query set: 2 CTAs / SM.
+constexpr int kStageBytes = 96 * 1024;
+
 template <int NV4>
 __global__ void __launch_bounds__(256, 2)
 cell_major_scan_kernel(const RefinerBank bank, const float* __restrict__ q, const int* __restrict__ cell_start,
                        const int* __restrict__ order, int topk, float* __restrict__ best_logit,
                        float* __restrict__ best_lnglat, int* __restrict__ best_proto) {
   constexpr int D = NV4 * 128;
-  extern __shared__ float4 qs[];                 // [D/4 * kQT/2 ... ] layout: (chunk i, lane, query-pair, 2 halves)
-  __shared__ float wbest_d[8][kQT];
-  __shared__ long wbest_p[8][kQT];
-  __shared__ float q_sqnorm[kQT];
+  constexpr int QS = (kStageBytes / (D * 4)) / kQT * kQT;   // queries staged per pass (32 at D = 768, 24 at D = 1024)
+  static_assert(QS >= kQT, "stage holds at least one chunk");
+  extern __shared__ float4 qs[];   // [QS/8][NV4][kQT/2][2][32] float4: chunk-major, lanes contiguous
+  __shared__ float rbest_d[8][QS]; // per-warp running best of every staged query
+  __shared__ int rbest_p[8][QS];   // ... as an offset from the cell's first prototype
+  __shared__ float q_sqnorm[QS];
   const int cell = blockIdx.x;
   const int n_pairs = cell_start[cell + 1] - cell_start[cell];
   if (n_pairs == 0) return;
@@ -215,28 +220,33 @@ cell_major_scan_kernel(const RefinerBank bank, const float* __restrict__ q, cons
   const long lo = bank.cell_off[cell], hi = bank.cell_off[cell + 1];
   const int* my_order = order + cell_start[cell];
 
-  for (int c0 = 0; c0 < n_pairs; c0 += kQT) {
-    const int nq = min(kQT, n_pairs - c0);
+  // One pass over the cell's prototype segment per staged query set: when a cell has at most QS pairs (the common
+  // case) the segment is read exactly once from HBM.
+  for (int c0 = 0; c0 < n_pairs; c0 += QS) {
+    const int nq = min(QS, n_pairs - c0);
+    const int nch = (nq + kQT - 1) / kQT;
     __syncthreads();
-    // stage the chunk's queries, two queries interleaved per float4:
-    //   qs[((i * (kQT/2) + qp) * 2 + h) * 32 + lane] = for h = 0: (q_{2qp}[4c], q_{2qp+1}[4c], q_{2qp}[4c+1], q_{2qp+1}[4c+1])
-    //                                                  for h = 1: the same for elements 4c+2, 4c+3;  c = lane + 32 i
-    for (int idx = threadIdx.x; idx < NV4 * 32 * (kQT / 2); idx += blockDim.x) {
+    // stage the queries, two interleaved per float4 (see the FFMA2 loop):
+    //   qs[(((ch * NV4 + i) * (kQT/2) + qp) * 2 + h) * 32 + lane] = for h = 0: (qA[4c], qB[4c], qA[4c+1], qB[4c+1]),
+    //   for h = 1 the same for elements 4c+2, 4c+3;  A = ch*8 + 2qp, B = A + 1, c = lane + 32 i
+    for (int idx = threadIdx.x; idx < nch * NV4 * (kQT / 2) * 32; idx += blockDim.x) {
       const int ln = idx & 31;
       const int qp = (idx >> 5) % (kQT / 2);
-      const int i = (idx >> 5) / (kQT / 2);
-      const int col4 = i * 32 + ln;      // float4 column index
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-      if (2 * qp < nq) a = reinterpret_cast<const float4*>(q + (long)(my_order[c0 + 2 * qp] / topk) * D)[col4];
-      if (2 * qp + 1 < nq) b = reinterpret_cast<const float4*>(q + (long)(my_order[c0 + 2 * qp + 1] / topk) * D)[col4];
-      const size_t base = (size_t)((i * (kQT / 2) + qp) * 2) * 32 + ln;   // lanes contiguous: conflict-free LDS.128
-      qs[base] = make_float4(a.x, b.x, a.y, b.y);
-      qs[base + 32] = make_float4(a.z, b.z, a.w, b.w);
+      const int i = ((idx >> 5) / (kQT / 2)) % NV4;
+      const int ch = (idx >> 5) / (kQT / 2) / NV4;
+      const int col4 = i * 32 + ln;
+      const int qa = ch * kQT + 2 * qp;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b2 = a;
+      if (qa < nq) a = reinterpret_cast<const float4*>(q + (long)(my_order[c0 + qa] / topk) * D)[col4];
+      if (qa + 1 < nq) b2 = reinterpret_cast<const float4*>(q + (long)(my_order[c0 + qa + 1] / topk) * D)[col4];
+      const size_t base = (size_t)(((ch * NV4 + i) * (kQT / 2) + qp) * 2) * 32 + ln;
+      qs[base] = make_float4(a.x, b2.x, a.y, b2.y);
+      qs[base + 32] = make_float4(a.z, b2.z, a.w, b2.w);
     }
-    {  // |q|^2 of the chunk's queries: warp w owns query w
+    for (int qi = warp; qi < nch * kQT; qi += 8) {   // |q|^2, warp per query
       float acc_q = 0.f;
-      if (warp < nq) {
-        const float4* q4 = reinterpret_cast<const float4*>(q + (long)(my_order[c0 + warp] / topk) * D);
+      if (qi < nq) {
+        const float4* q4 = reinterpret_cast<const float4*>(q + (long)(my_order[c0 + qi] / topk) * D);
 #pragma unroll
         for (int i = 0; i < NV4; ++i) {
           const float4 t = q4[lane + 32 * i];
@@ -245,106 +255,105 @@ cell_major_scan_kernel(const RefinerBank bank, const float* __restrict__ q, cons
         }
       }
       acc_q = warp_sum(acc_q);
-      if (lane == 0) q_sqnorm[warp] = acc_q;
+      if (lane == 0) q_sqnorm[qi] = acc_q;
     }
+    for (int i = lane; i < QS; i += 32) { rbest_d[warp][i] = INFINITY; rbest_p[warp][i] = 0x7fffffff; }
     __syncthreads();
 
-    float run_d[kQT];
-    long run_p[kQT];
-#pragma unroll
-    for (int i = 0; i < kQT; ++i) { run_d[i] = INFINITY; run_p[i] = hi; }
-
     for (long p0 = lo + warp * kPT; p0 < hi; p0 += 8 * kPT) {
-      float2 acc[kPT][kQT / 2];
-#pragma unroll
-      for (int a = 0; a < kPT; ++a)
-#pragma unroll
-        for (int b = 0; b < kQT / 2; ++b) acc[a][b] = make_float2(0.f, 0.f);
-      // d^2 = |p|^2 + |q|^2 - 2 p.q (the form torch.cdist itself uses beyond 25 rows): one FFMA2 per two (p, q) element
-      // pairs; |p|^2 is accumulated from the same registers.
-      float pn[kPT];
-#pragma unroll
-      for (int a = 0; a < kPT; ++a) pn[a] = 0.f;
+      // prototype tile: 4 rows in registers (all pieces requested up front), |p|^2 from the same registers
       float4 pr[NV4][kPT];
 #pragma unroll
       for (int i = 0; i < NV4; ++i) {
 #pragma unroll
         for (int a = 0; a < kPT; ++a) {
-          const long p = (p0 + a < hi) ? p0 + a : hi - 1;   // clamp: duplicates are discarded below
-          pr[i][a] = __ldg(reinterpret_cast<const float4*>(bank.proto_emb + p * D) + lane + 32 * i);
+          const long pidx = (p0 + a < hi) ? p0 + a : hi - 1;   // clamp: duplicates are discarded below
+          pr[i][a] = __ldg(reinterpret_cast<const float4*>(bank.proto_emb + pidx * D) + lane + 32 * i);
         }
       }
+      float pn[kPT];
 #pragma unroll
-      for (int i = 0; i < NV4; ++i) {
-        const float4* qrow = qs + (size_t)(i * (kQT / 2) * 2) * 32 + lane;
+      for (int a = 0; a < kPT; ++a) {
+        float t = 0.f;
 #pragma unroll
-        for (int a = 0; a < kPT; ++a) {
-          pn[a] = fmaf(pr[i][a].x, pr[i][a].x, pn[a]); pn[a] = fmaf(pr[i][a].y, pr[i][a].y, pn[a]);
-          pn[a] = fmaf(pr[i][a].z, pr[i][a].z, pn[a]); pn[a] = fmaf(pr[i][a].w, pr[i][a].w, pn[a]);
+        for (int i = 0; i < NV4; ++i) {
+          t = fmaf(pr[i][a].x, pr[i][a].x, t); t = fmaf(pr[i][a].y, pr[i][a].y, t);
+          t = fmaf(pr[i][a].z, pr[i][a].z, t); t = fmaf(pr[i][a].w, pr[i][a].w, t);
         }
+        pn[a] = warp_sum(t);
+      }
+      const float pn_mine = (lane >> 3) == 0 ? pn[0] : (lane >> 3) == 1 ? pn[1] : (lane >> 3) == 2 ? pn[2] : pn[3];
+      const int pp_mine = (int)(p0 - lo) + (lane >> 3);
+      const bool p_ok = (p0 + (lane >> 3)) < hi;
+
+      for (int ch = 0; ch < nch; ++ch) {
+        // d^2 = |p|^2 + |q|^2 - 2 p.q (the form torch.cdist itself uses beyond 25 rows): one FFMA2 per two (p, q)
+        // element pairs.
+        float2 acc[kPT][kQT / 2];
 #pragma unroll
-        for (int b = 0; b < kQT / 2; ++b) {
-          const float4 q01 = qrow[(2 * b) * 32], q23 = qrow[(2 * b + 1) * 32];
+        for (int a = 0; a < kPT; ++a)
 #pragma unroll
-          for (int a = 0; a < kPT; ++a) {
-            acc[a][b] = ffma2(make_float2(pr[i][a].x, pr[i][a].x), make_float2(q01.x, q01.y), acc[a][b]);
-            acc[a][b] = ffma2(make_float2(pr[i][a].y, pr[i][a].y), make_float2(q01.z, q01.w), acc[a][b]);
-            acc[a][b] = ffma2(make_float2(pr[i][a].z, pr[i][a].z), make_float2(q23.x, q23.y), acc[a][b]);
-            acc[a][b] = ffma2(make_float2(pr[i][a].w, pr[i][a].w), make_float2(q23.z, q23.w), acc[a][b]);
+          for (int b = 0; b < kQT / 2; ++b) acc[a][b] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < NV4; ++i) {
+          const float4* qrow = qs + (size_t)((ch * NV4 + i) * (kQT / 2) * 2) * 32 + lane;
+#pragma unroll
+          for (int b = 0; b < kQT / 2; ++b) {
+            const float4 q01 = qrow[(2 * b) * 32], q23 = qrow[(2 * b + 1) * 32];
+#pragma unroll
+            for (int a = 0; a < kPT; ++a) {
+              acc[a][b] = ffma2(make_float2(pr[i][a].x, pr[i][a].x), make_float2(q01.x, q01.y), acc[a][b]);
+              acc[a][b] = ffma2(make_float2(pr[i][a].y, pr[i][a].y), make_float2(q01.z, q01.w), acc[a][b]);
+              acc[a][b] = ffma2(make_float2(pr[i][a].z, pr[i][a].z), make_float2(q23.x, q23.y), acc[a][b]);
+              acc[a][b] = ffma2(make_float2(pr[i][a].w, pr[i][a].w), make_float2(q23.z, q23.w), acc[a][b]);
+            }
           }
         }
-      }
+        // 32 partial dot products (index = proto a * 8 + query) -> lane L ends with the warp total of index L
+        float v[32];
 #pragma unroll
-      for (int a = 0; a < kPT; ++a) pn[a] = warp_sum(pn[a]);
-      // 32 partial sums (index = proto a * 8 + query) -> lane L ends with the warp total of index L
-      float v[32];
+        for (int a = 0; a < kPT; ++a)
 #pragma unroll
-      for (int a = 0; a < kPT; ++a)
+          for (int b = 0; b < kQT / 2; ++b) { v[a * kQT + 2 * b] = acc[a][b].x; v[a * kQT + 2 * b + 1] = acc[a][b].y; }
 #pragma unroll
-        for (int b = 0; b < kQT / 2; ++b) { v[a * kQT + 2 * b] = acc[a][b].x; v[a * kQT + 2 * b + 1] = acc[a][b].y; }
+        for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
 #pragma unroll
-      for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
-#pragma unroll
-        for (int k = 0; k < n; ++k) {
-          const float send = (lane & off) ? v[k] : v[k + n];
-          const float keep = (lane & off) ? v[k + n] : v[k];
-          v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          for (int k = 0; k < n; ++k) {
+            const float send = (lane & off) ? v[k] : v[k + n];
+            const float keep = (lane & off) ? v[k + n] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
         }
-      }
-      // lane L: prototype p0 + (L >> 3) against query (L & 7); min over the 4 prototypes, first index wins
-      const float pn_mine = (lane >> 3) == 0 ? pn[0] : (lane >> 3) == 1 ? pn[1] : (lane >> 3) == 2 ? pn[2] : pn[3];
-      float d2 = fmaxf(pn_mine + q_sqnorm[lane & 7] - 2.f * v[0], 0.f);
-      long pp = p0 + (lane >> 3);
-      if (pp >= hi) d2 = INFINITY;
+        // lane L: prototype (L >> 3) of the tile against query ch*8 + (L & 7); min over the 4 prototypes, first index wins
+        float d2 = p_ok ? fmaxf(pn_mine + q_sqnorm[ch * kQT + (lane & 7)] - 2.f * v[0], 0.f) : INFINITY;
+        int pp = pp_mine;
 #pragma unroll
-      for (int off = 8; off <= 16; off <<= 1) {
-        const float od = __shfl_xor_sync(0xffffffffu, d2, off);
-        const long op = __shfl_xor_sync(0xffffffffu, pp, off);
-        if (od < d2 || (od == d2 && op < pp)) { d2 = od; pp = op; }
+        for (int off = 8; off <= 16; off <<= 1) {
+          const float od = __shfl_xor_sync(0xffffffffu, d2, off);
+          const int op = __shfl_xor_sync(0xffffffffu, pp, off);
+          if (od < d2 || (od == d2 && op < pp)) { d2 = od; pp = op; }
+        }
+        if (lane < kQT) {   // lanes 0..7 own the running best of query ch*8 + lane in this warp's private row
+          const int qi = ch * kQT + lane;
+          const float cd = rbest_d[warp][qi];
+          const int cp = rbest_p[warp][qi];
+          if (d2 < cd || (d2 == cd && pp < cp)) { rbest_d[warp][qi] = d2; rbest_p[warp][qi] = pp; }
+        }
+        __syncwarp();
       }
-      // lanes 0..7 now hold the group's best for query `lane`; keep running best per query in lanes 0..7
-#pragma unroll
-      for (int i = 0; i < kQT; ++i) {
-        const float gd = __shfl_sync(0xffffffffu, d2, i);
-        const long gp = __shfl_sync(0xffffffffu, pp, i);
-        if (gd < run_d[i] || (gd == run_d[i] && gp < run_p[i])) { run_d[i] = gd; run_p[i] = gp; }
-      }
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int i = 0; i < kQT; ++i) { wbest_d[warp][i] = run_d[i]; wbest_p[warp][i] = run_p[i]; }
     }
     __syncthreads();
-    // warp w finishes query w of the chunk: cross-warp arg-min, then the farthest-member pick, then the outputs
-    if (warp < nq) {
-      float bd = wbest_d[0][warp];
-      long bp = wbest_p[0][warp];
+    // warp w finishes queries w, w+8, ...: cross-warp arg-min, then the farthest-member pick, then the outputs
+    for (int qi = warp; qi < nq; qi += 8) {
+      float bd = rbest_d[0][qi];
+      int bpi = rbest_p[0][qi];
       for (int w = 1; w < 8; ++w) {
-        const float od = wbest_d[w][warp];
-        const long op = wbest_p[w][warp];
-        if (od < bd || (od == bd && op < bp)) { bd = od; bp = op; }
+        const float od = rbest_d[w][qi];
+        const int op = rbest_p[w][qi];
+        if (od < bd || (od == bd && op < bpi)) { bd = od; bpi = op; }
       }
-      const long pair = my_order[c0 + warp];
+      const long bp = lo + bpi;
+      const long pair = my_order[c0 + qi];
       const long b = pair / topk;
       float lng = bank.proto_lnglat[2 * bp], lat = bank.proto_lnglat[2 * bp + 1];
       if (bank.proto_count[bp] != 1) {
@@ -493,7 +502,8 @@ int refiner_scan_cell_major(const RefinerBank& bank, const float* q, const long 
     pair_scatter_kernel<<<(int)blocks, 256, 0, stream>>>(bank, cand, cand_stride, B, topk, cell_start, cursor, order);
   }
   if (check_launch("refiner_sort")) return 1;
-  const size_t smem = (size_t)bank.dim * kQT * sizeof(float);
+  // staged query set: QS = floor(96 KB / (D * 4)) rounded down to a multiple of 8 queries
+  const size_t smem = (size_t)((kStageBytes / (bank.dim * 4)) / kQT * kQT) * bank.dim * sizeof(float);
   ProfScope prof("refiner_scan", stream);
   switch (bank.dim / 128) {
 #define PG_CASE(N)                                                                                                   \
