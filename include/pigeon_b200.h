@@ -135,6 +135,13 @@ int pg_refiner_forward(const pg_refiner_bank* bank, const float* emb, int64_t B,
                        void* workspace, size_t workspace_bytes, float* out_lnglat, int64_t* out_cell,
                        float* best_logit, float* best_lnglat, int32_t* best_proto, int32_t* choice, void* stream);
 
+/* Prototype-bank builder (reference models/proto_refiner.py:359-378 `_compute_protos_for_cell`, the arithmetic of
+ * `load_prototypes`): data_views f32 [N, V, D] training embeddings (V = 4 for panoramas, 1 otherwise)
+ *   -> data_mean_out f32 [N, D]  (view mean, what `data_emb` of pg_refiner_bank holds)
+ *   -> proto_emb_out f32 [P, D]  (mean over member_idx[member_off[p] .. member_off[p+1]) of data_mean rows). */
+int pg_bank_build(const float* data_views, int64_t N, int32_t V, int32_t D, const int64_t* member_off,
+                  const int64_t* member_idx, int64_t P, float* data_mean_out, float* proto_emb_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Per-launch device timing (measurement aid for bench.py; not part of the reference-facing surface).
  * begin: subsequent launches of this library are bracketed with CUDA events on their launch stream;

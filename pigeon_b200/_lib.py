@@ -59,6 +59,7 @@ SIGNATURES = {
     "pg_refiner_forward": (c_int32, [C.POINTER(RefinerBank), c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
                                      c_int32, c_int32, c_float, c_double, c_void_p, c_size_t, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pg_bank_build": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "pg_profile_begin": (None, []),
     "pg_profile_end": (c_int32, []),
     "pg_profile_read": (None, [C.POINTER(C.c_char_p), C.POINTER(c_float), C.POINTER(c_int32), c_int32]),

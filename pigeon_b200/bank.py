@@ -39,13 +39,28 @@ def bank_from_arrays(proto_cell: np.ndarray, proto_lnglat: np.ndarray, proto_ind
     member_off = np.concatenate([[0], np.cumsum(member_len)]).astype(np.int64)
     member_idx = np.fromiter((i for r in rows for i in proto_indices[r]), np.int64, count=int(member_off[-1]))
     emb = torch.as_tensor(data_emb).to(device=device, dtype=torch.float32)
-    if emb.dim() == 3:
-        emb = emb.mean(dim=1)                                            # :370-371
-    # prototype embedding = mean over members (:373), segment by segment on `device`
-    seg = torch.repeat_interleave(torch.arange(len(rows), device=emb.device), torch.as_tensor(member_len, device=emb.device))
-    sums = torch.zeros((len(rows), emb.shape[1]), dtype=torch.float32, device=emb.device)
-    sums.index_add_(0, seg, emb[torch.as_tensor(member_idx, device=emb.device)])
-    proto_emb = (sums / torch.as_tensor(member_len, device=emb.device, dtype=torch.float32)[:, None])
+    if emb.is_cuda:
+        # GPU builder (pg_bank_build): view mean + one warp per prototype segmented mean
+        from ._lib import check, current_stream_ptr, load, ptr
+        views = (emb if emb.dim() == 3 else emb.unsqueeze(1)).contiguous()
+        n, v, d = views.shape
+        mo = torch.as_tensor(member_off, device=emb.device)
+        mi = torch.as_tensor(member_idx, device=emb.device)
+        if mi.numel() == 0:
+            mi = torch.zeros(1, dtype=torch.int64, device=emb.device)
+        mean = torch.empty((n, d), dtype=torch.float32, device=emb.device)
+        proto_emb = torch.empty((len(rows), d), dtype=torch.float32, device=emb.device)
+        check(load().pg_bank_build(ptr(views), n, v, d, ptr(mo), ptr(mi), len(rows), ptr(mean), ptr(proto_emb),
+                                   current_stream_ptr()), "pg_bank_build")
+        emb = mean
+    else:
+        # host restatement of the same cold path (CPU-only boxes: fixtures and tests)
+        if emb.dim() == 3:
+            emb = emb.mean(dim=1)                                        # :370-371
+        seg = torch.repeat_interleave(torch.arange(len(rows)), torch.as_tensor(member_len))
+        sums = torch.zeros((len(rows), emb.shape[1]), dtype=torch.float32)
+        sums.index_add_(0, seg, emb[torch.as_tensor(member_idx)])
+        proto_emb = sums / torch.as_tensor(member_len, dtype=torch.float32)[:, None]   # mean over members (:373)
     return dict(cell_off=cell_off, proto_emb=proto_emb.cpu().numpy(),
                 proto_lnglat=np.asarray(proto_lnglat, np.float64)[rows].astype(np.float32),
                 proto_count=member_len.astype(np.int32), member_off=member_off, member_idx=member_idx,

@@ -273,6 +273,18 @@ int pg_refiner_forward(const pg_refiner_bank* bank, const float* emb, int64_t B,
                           choice, stream);
 }
 
+int pg_bank_build(const float* data_views, int64_t N, int32_t V, int32_t D, const int64_t* member_off,
+                  const int64_t* member_idx, int64_t P, float* data_mean_out, float* proto_emb_out, void* stream) {
+  if (!data_views || !member_off || !member_idx || !data_mean_out || !proto_emb_out || N <= 0 || V <= 0 || D <= 0 || P < 0) {
+    set_last_error("pg_bank_build: bad argument"); return 1;
+  }
+  const int sms = sm_count();
+  if (sms < 0) return 1;
+  return bank_build(data_views, N, V, D, reinterpret_cast<const long long*>(member_off),
+                    reinterpret_cast<const long long*>(member_idx), P, data_mean_out, proto_emb_out, sms,
+                    reinterpret_cast<cudaStream_t>(stream));
+}
+
 // ---------------------------------------------------------------------------------------------- profiler
 void pg_profile_begin(void) { prof_begin(); }
 int pg_profile_end(void) { return prof_end(); }

@@ -381,6 +381,30 @@ cell_major_scan_kernel(const RefinerBank bank, const float* __restrict__ q, cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Bank builder (reference models/proto_refiner.py:359-378, `_compute_protos_for_cell`): prototype embedding = mean of its
+// members' embeddings (members' 4-view mean first).  One warp per prototype, lanes strided over D as float4.
+// ------------------------------------------------------------------------------------------------
+__global__ void proto_mean_kernel(const float* __restrict__ data_emb, const long long* __restrict__ member_off,
+                                  const long long* __restrict__ member_idx, long P, int D,
+                                  float* __restrict__ proto_emb) {
+  const int lane = threadIdx.x & 31;
+  const long warps = ((long)gridDim.x * blockDim.x) >> 5;
+  const int d4 = D >> 2;
+  for (long p = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < P; p += warps) {
+    const long lo = member_off[p], hi = member_off[p + 1];
+    const float inv = 1.0f / (float)(hi - lo);
+    for (int c = lane; c < d4; c += 32) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (long mi = lo; mi < hi; ++mi) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(data_emb + member_idx[mi] * D) + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      reinterpret_cast<float4*>(proto_emb + p * D)[c] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    }
+  }
+}
+
 // NaN ranks above everything, first index wins ties (torch.argmax).
 __device__ __forceinline__ bool better(float v, float bv) {
   const bool vn = isnan(v), bn = isnan(bv);
@@ -520,6 +544,18 @@ int refiner_scan_cell_major(const RefinerBank& bank, const float* q, const long 
       return 1;
   }
   return check_launch("refiner_scan_cell_major");
+}
+
+int bank_build(const float* data_views, long N, int V, int D, const long long* member_off, const long long* member_idx,
+               long P, float* data_mean, float* proto_emb, int num_sms, cudaStream_t stream) {
+  if (D % 4) { set_last_error("bank_build: D=%d not a multiple of 4", D); return 1; }
+  if (refiner_pool(data_views, data_mean, N, V, D, stream)) return 1;
+  if (P == 0) return 0;
+  long blocks = (P + 7) / 8;
+  if (blocks > (long)num_sms * 16) blocks = (long)num_sms * 16;
+  ProfScope prof("bank_proto_mean", stream);
+  proto_mean_kernel<<<(int)blocks, 256, 0, stream>>>(data_mean, member_off, member_idx, P, D, proto_emb);
+  return check_launch("bank_proto_mean");
 }
 
 int refiner_finalize(const float* best_logit, const float* best_lnglat, const long long* cand, const float* cand_prob,

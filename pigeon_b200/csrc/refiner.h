@@ -27,6 +27,9 @@ size_t refiner_sort_workspace_bytes(int num_cells, long pairs);
 int refiner_scan_cell_major(const RefinerBank& bank, const float* q, const long long* cand, int cand_stride, long B,
                             int topk, void* sort_ws, float* best_logit, float* best_lnglat, int* best_proto,
                             int num_sms, cudaStream_t stream);
+// data_views [N, V, D] -> data_mean [N, D] (view mean) and proto_emb [P, D] (mean of member rows of data_mean)
+int bank_build(const float* data_views, long N, int V, int D, const long long* member_off, const long long* member_idx,
+               long P, float* data_mean, float* proto_emb, int num_sms, cudaStream_t stream);
 int refiner_finalize(const float* best_logit, const float* best_lnglat, const long long* cand, const float* cand_prob,
                      int cand_stride, const double* init_lnglat, long B, int topk, float temperature,
                      double max_refinement, float* out_lnglat, long long* out_cell, int* out_choice,

@@ -182,3 +182,24 @@ def test_evaluate_model_loop_matches_direct_calls(cuda):
     assert np.array_equal(res["preds_geocell"], out.preds_geocell.cpu().numpy())
     assert np.array_equal(res["top_geocells"], out.top5_geocells.indices.cpu().numpy())
     np.testing.assert_allclose(res["loss"], out.loss.item(), rtol=1e-5)
+
+
+def test_bank_builder_matches_reference_prototypes(cuda):
+    """pg_bank_build (GPU segmented mean) == the prototype embeddings the reference constructor computed
+    (`_compute_protos_for_cell`, proto_refiner.py:359-378; packed into the golden by oracle/make_golden.py)."""
+    from pigeon_b200 import bank as bank_mod
+    z, meta = load("refiner_members")
+    off, idx = z["bank_member_off"], z["bank_member_idx"]
+    P = len(off) - 1
+    cells = np.searchsorted(z["bank_cell_off"], np.arange(P), side="right") - 1
+    indices = [idx[off[p]:off[p + 1]].tolist() for p in range(P)]
+    # 4-view training embeddings whose view mean is the stored data_emb (two +/- perturbations cancel exactly in fp32)
+    e = torch.from_numpy(z["bank_data_emb"])
+    d1 = torch.randn(e.shape, generator=torch.Generator().manual_seed(3)) * 0.01
+    views = torch.stack([e + d1, e - d1, e + 0.5 * d1, e - 0.5 * d1], dim=1)
+    b = bank_mod.bank_from_arrays(cells, z["bank_proto_lnglat"], indices, views, z["bank_data_lnglat"],
+                                  num_cells=len(z["bank_cell_off"]) - 1, device=cuda)
+    assert np.array_equal(b["cell_off"], z["bank_cell_off"]) and np.array_equal(b["member_idx"], idx)
+    np.testing.assert_allclose(b["data_emb"], z["bank_data_emb"], rtol=2e-6, atol=2e-7)
+    np.testing.assert_allclose(b["proto_emb"], z["bank_proto_emb"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(b["proto_count"], z["bank_proto_count"])
