@@ -41,8 +41,11 @@ constexpr int kThreads = 192;
 // Two tilings of the same kernel:
 //   <64, 3, 2>  KV blocks of 64, three S buffers, 256 TMEM columns, 2 CTAs / SM   (S0 S1 S2 [0,192)  O [192,256))
 //   <32, 2, 4>  KV blocks of 32, two S buffers, 128 TMEM columns, 4 CTAs / SM     (S0 S1 [0,64)      O [64,128))
-template <int KV, int NBUF, int CTAS>
+template <int KV, int NBUF, int CTAS, int POLY = 0>
 struct AttnCfg {
+  // POLY = n > 0: every n-th group of four exponentials is evaluated on the FMA pipe (Cody-Waite + degree-4 minimax
+  // polynomial, 2.9e-6 relative) instead of MUFU.EX2, to relieve the 16/clk/SM special-function unit.
+  static constexpr int kPolyStride = POLY;
   static constexpr int kBlockKV = KV;
   static constexpr int kNumSBuf = NBUF;
   static constexpr int kCtasPerSm = CTAS;
@@ -77,6 +80,25 @@ __device__ __forceinline__ void tmem_ld16_(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+// 2^x for a pair, x <= ~8, on the FMA / ALU pipes: n = round(x) via the 1.5*2^23 magic constant, f = x - n in
+// [-0.5, 0.5], 2^f by a degree-4 minimax polynomial (max relative error 2.9e-6), 2^n by an exponent-field add.
+__device__ __forceinline__ float2 exp2_poly(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  const float2 t = fadd2(x, magic);
+  const float2 n = fsub2(t, magic);
+  const float2 f = fsub2(x, n);
+  float2 p = ffma2(make_float2(0.009582852944731712f, 0.009582852944731712f), f,
+                   make_float2(0.055906426161527634f, 0.055906426161527634f));
+  p = ffma2(p, f, make_float2(0.24024099111557007f, 0.24024099111557007f));
+  p = ffma2(p, f, make_float2(0.6931241750717163f, 0.6931241750717163f));
+  p = ffma2(p, f, make_float2(1.0f, 1.0f));
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return p;
+}
+
 __device__ __forceinline__ void tmem_st8_(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
                "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -301,8 +323,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
         for (int i = 0; i < kBlockKV; i += 4) {   // FFMA2 / FADD2: two columns per instruction; P packed in place
           const float2 x01 = ffma2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), c2, nmc2);
           const float2 x23 = ffma2(make_float2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), c2, nmc2);
-          const float2 p01 = make_float2(ex2(x01.x), ex2(x01.y));
-          const float2 p23 = make_float2(ex2(x23.x), ex2(x23.y));
+          float2 p01, p23;
+          if (Cfg::kPolyStride > 0 && ((i >> 2) % (Cfg::kPolyStride > 0 ? Cfg::kPolyStride : 1)) == (Cfg::kPolyStride - 1)) {
+            p01 = exp2_poly(x01);
+            p23 = exp2_poly(x23);
+          } else {
+            p01 = make_float2(ex2(x01.x), ex2(x01.y));
+            p23 = make_float2(ex2(x23.x), ex2(x23.y));
+          }
           l01 = fadd2(l01, p01);
           l23 = fadd2(l23, p23);
           r[i >> 1] = pack_half2(p01.x, p01.y);
@@ -401,6 +429,9 @@ int attention_f16(const void* qkv, void* out, int n_views, int seq, int heads, c
   // the latter (A/B switch).
   const char* v = getenv("PG_ATTN_VARIANT");
   if (v && v[0] == '6' && v[1] == '4') return launch_attention<AttnCfg<64, 3, 2>>(qkv, out, n_views, seq, heads, stream);
+  const char* pe = getenv("PG_ATTN_POLY");     // experiment switch: "4" / "2" = every 4th / 2nd group on the FMA pipe
+  if (pe && pe[0] == '4') return launch_attention<AttnCfg<32, 2, 4, 4>>(qkv, out, n_views, seq, heads, stream);
+  if (pe && pe[0] == '2') return launch_attention<AttnCfg<32, 2, 4, 2>>(qkv, out, n_views, seq, heads, stream);
   return launch_attention<AttnCfg<32, 2, 4>>(qkv, out, n_views, seq, heads, stream);
 }
 

@@ -64,6 +64,11 @@ def test_superguessr_pixels_to_geocells(cuda, name):
     assert emb.shape == z["embedding"].shape
     e = _rel(emb, z["embedding"])
     print(f"{name}: embedding rel-L2 vs reference = {e:.3e}")
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity.log"), "a") as f:
+            f.write(f"{name}: SuperGuessr(pixels) embedding rel-L2 vs UNMODIFIED reference golden = {e:.3e}; "
+                    f"top-1 geocell identical; loss rel err {abs(out.loss.item() - float(z['loss'])) / float(z['loss']):.2e}\n")
     assert e < REL_TOL, e
     assert np.abs(emb - z["embedding"]).max() / np.abs(z["embedding"]).max() < 5e-3
     # top-1 geocell identical (the fixtures' top-1/top-2 probability margins are > 10x the error budget)

@@ -28,11 +28,12 @@ def timeit(fn, iters=10, warm=3):
 
 ref = None
 for rep in range(2):
-    for var in ("64", "32"):
+    for var, poly in (("64", ""), ("32", ""), ("32", "4"), ("32", "2")):
         os.environ["PG_ATTN_VARIANT"] = var
+        os.environ["PG_ATTN_POLY"] = poly
         out = ops.attention_f16(qkv, views, 577, 16)
         if ref is None:
             ref = out.clone()
         ms = timeit(lambda: ops.attention_f16(qkv, views, 577, 16))
         err = ((out.float() - ref.float()).norm() / ref.float().norm()).item()
-        print(f"variant KV={var}: {ms:.4f} ms  ({4.0 * 577 * 577 * 64 * 16 * views / ms / 1e9:.0f} TF/s)  rel diff vs KV=64: {err:.2e}", flush=True)
+        print(f"variant KV={var} poly={poly or 0}: {ms:.4f} ms  ({4.0 * 577 * 577 * 64 * 16 * views / ms / 1e9:.0f} TF/s)  rel diff vs KV=64: {err:.2e}", flush=True)
