@@ -107,6 +107,26 @@ int pg_head_loss(const float* logits, int32_t B, int32_t C, int32_t mode, const 
                  double* per_sample, double* loss_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Fine-tune step, head-only part ("next" row N1 with a frozen or absent base model): what loss.backward() and
+ * torch.optim.AdamW.step() do for cell_layer in reference training/train_eval_loop.py:187,215-221.
+ * ------------------------------------------------------------------------------------------------- */
+/* pg_head_loss plus its gradient: dlogits f32 [B, C] = grad_scale / B * (softmax(logits) * sum_c(target) - target)
+ * (the backward of CrossEntropyLoss(reduction='mean') at super_guessr.py:474 for index, soft or smoothed targets). */
+int pg_head_loss_grad(const float* logits, int32_t B, int32_t C, int32_t mode, const int64_t* labels_idx,
+                      const float* soft, const double* labels_lnglat, const double* centroids, double smoothing_km,
+                      double grad_scale, double* per_sample, double* loss_out, float* dlogits, void* stream);
+/* Backward of cell_layer (nn.Linear, super_guessr.py:447) in fp32:
+ *   dw f32 [C, D] (+)= dlogits^T . pooled;  db f32 [C] (+)= column sums of dlogits;  dpooled f32 [B, D] = dlogits . w.
+ * Any of dw / db / dpooled may be NULL; `accumulate` != 0 adds into dw/db (gradient accumulation, :218-221). */
+int pg_head_backward(const float* dlogits, const float* pooled, const float* w, int32_t B, int32_t C, int32_t D,
+                     int32_t accumulate, float* dw, float* db, float* dpooled, void* stream);
+/* torch.optim.AdamW single-tensor update on a flat fp32 parameter (amsgrad = maximize = False), `step` counts from 1;
+ * grad is read as grad * grad_scale (1/world_size after a summing all-reduce). */
+int pg_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                  double beta1, double beta2, double eps, double weight_decay, int64_t step, double grad_scale,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * ProtoRefiner (reference models/proto_refiner.py:121-255, 332-357; preprocessing/geo_utils.py:40-55)
  * ------------------------------------------------------------------------------------------------- */
 typedef struct pg_refiner_bank {

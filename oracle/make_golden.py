@@ -93,6 +93,50 @@ def head_fixture(tmp):
              labels_clf=labels_clf.numpy(), meta=json.dumps(dict(C=C, D=D, w_seed=21, cells_seed=0)), **out)
 
 
+def train_fixture(tmp):
+    """Head-only fine-tune steps through the UNMODIFIED reference module + torch.optim.AdamW, the way
+    training/train_eval_loop.py:187,215-221 drives it (model.train(); loss.backward(); gradient accumulation;
+    optimizer.step(); optimizer.zero_grad()) with base_model=None (training on embeddings, train_modes on_embeddings)."""
+    from models.super_guessr import SuperGuessr
+    C, D, B, steps, acc, lr = 1000, 128, 8, 3, 2, 1e-3
+    W, b = head_weights(C, D, seed=71)
+    g = torch.Generator().manual_seed(72)
+    emb = torch.randn(steps * acc, B, 4, D, generator=g) * 0.5
+    labels = torch.tensor(np.stack([synthetic.synthetic_geocells(B, 80 + i) for i in range(steps * acc)]))
+    labels_clf = torch.randint(0, C, (steps * acc, B), generator=g)
+    out = {}
+    with rs.chdir(tmp):
+        for name, smooth in (("smooth", True), ("index", False)):
+            sg = SuperGuessr(None, panorama=True, num_candidates=5, should_smooth_labels=smooth, embed_dim=D).train()
+            with torch.no_grad():
+                sg.cell_layer.weight.copy_(W)
+                sg.cell_layer.bias.copy_(b)
+            opt = torch.optim.AdamW(sg.parameters(), lr=lr)                       # train_eval_loop.py:187
+            opt.zero_grad()
+            losses = []
+            for i in range(steps * acc):
+                o = sg(embedding=emb[i], labels=labels[i], labels_clf=labels_clf[i])
+                o.loss.backward()
+                losses.append(float(o.loss))
+                if i % acc == acc - 1:                                            # :218-221
+                    if i == acc - 1:
+                        out[f"{name}_grad_w_step1"] = sg.cell_layer.weight.grad.detach().numpy().copy()
+                        out[f"{name}_grad_b_step1"] = sg.cell_layer.bias.grad.detach().numpy().copy()
+                    opt.step()
+                    opt.zero_grad()
+                    if i == acc - 1:
+                        out[f"{name}_w_step1"] = sg.cell_layer.weight.detach().numpy().copy()
+                        out[f"{name}_b_step1"] = sg.cell_layer.bias.detach().numpy().copy()
+            out[f"{name}_losses"] = np.asarray(losses, dtype=np.float64)
+            out[f"{name}_w_final"] = sg.cell_layer.weight.detach().numpy().copy()
+            out[f"{name}_b_final"] = sg.cell_layer.bias.detach().numpy().copy()
+            out["centroids"] = sg.lla_geocells.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "train_head.npz"), emb=emb.numpy(), labels=labels.numpy(),
+                        labels_clf=labels_clf.numpy(), w0=W.numpy(), b0=b.numpy(),
+                        meta=json.dumps(dict(C=C, D=D, B=B, steps=steps, acc=acc, lr=lr, betas=[0.9, 0.999], eps=1e-8,
+                                             weight_decay=0.01)), **out)
+
+
 def vit_fixture(tmp, name, dims: VitDims, sd_seed, n_samples, panorama, px_seed, std):
     """pixel_values -> reference SuperGuessr(HF CLIPVisionModel.base_model) -> ModelOutput; plus CLIPEmbedding."""
     from models.clip_embedder import CLIPEmbedding
@@ -239,8 +283,14 @@ def main():
     pd.DataFrame({"lng": cells[:, 0], "lat": cells[:, 1]}).to_csv(os.path.join(tmp, "data", "geocells_2203.csv"), index=False)
     rs.install()
     torch.set_num_threads(os.cpu_count())
+    only = set(sys.argv[1:])          # e.g. `python -m oracle.make_golden train` regenerates one family
+    if only:
+        if "train" in only:
+            train_fixture(tmp)
+        return
     geo_fixture()
     head_fixture(tmp)
+    train_fixture(tmp)
     small = VitDims(image_size=56, patch_size=14, hidden=256, heads=4, intermediate=512, layers=2)
     vit_fixture(tmp, "vit_small", small, sd_seed=41, n_samples=3, panorama=True, px_seed=42, std=0.05)
     vit_fixture(tmp, "vit_large_single", VitDims(), sd_seed=0, n_samples=1, panorama=False, px_seed=1, std=0.02)

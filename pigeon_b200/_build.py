@@ -28,6 +28,7 @@ SOURCES = [
     "vit_misc.cu",
     "head.cu",
     "refiner.cu",
+    "train.cu",
     "capi.cu",
 ]
 

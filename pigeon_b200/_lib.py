@@ -55,6 +55,12 @@ SIGNATURES = {
                                   c_void_p, c_void_p]),
     "pg_head_loss": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                                c_void_p, c_void_p, c_void_p]),
+    "pg_head_loss_grad": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
+                                    c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pg_head_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
+    "pg_adamw_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double,
+                                c_double, c_int64, c_double, c_void_p]),
     "pg_refiner_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
     "pg_refiner_forward": (c_int32, [C.POINTER(RefinerBank), c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
                                      c_int32, c_int32, c_float, c_double, c_void_p, c_size_t, c_void_p, c_void_p,

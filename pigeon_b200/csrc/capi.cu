@@ -15,6 +15,7 @@
 #include "head.h"
 #include "refiner.h"
 #include "tma_host.h"
+#include "train.h"
 #include "vit_misc.h"
 
 using namespace pg;
@@ -206,7 +207,41 @@ int pg_head_loss(const float* logits, int32_t B, int32_t C, int32_t mode, const 
                  double* loss_out, void* stream) {
   if (!logits || !per_sample || !loss_out || B <= 0 || C <= 0) { set_last_error("pg_head_loss: bad argument"); return 1; }
   return ce_loss(logits, B, C, mode, reinterpret_cast<const long long*>(labels_idx), soft, labels_lnglat, centroids,
-                 smoothing_km, per_sample, loss_out, reinterpret_cast<cudaStream_t>(stream));
+                 smoothing_km, per_sample, loss_out, nullptr, 1.0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pg_head_loss_grad(const float* logits, int32_t B, int32_t C, int32_t mode, const int64_t* labels_idx,
+                      const float* soft, const double* labels_lnglat, const double* centroids, double smoothing_km,
+                      double grad_scale, double* per_sample, double* loss_out, float* dlogits, void* stream) {
+  if (!logits || !per_sample || !loss_out || !dlogits || B <= 0 || C <= 0) {
+    set_last_error("pg_head_loss_grad: bad argument");
+    return 1;
+  }
+  return ce_loss(logits, B, C, mode, reinterpret_cast<const long long*>(labels_idx), soft, labels_lnglat, centroids,
+                 smoothing_km, per_sample, loss_out, dlogits, grad_scale, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pg_head_backward(const float* dlogits, const float* pooled, const float* w, int32_t B, int32_t C, int32_t D,
+                     int32_t accumulate, float* dw, float* db, float* dpooled, void* stream) {
+  if (!dlogits || B <= 0 || C <= 0 || D <= 0) { set_last_error("pg_head_backward: bad argument"); return 1; }
+  if ((dw && !pooled) || (dpooled && !w)) { set_last_error("pg_head_backward: missing operand"); return 1; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // dW[c, d] = sum_b dlogits[b, c] * pooled[b, d];  db[c] = sum_b dlogits[b, c];  dpooled = dlogits . W
+  if (dw && sgemm_f32(true, dlogits, pooled, dw, C, D, B, accumulate ? 1.f : 0.f, st)) return 1;
+  if (db && column_sum_f32(dlogits, db, B, C, accumulate ? 1.f : 0.f, st)) return 1;
+  if (dpooled && sgemm_f32(false, dlogits, w, dpooled, B, D, C, 0.f, st)) return 1;
+  return 0;
+}
+
+int pg_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                  double beta1, double beta2, double eps, double weight_decay, int64_t step, double grad_scale,
+                  void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) {
+    set_last_error("pg_adamw_step: bad argument");
+    return 1;
+  }
+  return adamw_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                    reinterpret_cast<cudaStream_t>(stream));
 }
 
 // ---------------------------------------------------------------------------------------------- refiner

@@ -173,7 +173,8 @@ __device__ __forceinline__ double haversine_km(double lng0, double lat0, double 
 __global__ void __launch_bounds__(256)
 ce_loss_kernel(const float* __restrict__ logits, int C, int mode, const long long* __restrict__ labels_idx,
                const float* __restrict__ soft, const double* __restrict__ labels_lnglat,
-               const double* __restrict__ centroids, double smoothing, double* __restrict__ per_sample) {
+               const double* __restrict__ centroids, double smoothing, double* __restrict__ per_sample,
+               float* __restrict__ dlogits, double grad_scale) {
   __shared__ double red[8];
   const int b = blockIdx.x, tid = threadIdx.x;
   const float* x = logits + (long)b * C;
@@ -185,10 +186,25 @@ ce_loss_kernel(const float* __restrict__ logits, int C, int mode, const long lon
   s = block_reduce(s, red, false);
   const double lse = m + log(s);
   double loss = 0;
+  // backward (dlogits != nullptr): d loss_b / d x_c = softmax_c * sum_c'(t_c') - t_c, times grad_scale
+  float* g = dlogits ? dlogits + (long)b * C : nullptr;
   if (mode == 0) {
-    if (tid == 0) loss = lse - (double)x[labels_idx[b]];
+    const long long y = labels_idx[b];
+    if (tid == 0) loss = lse - (double)x[y];
+    if (g)
+      for (int c = tid; c < C; c += 256) g[c] = (float)(grad_scale * (exp((double)x[c] - lse) - (c == y ? 1.0 : 0.0)));
   } else if (mode == 1) {
-    for (int c = tid; c < C; c += 256) loss += (double)soft[(long)b * C + c] * (lse - (double)x[c]);
+    double tsum = 0;
+    for (int c = tid; c < C; c += 256) {
+      const double t = (double)soft[(long)b * C + c];
+      loss += t * (lse - (double)x[c]);
+      tsum += t;
+    }
+    if (g) {
+      tsum = block_reduce(tsum, red, false);
+      for (int c = tid; c < C; c += 256)
+        g[c] = (float)(grad_scale * (exp((double)x[c] - lse) * tsum - (double)soft[(long)b * C + c]));
+    }
   } else {
     const double lng = labels_lnglat[2 * b], lat = labels_lnglat[2 * b + 1];
     double dmin = INFINITY;
@@ -198,6 +214,14 @@ ce_loss_kernel(const float* __restrict__ logits, int C, int mode, const long lon
       double t = exp(-(haversine_km(lng, lat, centroids[2 * c], centroids[2 * c + 1]) - dmin) / smoothing);
       if (isnan(t) || isinf(t)) t = 0;
       loss += t * (lse - (double)x[c]);
+      if (g) g[c] = (float)t;            // parked; turned into the gradient below once sum(t) is known
+    }
+    if (g) {
+      double tsum = 0;
+      for (int c = tid; c < C; c += 256) tsum += (double)g[c];   // same thread wrote these entries
+      tsum = block_reduce(tsum, red, false);
+      for (int c = tid; c < C; c += 256)
+        g[c] = (float)(grad_scale * (exp((double)x[c] - lse) * tsum - (double)g[c]));
     }
   }
   loss = block_reduce(loss, red, false);
@@ -254,7 +278,7 @@ int softmax_topk(const float* logits, float* probs, long long* pred_cell, double
 
 int ce_loss(const float* logits, int B, int C, int mode, const long long* labels_idx, const float* soft,
             const double* labels_lnglat, const double* centroids, double smoothing, double* per_sample,
-            double* loss_out, cudaStream_t stream) {
+            double* loss_out, float* dlogits, double grad_scale, cudaStream_t stream) {
   if (mode < 0 || mode > 2) { set_last_error("ce_loss: bad mode %d", mode); return 1; }
   if ((mode == 0 && !labels_idx) || (mode == 1 && !soft) || (mode == 2 && (!labels_lnglat || !centroids))) {
     set_last_error("ce_loss: missing labels for mode %d", mode);
@@ -262,7 +286,7 @@ int ce_loss(const float* logits, int B, int C, int mode, const long long* labels
   }
   ProfScope prof("head_ce_loss", stream);
   ce_loss_kernel<<<B, 256, 0, stream>>>(logits, C, mode, labels_idx, soft, labels_lnglat, centroids, smoothing,
-                                        per_sample);
+                                        per_sample, dlogits, grad_scale / B);
   if (check_launch("ce_loss")) return 1;
   mean_f64_kernel<<<1, 256, 0, stream>>>(per_sample, B, loss_out);
   return check_launch("ce_loss_mean");

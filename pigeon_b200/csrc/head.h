@@ -11,6 +11,6 @@ int softmax_topk(const float* logits, float* probs, long long* pred_cell, double
 
 int ce_loss(const float* logits, int B, int C, int mode, const long long* labels_idx, const float* soft,
             const double* labels_lnglat, const double* centroids, double smoothing, double* per_sample,
-            double* loss_out, cudaStream_t stream);
+            double* loss_out, float* dlogits, double grad_scale, cudaStream_t stream);
 
 }  // namespace pg
