@@ -107,6 +107,24 @@ int pg_head_loss(const float* logits, int32_t B, int32_t C, int32_t mode, const 
                  double* per_sample, double* loss_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Image pre-processing ("next" row N2): what `CLIPProcessor.from_pretrained(CLIP_MODEL)(images=...)` does on the
+ * CPU per item in reference dataset_creation/finetune/embed_dataset.py:17-22, preprocessing/dataset_preprocessing.py:
+ * 182-204, dataset_creation/benchmark/benchmark_dataset.py:100-104 (transformers 4.23.1 CLIPFeatureExtractor over
+ * Pillow): resize shortest edge to `size` (BICUBIC) -> center crop -> /255 -> (x - mean) / std, channel first.
+ * Bit-exact with Pillow's fixed-point resampler (uint8 stage) and with numpy float32 (normalisation).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct pg_image {
+  const uint8_t* data;  /* DEVICE pointer, RGB interleaved (H x W x 3) */
+  int32_t height, width;
+  int64_t row_stride;   /* bytes between rows, >= 3 * width */
+} pg_image;
+/* `images` is a HOST array of n descriptors.  0 on error (see pg_last_error). */
+size_t pg_preprocess_workspace_bytes(const pg_image* images, int32_t n, int32_t size);
+/* out: [n, 3, size, size] f32 (out_f16 = 0) or f16 (out_f16 = 1, round-to-nearest of the f32 value); mean/std: host float[3]. */
+int pg_preprocess_clip(const pg_image* images, int32_t n, int32_t size, const float* mean, const float* std,
+                       void* workspace, size_t workspace_bytes, void* out, int32_t out_f16, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Fine-tune step, head-only part ("next" row N1 with a frozen or absent base model): what loss.backward() and
  * torch.optim.AdamW.step() do for cell_layer in reference training/train_eval_loop.py:187,215-221.
  * ------------------------------------------------------------------------------------------------- */

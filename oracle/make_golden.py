@@ -8,6 +8,7 @@ them bit-identically (torch CPU generator), so the files stay small.
 """
 from __future__ import annotations
 
+import hashlib
 import json
 import os
 import sys
@@ -135,6 +136,40 @@ def train_fixture(tmp):
                         labels_clf=labels_clf.numpy(), w0=W.numpy(), b0=b.numpy(),
                         meta=json.dumps(dict(C=C, D=D, B=B, steps=steps, acc=acc, lr=lr, betas=[0.9, 0.999], eps=1e-8,
                                              weight_decay=0.01)), **out)
+
+
+def preprocess_fixture():
+    """Images through the third-party code the reference calls for pre-processing: Pillow's BICUBIC resize and the
+    PIL-backend CLIP image processor of the transformers installed here (the pinned 4.23.1 CLIPFeatureExtractor is the
+    same pipeline; its formulas are restated in oracle/preprocess.py).  Smooth synthetic photos + noise, several aspect
+    ratios, one up-scaling case, one that needs no resize."""
+    from PIL import Image
+    from transformers import CLIPImageProcessorPil
+    from oracle import preprocess as op
+    proc = CLIPImageProcessorPil(do_resize=True, size={"shortest_edge": 336}, resample=3, do_center_crop=True,
+                                 crop_size={"height": 336, "width": 336}, do_rescale=True, rescale_factor=1 / 255,
+                                 do_normalize=True, image_mean=list(op.CLIP_MEAN), image_std=list(op.CLIP_STD),
+                                 do_convert_rgb=True)
+    out = {}
+    shapes = [(480, 640), (500, 375), (150, 210), (336, 400), (900, 1300)]
+    for i, (h, w) in enumerate(shapes):
+        img = synthetic.synthetic_photo(h, w, seed=91 + i)        # integer-only generator: regenerated by the tests
+        pil = Image.fromarray(img)
+        nh, nw = op.resized_shape(h, w)
+        resized = np.asarray(pil.resize((nw, nh), resample=Image.BICUBIC))
+        top, left = (nh - 336) // 2, (nw - 336) // 2
+        crop = resized[top:top + 336, left:left + 336]
+        px = proc(images=pil, return_tensors="np")["pixel_values"][0]
+        assert np.array_equal(px, op.clip_preprocess(img)), "restated pipeline != HF PIL-backend processor"
+        assert np.array_equal(crop, op.clip_preprocess(img, return_u8=True)[1])
+        sha = lambda a: np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+        out[f"img{i}_sha"] = sha(img)
+        out[f"crop{i}_sha"] = sha(crop)                       # uint8 stage (Pillow), full tensor
+        out[f"px{i}_sha"] = sha(px)                           # float32 stage (HF PIL-backend processor), full tensor
+        out[f"crop{i}_sample"] = crop[::6].copy()
+        out[f"px{i}_sample"] = px[:, ::12, ::7].copy()
+    out["shapes"] = np.asarray(shapes)
+    np.savez_compressed(os.path.join(OUT, "preprocess.npz"), **out)
 
 
 def vit_fixture(tmp, name, dims: VitDims, sd_seed, n_samples, panorama, px_seed, std):
@@ -287,10 +322,13 @@ def main():
     if only:
         if "train" in only:
             train_fixture(tmp)
+        if "preprocess" in only:
+            preprocess_fixture()
         return
     geo_fixture()
     head_fixture(tmp)
     train_fixture(tmp)
+    preprocess_fixture()
     small = VitDims(image_size=56, patch_size=14, hidden=256, heads=4, intermediate=512, layers=2)
     vit_fixture(tmp, "vit_small", small, sd_seed=41, n_samples=3, panorama=True, px_seed=42, std=0.05)
     vit_fixture(tmp, "vit_large_single", VitDims(), sd_seed=0, n_samples=1, panorama=False, px_seed=1, std=0.02)

@@ -29,6 +29,7 @@ SOURCES = [
     "head.cu",
     "refiner.cu",
     "train.cu",
+    "preprocess.cu",
     "capi.cu",
 ]
 

@@ -23,6 +23,10 @@ class VitConfig(C.Structure):
                 ("intermediate", c_int32), ("layers", c_int32), ("ln_eps", c_float), ("patch_k_pad", c_int32)]
 
 
+class Image(C.Structure):
+    _fields_ = [("data", c_void_p), ("height", c_int32), ("width", c_int32), ("row_stride", c_int64)]
+
+
 class VitLayer(C.Structure):
     _fields_ = [(n, c_void_p) for n in ("ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_g", "ln2_b",
                                         "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
@@ -55,6 +59,9 @@ SIGNATURES = {
                                   c_void_p, c_void_p]),
     "pg_head_loss": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                                c_void_p, c_void_p, c_void_p]),
+    "pg_preprocess_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32]),
+    "pg_preprocess_clip": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_int32,
+                                     c_void_p]),
     "pg_head_loss_grad": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                                     c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pg_head_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,

@@ -13,6 +13,7 @@
 #include "attention.h"
 #include "gemm.h"
 #include "head.h"
+#include "preprocess.h"
 #include "refiner.h"
 #include "tma_host.h"
 #include "train.h"
@@ -208,6 +209,16 @@ int pg_head_loss(const float* logits, int32_t B, int32_t C, int32_t mode, const 
   if (!logits || !per_sample || !loss_out || B <= 0 || C <= 0) { set_last_error("pg_head_loss: bad argument"); return 1; }
   return ce_loss(logits, B, C, mode, reinterpret_cast<const long long*>(labels_idx), soft, labels_lnglat, centroids,
                  smoothing_km, per_sample, loss_out, nullptr, 1.0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t pg_preprocess_workspace_bytes(const pg_image* images, int32_t n, int32_t size) {
+  return preprocess_workspace_bytes(images, n, size);
+}
+
+int pg_preprocess_clip(const pg_image* images, int32_t n, int32_t size, const float* mean, const float* stdv,
+                       void* workspace, size_t workspace_bytes, void* out, int32_t out_f16, void* stream) {
+  return preprocess_clip(images, n, size, mean, stdv, workspace, workspace_bytes, out, out_f16,
+                         reinterpret_cast<cudaStream_t>(stream));
 }
 
 int pg_head_loss_grad(const float* logits, int32_t B, int32_t C, int32_t mode, const int64_t* labels_idx,

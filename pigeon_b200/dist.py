@@ -17,6 +17,10 @@ def is_distributed() -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
+def world_size() -> int:
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous shard [lo, hi) of `total` samples for `rank` (remainder spread over the first ranks)."""
     base, rem = divmod(total, world)

@@ -265,44 +265,97 @@ class SuperGuessr(nn.Module):
 
     def _packed_head(self) -> Tensor:
         w = self.cell_layer.weight
-        key = (w.data_ptr(), w._version)
+        key = (w.data_ptr(), w._version, getattr(w, "_pg_version", 0))
         if self._w3 is None or self._w3_key != key:
             self._w3 = ops.head_pack_weight(w.detach())
             self._w3_key = key
         return self._w3
 
-    def _classification_loss(self, logits: Tensor, labels: Optional[Tensor], labels_clf: Tensor) -> Tensor:
-        """reference :456,468-474 on the GPU (pg_head_loss)."""
+    def _classification_loss(self, logits: Tensor, labels: Optional[Tensor], labels_clf: Tensor,
+                             want_grad: bool = False) -> Tensor:
+        """reference :456,468-474 on the GPU (pg_head_loss); with `want_grad` also d loss / d logits (pg_head_loss_grad),
+        kept in `self._saved_dlogits` for `backward()`."""
         B, Cc = logits.shape
         dev = logits.device
         per = torch.empty(B, dtype=torch.float64, device=dev)
         out = torch.empty(1, dtype=torch.float64, device=dev)
+        dlog = torch.empty((B, Cc), dtype=torch.float32, device=dev) if want_grad else None
         lib = load()
+
+        def run(mode, idx=None, soft=None, lab=None, cells=None, smoothing=0.0):
+            if want_grad:
+                check(lib.pg_head_loss_grad(ptr(logits), B, Cc, mode, ptr(idx), ptr(soft), ptr(lab), ptr(cells), smoothing,
+                                            1.0, ptr(per), ptr(out), ptr(dlog), current_stream_ptr()), "pg_head_loss_grad")
+            else:
+                check(lib.pg_head_loss(ptr(logits), B, Cc, mode, ptr(idx), ptr(soft), ptr(lab), ptr(cells), smoothing,
+                                       ptr(per), ptr(out), current_stream_ptr()), "pg_head_loss")
+
+        self._saved_dlogits = dlog
         if self.should_smooth_labels:
             lab = labels.to(device=dev, dtype=torch.float64).contiguous()
-            check(lib.pg_head_loss(ptr(logits), B, Cc, 2, None, None, ptr(lab), ptr(self.lla_geocells.data),
-                                   float(LABEL_SMOOTHING_CONSTANT), ptr(per), ptr(out), current_stream_ptr()), "pg_head_loss")
+            run(2, lab=lab, cells=self.lla_geocells.data, smoothing=float(LABEL_SMOOTHING_CONSTANT))
             return out[0]                                    # float64, like the reference's promoted soft-target CE
         if labels_clf.dim() == 0:                            # _to_one_hot (:298-313)
             labels_clf = labels_clf.reshape(1).expand(B)
         if labels_clf.dim() == 1:
-            idx = labels_clf.to(device=dev, dtype=torch.int64).contiguous()
-            check(lib.pg_head_loss(ptr(logits), B, Cc, 0, ptr(idx), None, None, None, 0.0, ptr(per), ptr(out),
-                                   current_stream_ptr()), "pg_head_loss")
+            run(0, idx=labels_clf.to(device=dev, dtype=torch.int64).contiguous())
         else:
-            soft = labels_clf.to(device=dev, dtype=torch.float32).contiguous()
-            check(lib.pg_head_loss(ptr(logits), B, Cc, 1, None, ptr(soft), None, None, 0.0, ptr(per), ptr(out),
-                                   current_stream_ptr()), "pg_head_loss")
+            run(1, soft=labels_clf.to(device=dev, dtype=torch.float32).contiguous())
         return out[0].to(torch.float32)
+
+    # ---------------------------------------------------------------------------------- fine-tune step (head only)
+    def _trainable_outside_head(self):
+        head = {id(self.cell_layer.weight), id(self.cell_layer.bias)}
+        return [n for n, p in self.named_parameters() if p.requires_grad and id(p) not in head]
+
+    def backward(self, loss: Optional[Tensor] = None, grad_scale: float = 1.0) -> None:
+        """What `accelerator.backward(output.loss)` does in reference training/train_eval_loop.py:216 for the
+        parameters this path trains: accumulates d loss / d cell_layer.{weight,bias} into `.grad` (pg_head_backward).
+        Under torch.distributed the micro-batch gradient is all-reduced and averaged first, like DDP (:192)."""
+        if getattr(self, "_saved_dlogits", None) is None or self.last_pooled is None:
+            raise PigeonB200Error("backward() needs a preceding training-mode forward with labels")
+        from . import dist as pdist
+        w, b = self.cell_layer.weight, self.cell_layer.bias
+        dlog, pooled = self._saved_dlogits, self.last_pooled
+        B, Cc = dlog.shape
+        D = pooled.shape[1]
+        if grad_scale != 1.0:
+            dlog = dlog * grad_scale
+        lib = load()
+        world = pdist.world_size()
+        fresh = w.grad is None
+        if fresh:                                             # one flat buffer -> one all-reduce for weight and bias
+            flat = torch.empty(Cc * D + Cc, dtype=torch.float32, device=dlog.device)
+            w.grad, b.grad = flat[: Cc * D].view(Cc, D), flat[Cc * D:]
+            self._flat_grad = flat
+        if world > 1:
+            scratch = torch.empty(Cc * D + Cc, dtype=torch.float32, device=dlog.device)
+            check(lib.pg_head_backward(ptr(dlog), ptr(pooled), None, B, Cc, D, 0, ptr(scratch), ptr(scratch[Cc * D:]), None,
+                                       current_stream_ptr()), "pg_head_backward")
+            torch.distributed.all_reduce(scratch)
+            if fresh:
+                self._flat_grad.copy_(scratch).mul_(1.0 / world)
+            else:
+                w.grad.add_(scratch[: Cc * D].view(Cc, D), alpha=1.0 / world)
+                b.grad.add_(scratch[Cc * D:], alpha=1.0 / world)
+        else:
+            check(lib.pg_head_backward(ptr(dlog), ptr(pooled), None, B, Cc, D, 0 if fresh else 1, ptr(w.grad), ptr(b.grad),
+                                       None, current_stream_ptr()), "pg_head_backward")
+        self._saved_dlogits = None
 
     # ---------------------------------------------------------------------------------- forward (reference :350-483)
     def forward(self, pixel_values: Tensor = None, embedding: Tensor = None, heading: Tensor = None,
                 labels: Tensor = None, labels_clf: Tensor = None, labels_multi_task: Tensor = None,
                 labels_climate: Tensor = None, labels_month: Tensor = None, index: Tensor = None) -> ModelOutput:
         self._assert_requirements(pixel_values, embedding, heading)
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("training forward/backward (fine-tune step) is not built on the B200 path yet; "
-                                      "call .eval() / torch.no_grad() for inference")
+        want_grad = self.training and torch.is_grad_enabled() and self.cell_layer.weight.requires_grad
+        if want_grad:
+            outside = self._trainable_outside_head()
+            if outside or self.multi_task:
+                raise NotImplementedError(
+                    "the B200 fine-tune step covers the geocell head only (base_model=None or freeze_base=True, "
+                    f"multi_task=False); trainable outside the head: {outside[:3]}{'...' if len(outside) > 3 else ''} — "
+                    "the tower backward is not built; freeze the base or call .eval() / torch.no_grad()")
         dev = self._device()
         with torch.no_grad():
             # host -> device (reference _move_to_cuda, :193-217)
@@ -360,7 +413,7 @@ class SuperGuessr(nn.Module):
             if labels_clf is None:
                 # the reference dereferences labels_clf unconditionally here (:456 -> _to_one_hot -> .dim())
                 raise AttributeError("'NoneType' object has no attribute 'dim' (labels_clf is required unless serving=True)")
-            loss_clf = self._classification_loss(logits, labels, labels_clf)
+            loss_clf = self._classification_loss(logits, labels, labels_clf, want_grad=want_grad)
             loss = loss_clf
             if self.multi_task:
                 loss = loss_clf + loss_reg + loss_climate + loss_month

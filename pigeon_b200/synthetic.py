@@ -112,3 +112,22 @@ def synthetic_queries(bank: Dict[str, np.ndarray], cand: np.ndarray, views: int 
                 q[b] = bank["proto_emb"][rng.integers(lo, hi)] + rng.standard_normal(D, dtype=np.float32) * noise
     v = q[:, None, :] + rng.standard_normal((B, views, D), dtype=np.float32) * (noise * 0.1)
     return v.astype(np.float32)
+
+
+def synthetic_photo(height: int, width: int, seed: int = 0) -> np.ndarray:
+    """Deterministic uint8 RGB test image [H, W, 3] from integer arithmetic only (triangle-wave gradients, PCG64 integer
+    noise, two saturated blocks so that bicubic overshoot has to clip): identical on every machine."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.int64)
+    img = np.empty((height, width, 3), dtype=np.int64)
+    for c in range(3):
+        t = (xx * (3 + c) + yy * (5 - c)) % 510
+        tri = np.where(t > 255, 510 - t, t)
+        u = (xx * yy // (17 + 4 * c)) % 256
+        img[..., c] = (tri * 3 + u) // 4
+    img += rng.integers(-40, 41, size=img.shape)
+    img = np.clip(img, 0, 255)
+    h4, w4 = height // 4, width // 4
+    img[h4:h4 + height // 10, w4:w4 + width // 8] = 255
+    img[h4 + height // 10:h4 + height // 5, w4:w4 + width // 8] = 0
+    return img.astype(np.uint8)
