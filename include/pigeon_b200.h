@@ -145,6 +145,58 @@ int pg_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Fine-tune step, vision tower ("next" row N1): the forward of pg_vit_forward with every activation the backward
+ * needs kept in caller-provided buffers, and the backward itself — what autograd runs through HF
+ * CLIPVisionTransformer for `accelerator.backward(output.loss)` in reference training/train_eval_loop.py:216.
+ * Gradients flow in bf16 operands with fp32 accumulation; weight gradients accumulate in fp32.
+ * rows = n_views * tokens.  All pointers are device pointers; the *_host arrays live on the host.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct pg_vit_saved_layer {
+  float* x0;    /* f32 [rows, hidden]        residual stream entering the layer */
+  void* xn1;    /* f16 [rows, hidden]        layer_norm1 output */
+  void* qkv;    /* f16 [rows, 3*hidden]      q | k | v projections */
+  float* lse2;  /* f32 [n_views*heads, tokens] log2-sum-exp of the scaled logits */
+  void* ao;     /* f16 [rows, hidden]        attention output (input of out_proj) */
+  float* x1;    /* f32 [rows, hidden]        residual stream after the attention block */
+  void* xn2;    /* f16 [rows, hidden]        layer_norm2 output */
+  void* h;      /* f16 [rows, intermediate]  quick_gelu(fc1) */
+} pg_vit_saved_layer;
+
+typedef struct pg_vit_saved {
+  void* im2col;  /* f16 [n_views*patches, patch_k_pad] */
+  float* e;      /* f32 [rows, hidden] class/patch + position embeddings (input of pre_layrnorm) */
+  float* x_out;  /* f32 [rows, hidden] last_hidden_state */
+  const pg_vit_saved_layer* layers_host;  /* [layers] */
+} pg_vit_saved;
+
+/* emb_out f32 [n_views, hidden] = token mean of last_hidden_state, as pg_vit_forward. */
+int pg_vit_forward_train(pg_vit* h, const void* pixels, int32_t pixels_f16, int32_t n_views, const pg_vit_saved* saved,
+                         float* emb_out, void* stream);
+
+typedef struct pg_vit_layer_bwd {
+  /* bf16 transposed weights for the data gradients: w_qkv_t [hidden, 3*hidden], w_o_t [hidden, hidden],
+   * w_fc1_t [hidden, intermediate], w_fc2_t [intermediate, hidden] (row-major, = W^T of the [out, in] Linear weights) */
+  const void *w_qkv_t, *w_o_t, *w_fc1_t, *w_fc2_t;
+  /* f32 gradient accumulators (+=), same shapes as the parameters; all NULL = frozen layer
+   * (reference freeze policy, models/super_guessr.py:159-160) */
+  float *d_ln1_g, *d_ln1_b, *d_w_qkv, *d_b_qkv, *d_w_o, *d_b_o, *d_ln2_g, *d_ln2_b, *d_w_fc1, *d_b_fc1, *d_w_fc2, *d_b_fc2;
+} pg_vit_layer_bwd;
+
+typedef struct pg_vit_grads {
+  /* embeddings + pre_layrnorm, f32 (+=); all NULL = frozen (the backward then stops at the lowest trainable layer) */
+  float *d_patch_w;   /* [hidden, patch_k_pad] */
+  float *d_class_emb; /* [hidden] */
+  float *d_pos_emb;   /* [tokens, hidden] */
+  float *d_pre_ln_g, *d_pre_ln_b;
+  const pg_vit_layer_bwd* layers_host;  /* [layers] */
+} pg_vit_grads;
+
+size_t pg_vit_backward_workspace_bytes(const pg_vit* h, int32_t n_views);
+/* d_emb f32 [n_views, hidden]: gradient of the loss with respect to the token-mean embedding of each view. */
+int pg_vit_backward(pg_vit* h, const pg_vit_saved* saved, const float* d_emb, int32_t n_views, const pg_vit_grads* grads,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * ProtoRefiner (reference models/proto_refiner.py:121-255, 332-357; preprocessing/geo_utils.py:40-55)
  * ------------------------------------------------------------------------------------------------- */
 typedef struct pg_refiner_bank {
@@ -202,11 +254,30 @@ enum {
 /* D[M,N] = A[M,K] (fp16, row stride lda) * W[N,K]^T (fp16, row stride ldw), fp32 accumulate on tcgen05. */
 int pg_gemm_f16(const void* a, int32_t lda, const void* w, int32_t ldw, void* out, int32_t ldo, const float* bias,
                 int32_t M, int32_t N, int32_t K, int32_t epilogue, void* stream);
+/* pg_gemm_f16 with bf16 operands (operand_bf16 != 0) and, for PG_EPI_F32_BIAS_RESID, an out-of-place residual source
+ * `resid` f32 [M, ldo] (NULL = update `out` in place). */
+int pg_gemm_ex(const void* a, int32_t lda, const void* w, int32_t ldw, void* out, int32_t ldo, const float* bias,
+               const float* resid, int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t operand_bf16, void* stream);
 /* LayerNorm over the last dim: x f32 [rows, hidden] -> y fp16 [rows, hidden]. */
 int pg_layernorm_f16(const float* x, void* y, const float* gamma, const float* beta, int64_t rows, int32_t hidden,
                      float eps, void* stream);
 /* softmax(q k^T / 8) v per (view, head); qkv fp16 [n_views*seq, 3*heads*64] -> out fp16 [n_views*seq, heads*64]. */
 int pg_attention_f16(const void* qkv, void* out, int32_t n_views, int32_t seq, int32_t heads, void* stream);
+/* Same, also writing lse2 f32 [n_views*heads, seq] (log2-sum-exp of the scaled logits) for the backward pass. */
+int pg_attention_f16_lse(const void* qkv, void* out, float* lse2, int32_t n_views, int32_t seq, int32_t heads, void* stream);
+/* Backward of the attention core: qkv f16 [n_views*seq, 3*heads*64], d_out f32 and out f16 [n_views*seq, heads*64],
+ * lse2 from the forward -> dqkv bf16 [n_views*seq, 3*heads*64].  workspace: pg_attention_backward_workspace_bytes. */
+size_t pg_attention_backward_workspace_bytes(int32_t n_views, int32_t seq, int32_t heads);
+int pg_attention_backward(const void* qkv, const void* out, const float* d_out, const float* lse2, void* dqkv_bf16,
+                          int32_t n_views, int32_t seq, int32_t heads, void* workspace, size_t workspace_bytes, void* stream);
+/* LayerNorm backward: dx (+)= dLN(x)/dx . dy;  dgamma / dbeta (both or neither NULL) += their gradients. */
+int pg_layernorm_backward(const float* dy, const float* x, const float* gamma, float* dx, int32_t accumulate, float* dgamma,
+                          float* dbeta, int64_t rows, int32_t hidden, float eps, void* stream);
+/* du bf16 [n] = dh f32 [n] * quick_gelu'(u f16 [n]) */
+int pg_dgelu_bf16(const float* dh, const void* u, void* du, int64_t n, void* stream);
+/* out bf16 [cols, ldo] = transpose(src [rows, lds]); src_type 0 = f32, 1 = f16, 2 = bf16 */
+int pg_transpose_to_bf16(const void* src, int32_t src_type, int64_t lds, void* out, int64_t ldo, int64_t rows, int32_t cols,
+                         void* stream);
 
 #ifdef __cplusplus
 }

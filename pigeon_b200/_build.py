@@ -30,6 +30,9 @@ SOURCES = [
     "refiner.cu",
     "train.cu",
     "preprocess.cu",
+    "train_vit.cu",
+    "attention_bwd_tcgen05.cu",
+    "vit_train_capi.cu",
     "capi.cu",
 ]
 

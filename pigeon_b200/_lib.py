@@ -32,6 +32,25 @@ class VitLayer(C.Structure):
                                         "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
 
 
+class VitSavedLayer(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("x0", "xn1", "qkv", "lse2", "ao", "x1", "xn2", "h")]
+
+
+class VitSaved(C.Structure):
+    _fields_ = [("im2col", c_void_p), ("e", c_void_p), ("x_out", c_void_p), ("layers_host", C.POINTER(VitSavedLayer))]
+
+
+class VitLayerBwd(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("w_qkv_t", "w_o_t", "w_fc1_t", "w_fc2_t", "d_ln1_g", "d_ln1_b", "d_w_qkv",
+                                        "d_b_qkv", "d_w_o", "d_b_o", "d_ln2_g", "d_ln2_b", "d_w_fc1", "d_b_fc1",
+                                        "d_w_fc2", "d_b_fc2")]
+
+
+class VitGrads(C.Structure):
+    _fields_ = [("d_patch_w", c_void_p), ("d_class_emb", c_void_p), ("d_pos_emb", c_void_p), ("d_pre_ln_g", c_void_p),
+                ("d_pre_ln_b", c_void_p), ("layers_host", C.POINTER(VitLayerBwd))]
+
+
 class VitWeights(C.Structure):
     _fields_ = [("patch_w", c_void_p), ("class_emb", c_void_p), ("pos_emb", c_void_p), ("pre_ln_g", c_void_p),
                 ("pre_ln_b", c_void_p), ("layers_host", C.POINTER(VitLayer))]
@@ -52,6 +71,20 @@ SIGNATURES = {
     "pg_vit_destroy": (None, [c_void_p]),
     "pg_vit_workspace_bytes": (c_size_t, [c_void_p, c_int32]),
     "pg_vit_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "pg_vit_forward_train": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, C.POINTER(VitSaved), c_void_p, c_void_p]),
+    "pg_vit_backward_workspace_bytes": (c_size_t, [c_void_p, c_int32]),
+    "pg_vit_backward": (c_int32, [c_void_p, C.POINTER(VitSaved), c_void_p, c_int32, C.POINTER(VitGrads), c_void_p, c_size_t,
+                                  c_void_p]),
+    "pg_gemm_ex": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32,
+                             c_int32, c_int32, c_int32, c_void_p]),
+    "pg_attention_f16_lse": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "pg_attention_backward_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "pg_attention_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                        c_void_p, c_size_t, c_void_p]),
+    "pg_layernorm_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int64,
+                                        c_int32, c_float, c_void_p]),
+    "pg_dgelu_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "pg_transpose_to_bf16": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p]),
     "pg_head_pack_weight": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "pg_head_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "pg_head_forward": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32,

@@ -5,6 +5,14 @@
 namespace pg {
 
 // qkv: fp16 [n_views*seq, 3*heads*64]; out: fp16 [n_views*seq, heads*64]. head_dim is 64.
-int attention_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream);
+// lse2 (optional): f32 [n_views*heads, seq], log2-domain log-sum-exp of the scaled logits, kept for the backward pass.
+int attention_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream,
+                  float* lse2 = nullptr);
+
+// Backward of the attention core (attention_bwd_tcgen05.cu).
+//   qkv f16 / qkv_bf16 [n_views*seq, 3*heads*64] (same values, two operand types), d_out_bf16 [n_views*seq, heads*64],
+//   lse2 / delta f32 [n_views*heads, seq]  ->  dqkv bf16 [n_views*seq, 3*heads*64]
+int attention_backward(const void* qkv_f16, const void* qkv_bf16, const void* d_out_bf16, const float* lse2,
+                       const float* delta, void* dqkv_bf16, int n_views, int seq, int heads, cudaStream_t stream);
 
 }  // namespace pg

@@ -1,0 +1,330 @@
+// Backward of the multi-head attention core on sm_100a (tcgen05 + TMEM + TMA), head_dim 64 — part of the fine-tune
+// step ("next" row N1; what autograd runs for HF CLIPAttention in reference training/train_eval_loop.py:216).
+//
+//   S = scale Q K^T,  P = softmax(S),  O = P V          (forward, attention_tcgen05.cu; it keeps lse2 = log2 sum exp)
+//   dV = P^T dO,  dP = dO V^T,  dS = P o (dP - delta),  delta = rowsum(dO o O),  dQ = scale dS K,  dK = scale dS^T Q
+//
+// Two launches of one kernel template, each "row tile" of 128 rows owning its accumulators in TMEM for the whole loop,
+// so that no atomics and no transposes are needed and every MMA uses an operand form the forward kernel already uses:
+//   MODE_DQ   CTA = (128 query rows, head, view), loops over KV blocks of 64:
+//             S = Q K_j^T (f16), dP = dO V_j^T (bf16)  ->  dS  ->  dQ += dS K_j        (dS: TMEM A operand, K_j: MN-major B)
+//   MODE_DKV  CTA = (128 key/value rows, head, view), loops over query blocks of 64:
+//             S^T = K Q_j^T (f16), dP^T = V dO_j^T (bf16)  ->  P^T, dS^T  ->  dV += P^T dO_j,  dK += dS^T Q_j
+// The logits are recomputed from the SAME fp16 q/k the forward used (so P is reproduced exactly); everything that carries
+// gradient magnitude (dO, dS, and the q/k/v copies they multiply) is bf16 — gradients underflow fp16's range.
+//
+//   warp 0     TMA producer: the row tile's two operands once, then three 64 x 64 tiles per block through a 2-slot ring
+//   warp 1     TMEM allocator + MMA issuer
+//   warps 2-5  one TMEM lane (= one row of the row tile) per thread: P / dS from S, dP, lse2, delta; written back to TMEM
+//              as packed bf16 over the columns they were read from
+// TMEM (256 columns): S [0,64)  dP [64,128)  acc1 [128,192) (dQ | dV)  acc2 [192,256) (dK).  Correctness-first version:
+// one S/dP buffer (the MMA warp and the row threads alternate); two CTAs per SM overlap each other's bubbles.
+#include <cuda_bf16.h>
+
+#include "attention.h"
+#include "prof.h"
+#include "ptx.cuh"
+#include "tma_host.h"
+
+namespace pg {
+
+namespace {
+
+constexpr int kHeadDim = 64;
+constexpr int kRows = 128;                             // row tile
+constexpr int kBlk = 64;                               // column block
+constexpr int kThreads = 192;
+constexpr int kRowTileBytes = kRows * kHeadDim * 2;    // 16 KB
+constexpr int kTileBytes = kBlk * kHeadDim * 2;        // 8 KB
+constexpr int kStageBytes = 3 * kTileBytes;            // 24 KB
+constexpr int kStages = 2;
+constexpr int kTmemCols = 256;
+constexpr int kSmemBytes = 2 * kRowTileBytes + kStages * kStageBytes + 2 * 128 * 4 + 1024 + 256;
+constexpr uint32_t kBf16Fmt = (1u << 7) | (1u << 10);
+
+enum { MODE_DQ = 0, MODE_DKV = 1 };
+
+struct BwdArgs {
+  int seq, hidden;
+  const float* lse2;    // [n_views * heads, seq]
+  const float* delta;   // [n_views * heads, seq]
+  __nv_bfloat16* dqkv;  // [n_views * seq, 3 * hidden]
+  float scale;          // 1 / sqrt(64)
+  float scale_log2;     // scale * log2(e)
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void bar_sync_compute() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 2)
+attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_f16, const __grid_constant__ CUtensorMap tmap_bf16,
+                     const __grid_constant__ CUtensorMap tmap_do, const BwdArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_r16 = smem;                              // row tile, fp16 (Q | K)
+  uint8_t* smem_rbf = smem + kRowTileBytes;              // row tile, bf16 (dO | V)
+  uint8_t* smem_st = smem + 2 * kRowTileBytes;           // ring: [C16 | Cbf1 | Cbf2] per slot
+  float* cbuf = reinterpret_cast<float*>(smem_st + kStages * kStageBytes);   // [2][128]: lse2 | delta of a column block
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(cbuf) + 2 * 128 * 4);
+  uint64_t* full_bar = bars;                 // [kStages] TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;      // [kStages] MMA -> TMA
+  uint64_t* r_full = bars + 2 * kStages;     // row tile landed
+  uint64_t* s_full = r_full + 1;             // MMA -> rows : S and dP of this block complete
+  uint64_t* ds_ready = s_full + 1;           // rows -> MMA : P / dS written (4 warps arrive)
+  uint64_t* acc_full = ds_ready + 1;         // MMA -> rows : accumulators complete
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, head = blockIdx.y, view = blockIdx.z;
+  const int S = args.seq;
+  const int heads = args.hidden / kHeadDim;
+  const int nb = (S + kBlk - 1) / kBlk;
+  const int row0 = view * S;
+  const int q_col = head * kHeadDim, k_col = args.hidden + q_col, v_col = 2 * args.hidden + q_col;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_f16);
+    tma_prefetch_desc(&tmap_bf16);
+    tma_prefetch_desc(&tmap_do);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(r_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(ds_ready, 4);
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  constexpr uint32_t kSCol = 0, kDpCol = 64, kAcc1Col = 128, kAcc2Col = 192;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      const int r_row = row0 + tile * kRows;
+      mbar_arrive_expect_tx(r_full, 2 * kRowTileBytes);
+#pragma unroll
+      for (int part = 0; part < kRows / kBlk; ++part) {
+        if (MODE == MODE_DQ) {
+          tma_load_2d(smem_r16 + part * kTileBytes, &tmap_f16, r_full, q_col, r_row + part * kBlk);
+          tma_load_2d(smem_rbf + part * kTileBytes, &tmap_do, r_full, q_col, r_row + part * kBlk);
+        } else {
+          tma_load_2d(smem_r16 + part * kTileBytes, &tmap_f16, r_full, k_col, r_row + part * kBlk);
+          tma_load_2d(smem_rbf + part * kTileBytes, &tmap_bf16, r_full, v_col, r_row + part * kBlk);
+        }
+      }
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nb; ++j) {
+        mbar_wait(&empty_bar[slot], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[slot], kStageBytes);
+        uint8_t* st = smem_st + slot * kStageBytes;
+        const int c_row = row0 + j * kBlk;
+        if (MODE == MODE_DQ) {
+          tma_load_2d(st, &tmap_f16, &full_bar[slot], k_col, c_row);                       // K_j  fp16  (S)
+          tma_load_2d(st + kTileBytes, &tmap_bf16, &full_bar[slot], v_col, c_row);         // V_j  bf16  (dP)
+          tma_load_2d(st + 2 * kTileBytes, &tmap_bf16, &full_bar[slot], k_col, c_row);     // K_j  bf16  (dQ)
+        } else {
+          tma_load_2d(st, &tmap_f16, &full_bar[slot], q_col, c_row);                       // Q_j  fp16  (S^T)
+          tma_load_2d(st + kTileBytes, &tmap_do, &full_bar[slot], q_col, c_row);           // dO_j bf16  (dP^T, dV)
+          tma_load_2d(st + 2 * kTileBytes, &tmap_bf16, &full_bar[slot], q_col, c_row);     // Q_j  bf16  (dK)
+        }
+        if (++slot == kStages) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(kRows, kBlk, 0, 0);                  // fp16 x fp16, both K-major
+      const uint32_t idesc_dp = make_idesc_f16(kRows, kBlk, 0, 0) | kBf16Fmt;      // bf16 x bf16, both K-major
+      const uint32_t idesc_acc = make_idesc_f16(kRows, kHeadDim, 0, 1) | kBf16Fmt; // A from TMEM, B MN-major
+      const uint32_t r16_addr = smem_u32(smem_r16), rbf_addr = smem_u32(smem_rbf);
+      mbar_wait(r_full, 0);
+      tc_fence_after();
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nb; ++j) {
+        mbar_wait(&full_bar[slot], phase);
+        tc_fence_after();
+        const uint32_t c16 = smem_u32(smem_st + slot * kStageBytes);
+        const uint32_t cb1 = c16 + kTileBytes, cb2 = c16 + 2 * kTileBytes;
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k)
+          umma_ss(tmem_base + kSCol, make_smem_desc(r16_addr + k * 32, 16, 1024, kLayoutSw128),
+                  make_smem_desc(c16 + k * 32, 16, 1024, kLayoutSw128), idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k)
+          umma_ss(tmem_base + kDpCol, make_smem_desc(rbf_addr + k * 32, 16, 1024, kLayoutSw128),
+                  make_smem_desc(cb1 + k * 32, 16, 1024, kLayoutSw128), idesc_dp, k != 0);
+        tc_commit(s_full);
+        mbar_wait(ds_ready, j & 1);
+        tc_fence_after();
+        if (MODE == MODE_DQ) {
+#pragma unroll
+          for (int k = 0; k < kBlk / 16; ++k)      // dQ += dS K_j : contraction over the block's 64 kv rows
+            umma_ts(tmem_base + kAcc1Col, tmem_base + kDpCol + k * 8,
+                    make_smem_desc(cb2 + k * 16 * 128, 1024, 1024, kLayoutSw128), idesc_acc, (j | k) != 0);
+        } else {
+#pragma unroll
+          for (int k = 0; k < kBlk / 16; ++k)      // dV += P^T dO_j : contraction over the block's 64 query rows
+            umma_ts(tmem_base + kAcc1Col, tmem_base + kSCol + k * 8,
+                    make_smem_desc(cb1 + k * 16 * 128, 1024, 1024, kLayoutSw128), idesc_acc, (j | k) != 0);
+#pragma unroll
+          for (int k = 0; k < kBlk / 16; ++k)      // dK += dS^T Q_j
+            umma_ts(tmem_base + kAcc2Col, tmem_base + kDpCol + k * 8,
+                    make_smem_desc(cb2 + k * 16 * 128, 1024, 1024, kLayoutSw128), idesc_acc, (j | k) != 0);
+        }
+        tc_commit(&empty_bar[slot]);
+        if (++slot == kStages) { slot = 0; phase ^= 1; }
+      }
+      tc_commit(acc_full);
+    }
+  } else {
+    // ---------------------------------------------------------------- row threads
+    const int qd = warp & 3;                                  // TMEM lane quarter this warp may touch
+    const int ct = (warp - 2) * 32 + lane;                    // 0..127 among the row threads (cbuf staging)
+    const uint32_t lane_base = uint32_t(qd * 32) << 16;
+    const int r = tile * kRows + qd * 32 + lane;              // row index inside the view
+    const bool row_valid = r < S;
+    const float c = args.scale_log2, scale = args.scale;
+    const size_t stat0 = ((size_t)view * heads + head) * S;
+    float lse_r = 0.f, delta_r = 0.f;
+    if (MODE == MODE_DQ && row_valid) { lse_r = args.lse2[stat0 + r]; delta_r = args.delta[stat0 + r]; }
+
+    for (int j = 0; j < nb; ++j) {
+      float* cb = cbuf + (j & 1) * 128;
+      if (MODE == MODE_DKV) {   // per-column statistics of this query block
+        const int qi = j * kBlk + (ct & 63);
+        float v = 0.f;
+        if (qi < S) v = (ct < 64) ? args.lse2[stat0 + qi] : args.delta[stat0 + qi];
+        cb[ct] = v;
+        bar_sync_compute();
+      }
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t sv[32], dv[32], pk_p[16], pk_ds[16];
+        tmem_ld32(tmem_base + lane_base + kSCol + 32 * h, sv);
+        tmem_ld32(tmem_base + lane_base + kDpCol + 32 * h, dv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p[2], ds[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = j * kBlk + 32 * h + i + e;        // index of the column inside the view
+            float lse_c, delta_c;
+            if (MODE == MODE_DQ) { lse_c = lse_r; delta_c = delta_r; }
+            else { lse_c = cb[32 * h + i + e]; delta_c = cb[64 + 32 * h + i + e]; }
+            const bool ok = row_valid && (col < S);
+            const float pe = ex2(fmaf(__uint_as_float(sv[i + e]), c, -lse_c));
+            p[e] = ok ? pe : 0.f;
+            ds[e] = ok ? pe * (__uint_as_float(dv[i + e]) - delta_c) * scale : 0.f;
+          }
+          pk_p[i >> 1] = pack_bf16x2(p[0], p[1]);
+          pk_ds[i >> 1] = pack_bf16x2(ds[0], ds[1]);
+        }
+        // packed bf16 pairs over columns this thread has already consumed: P at S[16h, 16h+16), dS at dP[16h, 16h+16)
+        if (MODE == MODE_DKV) tmem_st16(tmem_base + lane_base + kSCol + 16 * h, pk_p);
+        tmem_st16(tmem_base + lane_base + kDpCol + 16 * h, pk_ds);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_ready);
+    }
+
+    // epilogue: accumulators -> bf16 -> dqkv
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    __nv_bfloat16* orow = args.dqkv + (size_t)(row0 + r) * (3 * args.hidden);
+    constexpr int kNumAcc = (MODE == MODE_DQ) ? 1 : 2;
+#pragma unroll
+    for (int a = 0; a < kNumAcc; ++a) {
+      // MODE_DQ: acc1 = dQ -> q section;  MODE_DKV: acc1 = dV -> v section, acc2 = dK -> k section
+      const int out_col = (MODE == MODE_DQ) ? q_col : (a == 0 ? v_col : k_col);
+      const uint32_t acc = tmem_base + lane_base + (a == 0 ? kAcc1Col : kAcc2Col);
+#pragma unroll
+      for (int c0 = 0; c0 < kHeadDim; c0 += 32) {
+        uint32_t o[32];
+        tmem_ld32(acc + c0, o);
+        tmem_ld_wait();
+        if (row_valid) {
+          uint4* o4 = reinterpret_cast<uint4*>(orow + out_col + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]), __uint_as_float(o[8 * i + 1]));
+            v.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]), __uint_as_float(o[8 * i + 3]));
+            v.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]), __uint_as_float(o[8 * i + 5]));
+            v.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]), __uint_as_float(o[8 * i + 7]));
+            o4[i] = v;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int MODE>
+int launch_bwd(const CUtensorMap& t16, const CUtensorMap& tbf, const CUtensorMap& tdo, const BwdArgs& a, int n_views,
+               int heads, cudaStream_t stream) {
+  auto kern = attention_bwd_kernel<MODE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) { set_last_error("attention_backward: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
+    attr_set = true;
+  }
+  dim3 grid((a.seq + kRows - 1) / kRows, heads, n_views);
+  ProfScope prof(MODE == MODE_DQ ? "attention_bwd_dq" : "attention_bwd_dkv", stream);
+  kern<<<grid, kThreads, kSmemBytes, stream>>>(t16, tbf, tdo, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_last_error("attention_backward launch: %s", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
+}  // namespace
+
+int attention_backward(const void* qkv_f16, const void* qkv_bf16, const void* d_out_bf16, const float* lse2,
+                       const float* delta, void* dqkv_bf16, int n_views, int seq, int heads, cudaStream_t stream) {
+  if (n_views <= 0) return 0;
+  const int hidden = heads * kHeadDim;
+  const uint64_t rows = (uint64_t)n_views * seq;
+  CUtensorMap t16, tbf, tdo;
+  if (make_tmap_f16_2d(&t16, qkv_f16, rows, 3 * hidden, 3 * hidden, kBlk, kHeadDim)) return 1;
+  if (make_tmap_f16_2d(&tbf, qkv_bf16, rows, 3 * hidden, 3 * hidden, kBlk, kHeadDim)) return 1;
+  if (make_tmap_f16_2d(&tdo, d_out_bf16, rows, hidden, hidden, kBlk, kHeadDim)) return 1;
+  BwdArgs a;
+  a.seq = seq; a.hidden = hidden; a.lse2 = lse2; a.delta = delta;
+  a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv_bf16);
+  a.scale = 0.125f;
+  a.scale_log2 = 0.125f * 1.4426950408889634f;
+  if (launch_bwd<MODE_DQ>(t16, tbf, tdo, a, n_views, heads, stream)) return 1;
+  return launch_bwd<MODE_DKV>(t16, tbf, tdo, a, n_views, heads, stream);
+}
+
+}  // namespace pg

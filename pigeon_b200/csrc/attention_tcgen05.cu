@@ -63,6 +63,7 @@ struct AttnArgs {
   int hidden;   // heads * 64
   __half* out;  // [n_views*seq, hidden]
   float scale_log2;  // (1/sqrt(64)) * log2(e)
+  float* lse2;       // optional [n_views * heads, seq]: log2-domain log-sum-exp of the scaled logits (for the backward pass)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -364,7 +365,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
     // epilogue: O / l -> fp16 -> global
     mbar_wait(o_full, 0);
     tc_fence_after();
-    const float inv_l = 1.0f / ((l0 + l1) + (l2 + l3));
+    const float l_sum = (l0 + l1) + (l2 + l3);
+    const float inv_l = 1.0f / l_sum;
+    if (args.lse2 != nullptr && q_row < S)
+      args.lse2[((size_t)view * (args.hidden / kHeadDim) + head) * S + q_row] = m * c + log2f(l_sum);
     __half* orow = args.out + (size_t)(row0 + q_row) * args.hidden + q_col;
 #pragma unroll
     for (int c0 = 0; c0 < kHeadDim; c0 += 32) {
@@ -396,7 +400,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
 }
 
 template <class Cfg>
-int launch_attention(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream) {
+int launch_attention(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream, float* lse2) {
   const int hidden = heads * kHeadDim;
   CUtensorMap tm;
   if (make_tmap_f16_2d(&tm, qkv, (uint64_t)n_views * seq, 3 * hidden, 3 * hidden, Cfg::kBlockKV, kHeadDim)) return 1;
@@ -412,6 +416,7 @@ int launch_attention(const void* qkv, void* out, int n_views, int seq, int heads
   a.hidden = hidden;
   a.out = reinterpret_cast<__half*>(out);
   a.scale_log2 = 0.125f * 1.4426950408889634f;
+  a.lse2 = lse2;
   dim3 grid((seq + kBlockQ - 1) / kBlockQ, heads, n_views);
   ProfScope prof("attention", stream);
   kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tm, a);
@@ -422,17 +427,17 @@ int launch_attention(const void* qkv, void* out, int n_views, int seq, int heads
 
 }  // namespace
 
-int attention_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream) {
+int attention_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream, float* lse2) {
   if (n_views <= 0) return 0;
   // Default tiling: KV blocks of 32, 2 S buffers, 128 TMEM columns -> 4 co-resident CTAs per SM (measured 0.379 ms vs
   // 0.436 ms per 128-view layer for the 64-wide / 3-buffer / 2-CTA tiling on the same box).  PG_ATTN_VARIANT=64 selects
   // the latter (A/B switch).
   const char* v = getenv("PG_ATTN_VARIANT");
-  if (v && v[0] == '6' && v[1] == '4') return launch_attention<AttnCfg<64, 3, 2>>(qkv, out, n_views, seq, heads, stream);
+  if (v && v[0] == '6' && v[1] == '4') return launch_attention<AttnCfg<64, 3, 2>>(qkv, out, n_views, seq, heads, stream, lse2);
   const char* pe = getenv("PG_ATTN_POLY");     // experiment switch: "4" / "2" = every 4th / 2nd group on the FMA pipe
-  if (pe && pe[0] == '4') return launch_attention<AttnCfg<32, 2, 4, 4>>(qkv, out, n_views, seq, heads, stream);
-  if (pe && pe[0] == '2') return launch_attention<AttnCfg<32, 2, 4, 2>>(qkv, out, n_views, seq, heads, stream);
-  return launch_attention<AttnCfg<32, 2, 4>>(qkv, out, n_views, seq, heads, stream);
+  if (pe && pe[0] == '4') return launch_attention<AttnCfg<32, 2, 4, 4>>(qkv, out, n_views, seq, heads, stream, lse2);
+  if (pe && pe[0] == '2') return launch_attention<AttnCfg<32, 2, 4, 2>>(qkv, out, n_views, seq, heads, stream, lse2);
+  return launch_attention<AttnCfg<32, 2, 4>>(qkv, out, n_views, seq, heads, stream, lse2);
 }
 
 }  // namespace pg

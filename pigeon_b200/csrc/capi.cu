@@ -17,13 +17,14 @@
 #include "refiner.h"
 #include "tma_host.h"
 #include "train.h"
+#include "vit_handle.h"
 #include "vit_misc.h"
 
 using namespace pg;
 
-namespace {
+namespace pg {
 
-int g_sm_count = 0;
+static int g_sm_count = 0;
 int sm_count() {
   if (g_sm_count <= 0) {
     int dev = 0, n = 0;
@@ -37,28 +38,7 @@ int sm_count() {
   return g_sm_count;
 }
 
-inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-struct Carver {
-  uint8_t* base;
-  size_t off = 0;
-  explicit Carver(void* p) : base(reinterpret_cast<uint8_t*>(p)) {}
-  void* take(size_t bytes) {
-    void* p = base ? base + off : nullptr;
-    off += align_up(bytes, 1024);
-    return p;
-  }
-};
-
-}  // namespace
-
-struct pg_vit {
-  pg_vit_config cfg;
-  pg_vit_weights w;
-  std::vector<pg_vit_layer> layers;
-  int tokens;
-  int grid_patches;
-};
+}  // namespace pg
 
 extern "C" {
 

@@ -23,6 +23,8 @@ struct GemmProblem {
   const float* bias;
   int epi;
   int rowmap_div, rowmap_mul, rowmap_add;
+  int operand_bf16;     // A and W hold bf16 instead of fp16 (backward GEMMs); outputs are unaffected
+  const float* resid;   // EPI_F32_BIAS_RESID: residual read from here instead of `out` (same ldo); nullptr = in place
 };
 
 // Enqueues the GEMM on `stream`. Returns 0 on success; on failure the message is in pg::last_error().

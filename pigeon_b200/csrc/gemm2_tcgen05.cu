@@ -164,7 +164,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(2 * BLOCK_M_CTA, BLOCK_N, 0, 0);
+      const uint32_t idesc = make_idesc_f16(2 * BLOCK_M_CTA, BLOCK_N, 0, 0) | args.idesc_fmt;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -239,6 +239,8 @@ int launch2(const GemmProblem& p, int num_sms, cudaStream_t stream) {
   a.M = p.M; a.N = p.N; a.K = p.K; a.out = p.out; a.ldo = p.ldo; a.bias = p.bias;
   a.vec_ok = (p.ldo % (f16_out ? 8 : 4)) == 0;
   a.rowmap_div = p.rowmap_div > 0 ? p.rowmap_div : 1; a.rowmap_mul = p.rowmap_mul; a.rowmap_add = p.rowmap_add;
+  a.idesc_fmt = p.operand_bf16 ? ((1u << 7) | (1u << 10)) : 0u;
+  a.resid = p.resid ? p.resid : reinterpret_cast<const float*>(p.out);
   const int tiles = ((p.M + 255) / 256) * (p.N / BLOCK_N);
   int pairs = num_sms / 2;
   if (tiles < pairs) pairs = tiles;

@@ -16,6 +16,8 @@ struct GemmArgs {
   // EPI_F32_ROWMAP: output row = rowmap_mul * (row / rowmap_div) + row % rowmap_div + rowmap_add
   int rowmap_div, rowmap_mul, rowmap_add;
   int vec_ok;  // output rows are 16-byte aligned -> vector stores allowed
+  uint32_t idesc_fmt;  // A/B format bits of the instruction descriptor (0 = fp16, bf16 otherwise)
+  const float* resid;  // residual source of EPI_F32_BIAS_RESID (== out when updating in place)
 };
 
 __device__ __forceinline__ float quick_gelu(float v) {
@@ -47,7 +49,7 @@ __device__ __forceinline__ void load_residual(const GemmArgs& args, float4 (&res
     const int grow = warp_row0 + i * 4 + sub;
     res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (grow < args.M)
-      res[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(args.out) +
+      res[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(args.resid) +
                                                 ((long)grow * args.ldo + col0) * 4 + c16 * 16);
   }
 }
@@ -159,7 +161,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
           for (int i = 0; i < CHUNK; ++i)
             if (col0 + i < args.N) {
               float x = v[i];
-              if (kResid) x += o[i];
+              if (kResid) x += args.resid[orow * args.ldo + col0 + i];
               o[i] = x;
             }
         }

@@ -111,7 +111,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BLOCK_M, BLOCK_N, 0, 0);
+      const uint32_t idesc = make_idesc_f16(BLOCK_M, BLOCK_N, 0, 0) | args.idesc_fmt;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -185,6 +185,8 @@ int launch(const GemmProblem& p, int num_sms, cudaStream_t stream) {
   a.M = p.M; a.N = p.N; a.K = p.K; a.out = p.out; a.ldo = p.ldo; a.bias = p.bias;
   a.vec_ok = (p.ldo % (f16_out ? 8 : 4)) == 0;
   a.rowmap_div = p.rowmap_div > 0 ? p.rowmap_div : 1; a.rowmap_mul = p.rowmap_mul; a.rowmap_add = p.rowmap_add;
+  a.idesc_fmt = p.operand_bf16 ? ((1u << 7) | (1u << 10)) : 0u;
+  a.resid = p.resid ? p.resid : reinterpret_cast<const float*>(p.out);
   const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M, n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int tiles = m_blocks * n_blocks;
   const int grid = tiles < num_sms ? tiles : num_sms;

@@ -109,7 +109,7 @@ __global__ void layernorm_f16_kernel(const float* __restrict__ x, __half* __rest
 template <int NV4>
 __global__ void embed_preln_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
                                    const float* __restrict__ g, const float* __restrict__ b, long rows, int tokens,
-                                   float eps) {
+                                   float eps, float* __restrict__ e_out) {
   constexpr int hidden = NV4 * 128;
   const int lane = threadIdx.x & 31;
   const long warps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -124,6 +124,11 @@ __global__ void embed_preln_kernel(float* __restrict__ x, const float* __restric
       const float4 a = src[lane + 32 * i];
       const float4 p = __ldg(pr + lane + 32 * i);
       v[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+    }
+    if (e_out != nullptr) {   // training: keep the pre-LayerNorm embedding sum for the backward pass
+      float4* er = reinterpret_cast<float4*>(e_out + row * hidden);
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) er[lane + 32 * i] = v[i];
     }
     ln_row<NV4>(v, g, b, hidden, eps, lane);
 #pragma unroll
@@ -214,12 +219,12 @@ int layernorm_f16(const float* x, void* y, const float* gamma, const float* beta
 }
 
 int embed_preln(float* x, const float* cls, const float* pos, const float* gamma, const float* beta, long rows,
-                int tokens, int hidden, float eps, int num_sms, cudaStream_t stream) {
+                int tokens, int hidden, float eps, int num_sms, cudaStream_t stream, float* e_out) {
   if (hidden % 128) { set_last_error("embed_preln: hidden %d not a multiple of 128", hidden); return 1; }
   const int grid = grid_for(rows, 8, num_sms);
   ProfScope prof("embed_preln", stream);
   PG_DISPATCH_NV4(hidden, (embed_preln_kernel<NV4><<<grid, 256, 0, stream>>>(x, cls, pos, gamma, beta, rows,
-                                                                               tokens, eps)));
+                                                                               tokens, eps, e_out)));
   return check_launch("embed_preln");
 }
 
