@@ -172,6 +172,45 @@ def preprocess_fixture():
     np.savez_compressed(os.path.join(OUT, "preprocess.npz"), **out)
 
 
+def train_tower_fixture(tmp, name, dims: VitDims, n_views, sd_seed, px_seed, std, stride):
+    """Gradients of the reference fine-tune step through the tower: the UNMODIFIED reference SuperGuessr over a HF
+    CLIPVisionModel, loss.backward() under torch autograd in fp32 (training/train_eval_loop.py:215-216), every tower and
+    head parameter trainable.  Views go through the non-panorama branch (super_guessr.py:388 hard-codes 336 x 336 in the
+    panorama reshape).  Per parameter the fixture keeps the L2 norm and every `stride`-th element of the gradient."""
+    from models.super_guessr import SuperGuessr
+    C = 1000
+    sd = synthetic.random_vit_state_dict(dims, seed=sd_seed, std=std)
+    hf = hf_model(dims, sd)
+    W, b = head_weights(C, dims.hidden, seed=33)
+    g = torch.Generator().manual_seed(px_seed)
+    px = torch.randn(n_views, 3, dims.image_size, dims.image_size, generator=g)
+    labels = torch.tensor(synthetic.synthetic_geocells(n_views, 7))
+    labels_clf = (torch.arange(n_views) * 13 + 5) % C
+    with rs.chdir(tmp):
+        sg = SuperGuessr(hf.base_model, panorama=False, should_smooth_labels=True, num_candidates=5).train()
+    with torch.no_grad():
+        sg.cell_layer.weight.copy_(W)
+        sg.cell_layer.bias.copy_(b)
+    for p_ in sg.parameters():
+        p_.requires_grad_(p_.dtype == torch.float32)
+    sg.lla_geocells.requires_grad_(False)
+    o = sg(pixel_values=px, labels=labels, labels_clf=labels_clf)
+    o.loss.backward()
+    out = {}
+    for n_, p_ in sg.named_parameters():
+        if p_.grad is None:
+            continue
+        gflat = p_.grad.detach().reshape(-1).double()
+        key = n_.replace("base_model.", "")
+        out["norm/" + key] = np.asarray(float(gflat.norm()))
+        out["sub/" + key] = gflat[::stride].float().numpy()
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"),
+                        meta=json.dumps(dict(dims=dims.__dict__, sd_seed=sd_seed, std=std, px_seed=px_seed, n_views=n_views,
+                                             C=C, w_seed=33, stride=stride)),
+                        loss=np.asarray(float(o.loss)), labels=labels.numpy(), labels_clf=labels_clf.numpy(),
+                        centroids=sg.lla_geocells.detach().numpy().copy(), **out)
+
+
 def vit_fixture(tmp, name, dims: VitDims, sd_seed, n_samples, panorama, px_seed, std):
     """pixel_values -> reference SuperGuessr(HF CLIPVisionModel.base_model) -> ModelOutput; plus CLIPEmbedding."""
     from models.clip_embedder import CLIPEmbedding
@@ -310,6 +349,13 @@ def refiner_fixture(tmp, name, C, P, D, B, kc, topk, members, T, maxref, seed):
                         preds_LLH_noprob=ll_np.numpy(), preds_geocell_noprob=cell_np.numpy(), **{f"bank_{k}": v for k, v in packed.items()})
 
 
+def tower_train_fixtures(tmp):
+    small = VitDims(image_size=56, patch_size=14, hidden=256, heads=4, intermediate=512, layers=2)
+    train_tower_fixture(tmp, "train_tower_small", small, n_views=6, sd_seed=43, px_seed=44, std=0.05, stride=7)
+    mid = VitDims(image_size=224, patch_size=14, hidden=256, heads=4, intermediate=512, layers=2)
+    train_tower_fixture(tmp, "train_tower_mid", mid, n_views=3, sd_seed=45, px_seed=46, std=0.05, stride=7)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     tmp = tempfile.mkdtemp(prefix="pigeon_golden_")
@@ -324,11 +370,14 @@ def main():
             train_fixture(tmp)
         if "preprocess" in only:
             preprocess_fixture()
+        if "tower" in only:
+            tower_train_fixtures(tmp)
         return
     geo_fixture()
     head_fixture(tmp)
     train_fixture(tmp)
     preprocess_fixture()
+    tower_train_fixtures(tmp)
     small = VitDims(image_size=56, patch_size=14, hidden=256, heads=4, intermediate=512, layers=2)
     vit_fixture(tmp, "vit_small", small, sd_seed=41, n_samples=3, panorama=True, px_seed=42, std=0.05)
     vit_fixture(tmp, "vit_large_single", VitDims(), sd_seed=0, n_samples=1, panorama=False, px_seed=1, std=0.02)

@@ -118,7 +118,7 @@ class CLIPVisionTower(nn.Module):
         self._packed_version = None
 
     def _version(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return tuple((p.data_ptr(), p._version, getattr(p, "_pg_version", 0)) for p in self.parameters())
 
     def engine(self) -> VitEngine:
         p0 = next(self.parameters())
@@ -272,7 +272,7 @@ class SuperGuessr(nn.Module):
         return self._w3
 
     def _classification_loss(self, logits: Tensor, labels: Optional[Tensor], labels_clf: Tensor,
-                             want_grad: bool = False) -> Tensor:
+                             want_grad: bool = False, grad_scale: float = 1.0) -> Tensor:
         """reference :456,468-474 on the GPU (pg_head_loss); with `want_grad` also d loss / d logits (pg_head_loss_grad),
         kept in `self._saved_dlogits` for `backward()`."""
         B, Cc = logits.shape
@@ -285,7 +285,8 @@ class SuperGuessr(nn.Module):
         def run(mode, idx=None, soft=None, lab=None, cells=None, smoothing=0.0):
             if want_grad:
                 check(lib.pg_head_loss_grad(ptr(logits), B, Cc, mode, ptr(idx), ptr(soft), ptr(lab), ptr(cells), smoothing,
-                                            1.0, ptr(per), ptr(out), ptr(dlog), current_stream_ptr()), "pg_head_loss_grad")
+                                            float(grad_scale), ptr(per), ptr(out), ptr(dlog), current_stream_ptr()),
+                      "pg_head_loss_grad")
             else:
                 check(lib.pg_head_loss(ptr(logits), B, Cc, mode, ptr(idx), ptr(soft), ptr(lab), ptr(cells), smoothing,
                                        ptr(per), ptr(out), current_stream_ptr()), "pg_head_loss")
@@ -308,13 +309,83 @@ class SuperGuessr(nn.Module):
         head = {id(self.cell_layer.weight), id(self.cell_layer.bias)}
         return [n for n, p in self.named_parameters() if p.requires_grad and id(p) not in head]
 
+    def _forward_train_tower(self, pixel_values: Tensor, labels: Optional[Tensor], labels_clf: Tensor) -> ModelOutput:
+        """Training-mode forward when tower parameters require grad (reference freeze policy :159-160): the batch is
+        processed in chunks that fit the activation arena; each chunk runs tower forward -> head -> loss -> head
+        backward -> tower backward, and gradients accumulate in pending buffers that `backward()` publishes (after the
+        DDP-style all-reduce).  Numerically the sum over chunks of the mean-loss gradient = the full-batch gradient."""
+        from .vit_train import TowerTrainer
+        dev = self._device()
+        if getattr(self, "_trainer", None) is None or self._trainer.tower is not self.base_model:
+            self._trainer = TowerTrainer(self.base_model, max_views=getattr(self, "max_train_views", 64))
+        tr = self._trainer
+        V = 4 if self.panorama else 1
+        B = pixel_values.size(0)
+        s = self.base_model.dims.image_size
+        px = pixel_values.reshape((B * V, 3, s, s))
+        if labels_clf is None:
+            raise AttributeError("'NoneType' object has no attribute 'dim' (labels_clf is required unless serving=True)")
+        if labels_clf.dim() == 0:
+            labels_clf = labels_clf.reshape(1).expand(B)
+        step = max(1, tr.max_views // V)
+        w, b = self.cell_layer.weight, self.cell_layer.bias
+        Cc, D = w.shape
+        head_trains = w.requires_grad
+        flat = torch.zeros(Cc * D + Cc, dtype=torch.float32, device=dev)
+        lib = load()
+        outs, loss_total = [], None
+        with torch.no_grad():
+            for lo in range(0, B, step):
+                hi = min(B, lo + step)
+                n = hi - lo
+                emb = tr.forward(px[lo * V:hi * V].to(dev, non_blocking=True)).reshape(n, V, D)
+                h = ops.head_forward(emb.contiguous(), self._packed_head(), b.detach().float().contiguous(),
+                                     self.lla_geocells.data, self.num_candidates)
+                loss = self._classification_loss(h["logits"], None if labels is None else labels[lo:hi], labels_clf[lo:hi],
+                                                 want_grad=True, grad_scale=n / B)
+                dlog, self._saved_dlogits = self._saved_dlogits, None
+                dpooled = torch.empty((n, D), dtype=torch.float32, device=dev)
+                check(lib.pg_head_backward(ptr(dlog), ptr(h["pooled"]), ptr(w.detach()), n, Cc, D, 1,
+                                           ptr(flat) if head_trains else None, ptr(flat[Cc * D:]) if head_trains else None,
+                                           ptr(dpooled), current_stream_ptr()), "pg_head_backward")
+                d_emb = (dpooled / V).repeat_interleave(V, dim=0) if V > 1 else dpooled      # backward of the view mean
+                tr.backward(d_emb)
+                part = loss.double() * (n / B)
+                loss_total = part if loss_total is None else loss_total + part
+                outs.append((h, emb))
+        self._pend_head = flat
+        cat = lambda k: torch.cat([h[k] for h, _ in outs])
+        embedding = torch.cat([e for _, e in outs])
+        loss = loss_total if self.should_smooth_labels else loss_total.to(torch.float32)
+        self.last_pooled = cat("pooled")
+        return ModelOutput(loss, loss, 0, 0, 0, cat("pred_lnglat"), cat("pred_cell"), None, None, None,
+                           TopK(cat("topk_val"), cat("topk_idx")), embedding if self.panorama else embedding[:, 0])
+
     def backward(self, loss: Optional[Tensor] = None, grad_scale: float = 1.0) -> None:
         """What `accelerator.backward(output.loss)` does in reference training/train_eval_loop.py:216 for the
         parameters this path trains: accumulates d loss / d cell_layer.{weight,bias} into `.grad` (pg_head_backward).
         Under torch.distributed the micro-batch gradient is all-reduced and averaged first, like DDP (:192)."""
+        from . import dist as pdist
+        if getattr(self, "_pend_head", None) is not None:
+            # tower fine-tune path: forward() already ran forward + backward chunk by chunk; publish the gradients
+            world = pdist.world_size()
+            flat = self._pend_head
+            self._pend_head = None
+            if world > 1:
+                torch.distributed.all_reduce(flat)
+                flat.mul_(1.0 / world)
+            w, b = self.cell_layer.weight, self.cell_layer.bias
+            Cc, D = w.shape
+            if w.requires_grad:
+                if w.grad is None:
+                    w.grad, b.grad = flat[: Cc * D].view(Cc, D), flat[Cc * D:]
+                else:
+                    w.grad.add_(flat[: Cc * D].view(Cc, D))
+                    b.grad.add_(flat[Cc * D:])
+            self._trainer.finalize(world)
+            return
         if getattr(self, "_saved_dlogits", None) is None or self.last_pooled is None:
             raise PigeonB200Error("backward() needs a preceding training-mode forward with labels")
-        from . import dist as pdist
         w, b = self.cell_layer.weight, self.cell_layer.bias
         dlog, pooled = self._saved_dlogits, self.last_pooled
         B, Cc = dlog.shape
@@ -348,14 +419,17 @@ class SuperGuessr(nn.Module):
                 labels: Tensor = None, labels_clf: Tensor = None, labels_multi_task: Tensor = None,
                 labels_climate: Tensor = None, labels_month: Tensor = None, index: Tensor = None) -> ModelOutput:
         self._assert_requirements(pixel_values, embedding, heading)
-        want_grad = self.training and torch.is_grad_enabled() and self.cell_layer.weight.requires_grad
+        want_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if want_grad:
-            outside = self._trainable_outside_head()
-            if outside or self.multi_task:
-                raise NotImplementedError(
-                    "the B200 fine-tune step covers the geocell head only (base_model=None or freeze_base=True, "
-                    f"multi_task=False); trainable outside the head: {outside[:3]}{'...' if len(outside) > 3 else ''} — "
-                    "the tower backward is not built; freeze the base or call .eval() / torch.no_grad()")
+            if self.multi_task:
+                raise NotImplementedError("the B200 fine-tune step does not cover the multi-task heads (multi_task=True); "
+                                          "call .eval() / torch.no_grad() for inference")
+            tower_trains = self.base_model is not None and any(p.requires_grad for p in self.base_model.parameters())
+            stray = [n for n in self._trainable_outside_head() if not n.startswith("base_model.")]
+            if stray:
+                raise NotImplementedError(f"no backward for trainable parameters {stray[:3]}")
+            if tower_trains:
+                return self._forward_train_tower(pixel_values, labels, labels_clf)
         dev = self._device()
         with torch.no_grad():
             # host -> device (reference _move_to_cuda, :193-217)

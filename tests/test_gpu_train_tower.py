@@ -1,0 +1,222 @@
+"""Fine-tune step through the vision tower (N1): backward kernels one by one against torch autograd in fp32, then the
+whole tower backward and the SuperGuessr training forward against tests/golden/train_tower_*.npz — gradients the
+UNMODIFIED reference model produced under torch autograd (oracle/make_golden.py).
+
+Tolerance: the backward runs its GEMMs with bf16 operands (8-bit mantissa) and fp32 accumulation, the reference is fp32:
+per-tensor relative L2 error <= 3e-2 (typically 3e-3 .. 1e-2), cosine >= 0.999."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REL = 3e-2
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda:0")
+
+
+def _lib():
+    from pigeon_b200._lib import check, current_stream_ptr, load, ptr
+    return load(), check, ptr, current_stream_ptr
+
+
+def _rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+# ------------------------------------------------------------------------------------------------ building blocks
+@pytest.mark.parametrize("M,N,K", [(300, 512, 200), (1000, 256, 2308), (256, 640, 1152), (4096, 1024, 577)])
+def test_gemm_bf16_operands(cuda, M, N, K):
+    lib, check, ptr, sp = _lib()
+    g = torch.Generator().manual_seed(M + N)
+    Kp = (K + 7) // 8 * 8
+    a = torch.zeros(M, Kp, device=cuda, dtype=torch.bfloat16)
+    w = torch.zeros(N, Kp, device=cuda, dtype=torch.bfloat16)
+    a[:, :K] = (torch.randn(M, K, generator=g) * 1e-4).to(cuda, torch.bfloat16)          # gradient-sized values
+    w[:, :K] = (torch.randn(N, K, generator=g) * 0.05).to(cuda, torch.bfloat16)
+    a[:, K:] = 7.0                                                                         # must not be read (TMA extent = K)
+    out = torch.full((M, N), float("nan"), device=cuda)
+    check(lib.pg_gemm_ex(ptr(a), Kp, ptr(w), Kp, ptr(out), N, None, None, M, N, K, 3, 1, sp()), "pg_gemm_ex")
+    ref = a[:, :K].double() @ w[:, :K].double().t()
+    assert _rel(out, ref) < 1e-5
+    # accumulate into an existing buffer from a separate residual source (out-of-place residual epilogue)
+    resid = torch.randn(M, N, generator=g).to(cuda) * 1e-4
+    out2 = torch.zeros(M, N, device=cuda)
+    check(lib.pg_gemm_ex(ptr(a), Kp, ptr(w), Kp, ptr(out2), N, None, ptr(resid), M, N, K, 2, 1, sp()), "pg_gemm_ex")
+    assert _rel(out2, ref + resid.double()) < 1e-5
+
+
+def test_transpose_and_dgelu(cuda):
+    lib, check, ptr, sp = _lib()
+    g = torch.Generator().manual_seed(1)
+    for dt, code in ((torch.float32, 0), (torch.float16, 1), (torch.bfloat16, 2)):
+        src = torch.randn(577, 200, generator=g).to(cuda, dt)
+        out = torch.zeros(200, 584, device=cuda, dtype=torch.bfloat16)
+        check(lib.pg_transpose_to_bf16(ptr(src), code, 200, ptr(out), 584, 577, 200, sp()), "pg_transpose_to_bf16")
+        assert torch.equal(out[:, :577], src.float().t().to(torch.bfloat16))
+    u = (torch.randn(1000, 512, generator=g) * 3).to(cuda, torch.float16)
+    dh = torch.randn(1000, 512, generator=g).to(cuda) * 1e-3
+    du = torch.empty(1000, 512, device=cuda, dtype=torch.bfloat16)
+    check(lib.pg_dgelu_bf16(ptr(dh), ptr(u), ptr(du), u.numel(), sp()), "pg_dgelu_bf16")
+    x = u.float().requires_grad_(True)
+    (x * torch.sigmoid(1.702 * x)).backward(dh)
+    assert _rel(du.float(), x.grad) < 4e-3                                                 # bf16 rounding of the output
+
+
+@pytest.mark.parametrize("rows,hidden", [(37, 1024), (1000, 256), (5, 768)])
+def test_layernorm_backward(cuda, rows, hidden):
+    lib, check, ptr, sp = _lib()
+    g = torch.Generator().manual_seed(rows)
+    x = (torch.randn(rows, hidden, generator=g) * 2 + 0.3).to(cuda)
+    gamma = (1 + 0.2 * torch.randn(hidden, generator=g)).to(cuda)
+    beta = (0.1 * torch.randn(hidden, generator=g)).to(cuda)
+    dy = (torch.randn(rows, hidden, generator=g) * 1e-3).to(cuda)
+    dx0 = (torch.randn(rows, hidden, generator=g) * 1e-3).to(cuda)
+    xr = x.double().requires_grad_(True)
+    gr, br = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr, (hidden,), gr, br, 1e-5).backward(dy.double())
+    dx = dx0.clone()
+    dg = torch.full((hidden,), 0.5, device=cuda)
+    db = torch.full((hidden,), -0.25, device=cuda)
+    check(lib.pg_layernorm_backward(ptr(dy), ptr(x), ptr(gamma), ptr(dx), 1, ptr(dg), ptr(db), rows, hidden, 1e-5, sp()),
+          "pg_layernorm_backward")
+    assert _rel(dx, dx0.double() + xr.grad) < 1e-5
+    assert _rel(dg - 0.5, gr.grad) < 1e-4 and _rel(db + 0.25, br.grad) < 1e-4
+    dx2 = torch.full_like(dx, float("nan"))
+    check(lib.pg_layernorm_backward(ptr(dy), ptr(x), ptr(gamma), ptr(dx2), 0, None, None, rows, hidden, 1e-5, sp()),
+          "pg_layernorm_backward")
+    assert _rel(dx2, xr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("n_views,seq,heads", [(2, 17, 4), (3, 257, 2), (2, 577, 16), (1, 128, 1), (1, 64, 2)])
+def test_attention_backward_matches_autograd(cuda, n_views, seq, heads):
+    lib, check, ptr, sp = _lib()
+    hidden = heads * 64
+    rows = n_views * seq
+    g = torch.Generator().manual_seed(seq)
+    qkv = (torch.randn(rows, 3 * hidden, generator=g) * 0.8).to(cuda, torch.float16)
+    d_out = (torch.randn(rows, hidden, generator=g) * 1e-5).to(cuda)                      # far below fp16's normal range
+    out = torch.empty(rows, hidden, device=cuda, dtype=torch.float16)
+    lse2 = torch.empty(n_views * heads, seq, device=cuda)
+    check(lib.pg_attention_f16_lse(ptr(qkv), ptr(out), ptr(lse2), n_views, seq, heads, sp()), "pg_attention_f16_lse")
+    # fp32 reference of the same op on the same fp16 inputs
+    t = qkv.float().reshape(n_views, seq, 3, heads, 64).permute(2, 0, 3, 1, 4)            # [3, v, h, s, d]
+    q, k, v = (x.clone().requires_grad_(True) for x in t)
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    o = torch.softmax(s, dim=-1) @ v
+    ref_lse2 = torch.logsumexp(s, dim=-1) * 1.4426950408889634
+    assert (lse2.reshape(n_views, heads, seq) - ref_lse2).abs().max().item() < 2e-3
+    o.backward(d_out.reshape(n_views, seq, heads, 64).permute(0, 2, 1, 3))
+    ref = torch.stack([q.grad, k.grad, v.grad]).permute(1, 3, 0, 2, 4).reshape(rows, 3 * hidden)
+    dqkv = torch.full((rows, 3 * hidden), float("nan"), device=cuda, dtype=torch.bfloat16)
+    need = lib.pg_attention_backward_workspace_bytes(n_views, seq, heads)
+    from pigeon_b200.vit_train import _aligned_empty
+    ws = _aligned_empty(need, cuda)
+    check(lib.pg_attention_backward(ptr(qkv), ptr(out), ptr(d_out), ptr(lse2), ptr(dqkv), n_views, seq, heads, ptr(ws),
+                                    need, sp()), "pg_attention_backward")
+    got = dqkv.float()
+    assert torch.isfinite(got).all()
+    for i, name in enumerate("qkv"):
+        a, b = got[:, i * hidden:(i + 1) * hidden], ref[:, i * hidden:(i + 1) * hidden]
+        assert _rel(a, b) < 1.5e-2, (name, _rel(a, b))
+
+
+# ------------------------------------------------------------------------------------------------ whole tower vs the reference
+def _load(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    return z, json.loads(str(z["meta"]))
+
+
+def _model(meta, z, cuda):
+    from pigeon_b200 import CLIPVisionTower, SuperGuessr, VitDims, synthetic
+    dims = VitDims(**meta["dims"])
+    tower = CLIPVisionTower(dims)
+    tower.load_state_dict(synthetic.random_vit_state_dict(dims, seed=meta["sd_seed"], std=meta["std"]), strict=True)
+    sg = SuperGuessr(tower, panorama=False, should_smooth_labels=True, num_candidates=5, geocells=z["centroids"]).to(cuda)
+    g = torch.Generator().manual_seed(meta["w_seed"])
+    with torch.no_grad():
+        sg.cell_layer.weight.copy_(torch.randn(meta["C"], dims.hidden, generator=g) * 0.03)
+        sg.cell_layer.bias.copy_(torch.randn(meta["C"], generator=g) * 0.01)
+    gp = torch.Generator().manual_seed(meta["px_seed"])
+    px = torch.randn(meta["n_views"], 3, dims.image_size, dims.image_size, generator=gp)
+    return sg, px, dims
+
+
+def _check_grads(sg, z, meta, expect_names=None):
+    stride, worst = meta["stride"], {}
+    scale = max(float(z[k]) for k in z.files if k.startswith("norm/"))
+    for name, p in sg.named_parameters():
+        key = name.replace("base_model.", "")
+        if "sub/" + key not in z.files:
+            continue
+        if expect_names is not None and not expect_names(key):
+            assert p.grad is None, f"{key} should be frozen"
+            continue
+        assert p.grad is not None, key
+        got = p.grad.detach().reshape(-1).double().cpu()[::stride]
+        ref = torch.from_numpy(z["sub/" + key]).double()
+        norm = float(z["norm/" + key])
+        err = (got - ref).norm().item() / max(ref.norm().item(), 1e-30)
+        if norm < 1e-6 * scale:                       # k_proj.bias: mathematically zero gradient
+            assert got.norm().item() < 1e-3 * scale, key
+            continue
+        worst[key] = err
+        assert err < REL, (key, err)
+        cos = torch.dot(got, ref).item() / (got.norm().item() * ref.norm().item())
+        assert cos > 0.999, (key, cos)
+    return worst
+
+
+@pytest.mark.parametrize("name", ["train_tower_small", "train_tower_mid"])
+def test_tower_backward_matches_reference_autograd(cuda, name):
+    z, meta = _load(name)
+    sg, px, dims = _model(meta, z, cuda)
+    sg.train()
+    sg.max_train_views = 4                                     # forces two chunks for the 6-view fixture
+    out = sg(pixel_values=px.to(cuda), labels=torch.tensor(z["labels"]), labels_clf=torch.tensor(z["labels_clf"]))
+    np.testing.assert_allclose(float(out.loss), float(z["loss"]), rtol=1e-3)
+    sg.backward(out.loss)
+    worst = _check_grads(sg, z, meta)
+    with open(os.path.join(os.environ.get("GRAFT_REPO_ROOT", "."), "gpurun_out", "parity.log"), "a") as f:
+        f.write(f"{name}: worst per-tensor relative gradient error {max(worst.values()):.3e} "
+                f"({max(worst, key=worst.get)}), median {float(np.median(list(worst.values()))):.3e}\n")
+
+
+def test_reference_freeze_policy_and_optimizer_step(cuda):
+    """models/super_guessr.py:159-160: encoder.layers[:-1] frozen, embeddings + pre_layrnorm + last layer + head train."""
+    from pigeon_b200.training import AdamW
+    z, meta = _load("train_tower_mid")
+    sg, px, dims = _model(meta, z, cuda)
+    for p in sg.base_model.vision_model.encoder.layers[:-1].parameters():
+        p.requires_grad = False
+    sg.train()
+    lab, clf = torch.tensor(z["labels"]), torch.tensor(z["labels_clf"])
+    opt = AdamW(sg.parameters(), lr=1e-4)
+    out = sg(pixel_values=px.to(cuda), labels=lab, labels_clf=clf)
+    sg.backward(out.loss)
+    last = f"encoder.layers.{dims.layers - 1}."
+    _check_grads(sg, z, meta, expect_names=lambda k: ("encoder.layers." not in k) or (last in k))
+    before = {n: p.detach().clone() for n, p in sg.named_parameters() if p.grad is not None}
+    loss0 = float(out.loss)
+    opt.step()
+    opt.zero_grad()
+    for n, p in sg.named_parameters():
+        if n in before:
+            assert (p.detach() - before[n]).abs().max().item() > 0, n
+    out1 = sg(pixel_values=px.to(cuda), labels=lab, labels_clf=clf)     # repacked fp16 weights are the updated ones
+    assert float(out1.loss) < loss0
+    sg.backward(out1.loss)
+    sg.eval()
+    with torch.no_grad():
+        ev = sg(pixel_values=px.to(cuda), labels=lab, labels_clf=clf)
+    np.testing.assert_allclose(float(ev.loss), float(out1.loss), rtol=1e-4)
