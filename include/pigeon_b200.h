@@ -159,6 +159,7 @@ typedef struct pg_vit_saved_layer {
   void* ao;     /* f16 [rows, hidden]        attention output (input of out_proj) */
   float* x1;    /* f32 [rows, hidden]        residual stream after the attention block */
   void* xn2;    /* f16 [rows, hidden]        layer_norm2 output */
+  void* u;      /* f16 [rows, intermediate]  fc1 pre-activation */
   void* h;      /* f16 [rows, intermediate]  quick_gelu(fc1) */
 } pg_vit_saved_layer;
 
@@ -270,9 +271,10 @@ int pg_attention_f16_lse(const void* qkv, void* out, float* lse2, int32_t n_view
 size_t pg_attention_backward_workspace_bytes(int32_t n_views, int32_t seq, int32_t heads);
 int pg_attention_backward(const void* qkv, const void* out, const float* d_out, const float* lse2, void* dqkv_bf16,
                           int32_t n_views, int32_t seq, int32_t heads, void* workspace, size_t workspace_bytes, void* stream);
-/* LayerNorm backward: dx (+)= dLN(x)/dx . dy;  dgamma / dbeta (both or neither NULL) += their gradients. */
+/* LayerNorm backward: dx (+)= dLN(x)/dx . dy;  dgamma / dbeta (both or neither NULL) += their gradients;
+ * dx_bf16 (nullable): bf16 copy of the final dx, the operand of the next data-gradient GEMM. */
 int pg_layernorm_backward(const float* dy, const float* x, const float* gamma, float* dx, int32_t accumulate, float* dgamma,
-                          float* dbeta, int64_t rows, int32_t hidden, float eps, void* stream);
+                          float* dbeta, void* dx_bf16, int64_t rows, int32_t hidden, float eps, void* stream);
 /* du bf16 [n] = dh f32 [n] * quick_gelu'(u f16 [n]) */
 int pg_dgelu_bf16(const float* dh, const void* u, void* du, int64_t n, void* stream);
 /* out bf16 [cols, ldo] = transpose(src [rows, lds]); src_type 0 = f32, 1 = f16, 2 = bf16 */

@@ -33,7 +33,7 @@ class VitLayer(C.Structure):
 
 
 class VitSavedLayer(C.Structure):
-    _fields_ = [(n, c_void_p) for n in ("x0", "xn1", "qkv", "lse2", "ao", "x1", "xn2", "h")]
+    _fields_ = [(n, c_void_p) for n in ("x0", "xn1", "qkv", "lse2", "ao", "x1", "xn2", "u", "h")]
 
 
 class VitSaved(C.Structure):
@@ -81,7 +81,7 @@ SIGNATURES = {
     "pg_attention_backward_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "pg_attention_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                         c_void_p, c_size_t, c_void_p]),
-    "pg_layernorm_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int64,
+    "pg_layernorm_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64,
                                         c_int32, c_float, c_void_p]),
     "pg_dgelu_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "pg_transpose_to_bf16": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p]),

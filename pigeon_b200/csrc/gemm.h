@@ -10,6 +10,8 @@ enum GemmEpilogue {
   EPI_F32_BIAS_RESID = 2,  // out fp32 += acc + bias     (in-place residual stream update)
   EPI_F32_BIAS = 3,        // out fp32 = acc + bias      (bias may be null)
   EPI_F32_ROWMAP = 4,      // out fp32[rowmap(row)] = acc + bias ; rowmap(r) = mul*(r/div) + r%div + add
+  EPI_BF16_DGELU = 5,      // out bf16 = acc * quick_gelu'(aux fp16)          (backward through mlp.fc1's activation)
+  EPI_F16_BIAS_QGELU_SAVE = 6,  // out fp16 = quick_gelu(acc + bias), aux fp16 = acc + bias (training forward of mlp.fc1)
 };
 
 struct GemmProblem {
@@ -25,6 +27,7 @@ struct GemmProblem {
   int rowmap_div, rowmap_mul, rowmap_add;
   int operand_bf16;     // A and W hold bf16 instead of fp16 (backward GEMMs); outputs are unaffected
   const float* resid;   // EPI_F32_BIAS_RESID: residual read from here instead of `out` (same ldo); nullptr = in place
+  void* aux;            // fp16 [M, ldo]: pre-activation read by EPI_BF16_DGELU / written by EPI_F16_BIAS_QGELU_SAVE
 };
 
 // Enqueues the GEMM on `stream`. Returns 0 on success; on failure the message is in pg::last_error().

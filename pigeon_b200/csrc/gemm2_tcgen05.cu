@@ -224,7 +224,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 template <int EPI>
 int launch2(const GemmProblem& p, int num_sms, cudaStream_t stream) {
-  constexpr bool f16_out = (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_QGELU);
+  constexpr bool f16_out = EpiTraits<EPI>::kF16Out || EPI == EPI_BF16_DGELU;   // 2-byte output elements
   CUtensorMap ta, tb;
   if (make_tmap_f16_2d(&ta, p.a, p.M, p.K, p.lda, BLOCK_M_CTA, BLOCK_K)) return 1;
   if (make_tmap_f16_2d(&tb, p.w, p.N, p.K, p.ldw, BLOCK_N_CTA, BLOCK_K)) return 1;
@@ -241,11 +241,15 @@ int launch2(const GemmProblem& p, int num_sms, cudaStream_t stream) {
   a.rowmap_div = p.rowmap_div > 0 ? p.rowmap_div : 1; a.rowmap_mul = p.rowmap_mul; a.rowmap_add = p.rowmap_add;
   a.idesc_fmt = p.operand_bf16 ? ((1u << 7) | (1u << 10)) : 0u;
   a.resid = p.resid ? p.resid : reinterpret_cast<const float*>(p.out);
+  a.aux = p.aux;
+  if ((EPI == EPI_BF16_DGELU || EPI == EPI_F16_BIAS_QGELU_SAVE) && (!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15))) {
+    set_last_error("gemm: this epilogue needs a 16-byte aligned aux buffer"); return 1;
+  }
   const int tiles = ((p.M + 255) / 256) * (p.N / BLOCK_N);
   int pairs = num_sms / 2;
   if (tiles < pairs) pairs = tiles;
   static const char* const kNames[] = {"gemm_f16_bias", "gemm_f16_bias_qgelu", "gemm_f32_bias_resid", "gemm_f32_bias",
-                                       "gemm_f32_rowmap"};
+                                       "gemm_f32_rowmap", "gemm_bf16_dgelu", "gemm_f16_bias_qgelu_save"};
   ProfScope prof(kNames[EPI], stream);
   kern<<<2 * pairs, kNumThreads, kSmemBytes, stream>>>(ta, tb, a);
   cudaError_t e = cudaGetLastError();
@@ -262,6 +266,8 @@ int gemm2_f16(const GemmProblem& p, int num_sms, cudaStream_t stream) {
     case EPI_F32_BIAS_RESID: return launch2<EPI_F32_BIAS_RESID>(p, num_sms, stream);
     case EPI_F32_BIAS:       return launch2<EPI_F32_BIAS>(p, num_sms, stream);
     case EPI_F32_ROWMAP:     return launch2<EPI_F32_ROWMAP>(p, num_sms, stream);
+    case EPI_BF16_DGELU:     return launch2<EPI_BF16_DGELU>(p, num_sms, stream);
+    case EPI_F16_BIAS_QGELU_SAVE: return launch2<EPI_F16_BIAS_QGELU_SAVE>(p, num_sms, stream);
     default: set_last_error("gemm2: unknown epilogue %d", p.epi); return 1;
   }
 }

@@ -4,6 +4,8 @@
 #include "gemm.h"
 #include "ptx.cuh"
 
+#include <cuda_bf16.h>
+
 namespace pg {
 
 constexpr int kStageWarpBytes = 32 * 128;   // per epilogue warp: 32 rows x 128 B, 16-byte pieces XOR-swizzled by (row & 7)
@@ -18,6 +20,7 @@ struct GemmArgs {
   int vec_ok;  // output rows are 16-byte aligned -> vector stores allowed
   uint32_t idesc_fmt;  // A/B format bits of the instruction descriptor (0 = fp16, bf16 otherwise)
   const float* resid;  // residual source of EPI_F32_BIAS_RESID (== out when updating in place)
+  void* aux;           // EPI_BF16_DGELU: fc1 pre-activation (fp16, read);  EPI_F16_BIAS_QGELU_SAVE: where to keep it (written)
 };
 
 __device__ __forceinline__ float quick_gelu(float v) {
@@ -25,6 +28,19 @@ __device__ __forceinline__ float quick_gelu(float v) {
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.4554669595930157f * v));
   return __fdividef(v, 1.0f + e);
+}
+
+__device__ __forceinline__ float quick_gelu_grad(float x) {
+  // d/dx [x * sigmoid(1.702 x)] = s * (1 + 1.702 x (1 - s))
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.4554669595930157f * x));
+  const float sg = __fdividef(1.0f, 1.0f + e);
+  return sg * (1.0f + 1.702f * x * (1.0f - sg));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
 // One epilogue warp's share of one output tile: rows [warp_row0, warp_row0 + 32), tile columns [c_begin, c_end).
@@ -36,9 +52,9 @@ __device__ __forceinline__ float quick_gelu(float v) {
 // update are fetched ONE CHUNK AHEAD so that their HBM latency hides behind the current chunk's work.
 template <int EPI>
 struct EpiTraits {
-  static constexpr bool kF16Out = (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_QGELU);
+  static constexpr bool kF16Out = (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_QGELU || EPI == EPI_F16_BIAS_QGELU_SAVE);
   static constexpr int CHUNK = kF16Out ? 64 : 32;
-  static constexpr int kElt = kF16Out ? 2 : 4;
+  static constexpr int kElt = kF16Out ? 2 : 4;   // EPI_BF16_DGELU stages fp32 (CHUNK 32) and stores 2-byte elements
 };
 
 template <int EPI>
@@ -99,7 +115,51 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
           if (col0 + i < args.N) v[i] += __ldg(args.bias + col0 + i);
       }
     }
-    if (EPI == EPI_F16_BIAS_QGELU) {
+    constexpr bool kDgelu = (EPI == EPI_BF16_DGELU);
+    constexpr bool kSave = (EPI == EPI_F16_BIAS_QGELU_SAVE);
+    uint2 aux_u[8];
+    if (kDgelu && fast) {   // this lane's pre-activation pieces for the coalesced phase, issued before the staging work
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int grow = warp_row0 + i * 4 + sub;
+        aux_u[i] = make_uint2(0u, 0u);
+        if (grow < args.M)
+          aux_u[i] = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(args.aux) + (long)grow * args.ldo +
+                                                     col0 + c16 * 4);
+      }
+    }
+    if (kSave && fast) {    // keep the pre-activation (fp16) for the backward pass: same staging / coalesced store, to aux
+      uint8_t* srow = stage + lane * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 pk;
+        pk.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
+        pk.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+        pk.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+        pk.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+        *reinterpret_cast<uint4*>(srow + ((j ^ (lane & 7)) << 4)) = pk;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + sub;
+        const int grow = warp_row0 + rr;
+        if (grow < args.M)
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(args.aux) + ((long)grow * args.ldo + col0) * 2 + c16 * 16) =
+              *reinterpret_cast<const uint4*>(stage + rr * 128 + ((c16 ^ (rr & 7)) << 4));
+      }
+      __syncwarp();
+    }
+    if (EPI == EPI_F16_BIAS_QGELU || kSave) {
+      if (kSave && !fast) {   // ragged tail: scalar stores of the pre-activation
+        const int row = warp_row0 + lane;
+        if (row < args.M) {
+          __half* o = reinterpret_cast<__half*>(args.aux) + (long)row * args.ldo + col0;
+#pragma unroll
+          for (int i = 0; i < CHUNK; ++i)
+            if (col0 + i < args.N) o[i] = __float2half_rn(v[i]);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < CHUNK; ++i) v[i] = quick_gelu(v[i]);
     }
@@ -133,6 +193,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
           long orow = grow;
           if (EPI == EPI_F32_ROWMAP)
             orow = (long)args.rowmap_mul * (grow / args.rowmap_div) + (grow % args.rowmap_div) + args.rowmap_add;
+          if (kDgelu) {   // 4 fp32 gradients x gelu'(u) -> 4 bf16 (8 bytes per lane, 64 contiguous bytes per row segment)
+            const float2 u01 = __half22float2(*reinterpret_cast<const __half2*>(&aux_u[i].x));
+            const float2 u23 = __half22float2(*reinterpret_cast<const __half2*>(&aux_u[i].y));
+            uint2 o;
+            o.x = pack_bf16x2_rn(__uint_as_float(val.x) * quick_gelu_grad(u01.x), __uint_as_float(val.y) * quick_gelu_grad(u01.y));
+            o.y = pack_bf16x2_rn(__uint_as_float(val.z) * quick_gelu_grad(u23.x), __uint_as_float(val.w) * quick_gelu_grad(u23.y));
+            *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(args.out) + (orow * args.ldo + col0) * 2 + c16 * 8) = o;
+            continue;
+          }
           uint8_t* gp = reinterpret_cast<uint8_t*>(args.out) + (orow * args.ldo + col0) * kElt + c16 * 16;
           if (kResid) {
             val.x = __float_as_uint(__uint_as_float(val.x) + res[i].x);
@@ -155,6 +224,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
 #pragma unroll
           for (int i = 0; i < CHUNK; ++i)
             if (col0 + i < args.N) o[i] = __float2half_rn(v[i]);
+        } else if (kDgelu) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + orow * args.ldo + col0;
+          const __half* u = reinterpret_cast<const __half*>(args.aux) + orow * args.ldo + col0;
+#pragma unroll
+          for (int i = 0; i < CHUNK; ++i)
+            if (col0 + i < args.N) o[i] = __float2bfloat16_rn(v[i] * quick_gelu_grad(__half2float(u[i])));
         } else {
           float* o = reinterpret_cast<float*>(args.out) + orow * args.ldo + col0;
 #pragma unroll

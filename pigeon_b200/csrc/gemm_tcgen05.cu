@@ -170,7 +170,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 template <int BLOCK_N, int EPI>
 int launch(const GemmProblem& p, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
-  constexpr bool f16_out = (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_QGELU);
+  constexpr bool f16_out = EpiTraits<EPI>::kF16Out || EPI == EPI_BF16_DGELU;   // 2-byte output elements
   CUtensorMap ta, tb;
   if (make_tmap_f16_2d(&ta, p.a, p.M, p.K, p.lda, BLOCK_M, BLOCK_K)) return 1;
   if (make_tmap_f16_2d(&tb, p.w, p.N, p.K, p.ldw, BLOCK_N, BLOCK_K)) return 1;
@@ -187,10 +187,15 @@ int launch(const GemmProblem& p, int num_sms, cudaStream_t stream) {
   a.rowmap_div = p.rowmap_div > 0 ? p.rowmap_div : 1; a.rowmap_mul = p.rowmap_mul; a.rowmap_add = p.rowmap_add;
   a.idesc_fmt = p.operand_bf16 ? ((1u << 7) | (1u << 10)) : 0u;
   a.resid = p.resid ? p.resid : reinterpret_cast<const float*>(p.out);
+  a.aux = p.aux;
+  if ((EPI == EPI_BF16_DGELU || EPI == EPI_F16_BIAS_QGELU_SAVE) && (!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15))) {
+    set_last_error("gemm: this epilogue needs a 16-byte aligned aux buffer"); return 1;
+  }
   const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M, n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int tiles = m_blocks * n_blocks;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  static const char* const kNames[] = {"gemm_f16_bias", "gemm_f16_bias_qgelu", "gemm_f32_bias_resid", "gemm_f32_bias", "gemm_f32_rowmap"};
+  static const char* const kNames[] = {"gemm_f16_bias", "gemm_f16_bias_qgelu", "gemm_f32_bias_resid", "gemm_f32_bias", "gemm_f32_rowmap",
+                                       "gemm_bf16_dgelu", "gemm_f16_bias_qgelu_save"};
   ProfScope prof(kNames[EPI], stream);
   kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, a);
   cudaError_t e = cudaGetLastError();
@@ -227,6 +232,9 @@ int gemm_f16(const GemmProblem& p, int num_sms, cudaStream_t stream) {
     case EPI_F32_BIAS_RESID: return wide ? launch<256, EPI_F32_BIAS_RESID>(p, num_sms, stream) : launch<128, EPI_F32_BIAS_RESID>(p, num_sms, stream);
     case EPI_F32_BIAS:       return wide ? launch<256, EPI_F32_BIAS>(p, num_sms, stream)       : launch<128, EPI_F32_BIAS>(p, num_sms, stream);
     case EPI_F32_ROWMAP:     return wide ? launch<256, EPI_F32_ROWMAP>(p, num_sms, stream)     : launch<128, EPI_F32_ROWMAP>(p, num_sms, stream);
+    case EPI_BF16_DGELU:     return wide ? launch<256, EPI_BF16_DGELU>(p, num_sms, stream)     : launch<128, EPI_BF16_DGELU>(p, num_sms, stream);
+    case EPI_F16_BIAS_QGELU_SAVE:
+      return wide ? launch<256, EPI_F16_BIAS_QGELU_SAVE>(p, num_sms, stream) : launch<128, EPI_F16_BIAS_QGELU_SAVE>(p, num_sms, stream);
     default: set_last_error("gemm: unknown epilogue %d", p.epi); return 1;
   }
 }

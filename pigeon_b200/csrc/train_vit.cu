@@ -110,7 +110,7 @@ template <int NV4>
 __global__ void __launch_bounds__(256)
 ln_backward_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                    float* __restrict__ dx_out, int accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                   long rows, float eps) {
+                   __nv_bfloat16* __restrict__ dx_bf16, long rows, float eps) {
   constexpr int hidden = NV4 * 128;
   __shared__ float red[8][128];   // reused per float4 slot when reducing dgamma / dbeta across the 8 warps
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -164,6 +164,13 @@ ln_backward_kernel(const float* __restrict__ dy, const float* __restrict__ x, co
         o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
       }
       outr[lane + 32 * i] = o;
+      if (dx_bf16 != nullptr) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(o.x, o.y), b = __floats2bfloat162_rn(o.z, o.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&a);
+        pk.y = *reinterpret_cast<uint32_t*>(&b);
+        reinterpret_cast<uint2*>(dx_bf16 + row * hidden)[lane + 32 * i] = pk;
+      }
     }
   }
   if (dgamma != nullptr) {   // block-uniform
@@ -306,7 +313,7 @@ int dgelu_bf16(const float* dh, const void* u, void* du, long n, cudaStream_t st
   }
 
 int layernorm_backward(const float* dy, const float* x, const float* gamma, float* dx_out, int accumulate, float* dgamma,
-                       float* dbeta, long rows, int hidden, float eps, int num_sms, cudaStream_t stream) {
+                       float* dbeta, void* dx_bf16, long rows, int hidden, float eps, int num_sms, cudaStream_t stream) {
   if (hidden % 128) { set_last_error("layernorm_backward: hidden %d not a multiple of 128", hidden); return 1; }
   if ((dgamma == nullptr) != (dbeta == nullptr)) { set_last_error("layernorm_backward: dgamma and dbeta go together"); return 1; }
   if (rows <= 0) return 0;
@@ -314,8 +321,9 @@ int layernorm_backward(const float* dy, const float* x, const float* gamma, floa
   const long cap = (long)(num_sms > 0 ? num_sms : 148) * 8;
   if (blocks > cap) blocks = cap;
   ProfScope prof("train_ln_backward", stream);
-  PG_DISPATCH_NV4(hidden, (ln_backward_kernel<NV4><<<(int)blocks, 256, 0, stream>>>(dy, x, gamma, dx_out, accumulate,
-                                                                                  dgamma, dbeta, rows, eps)));
+  PG_DISPATCH_NV4(hidden, (ln_backward_kernel<NV4><<<(int)blocks, 256, 0, stream>>>(
+                              dy, x, gamma, dx_out, accumulate, dgamma, dbeta, reinterpret_cast<__nv_bfloat16*>(dx_bf16), rows,
+                              eps)));
   return check_launch("layernorm_backward");
 }
 

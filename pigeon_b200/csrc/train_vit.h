@@ -15,8 +15,10 @@ int transpose_to_bf16(const void* src, int src_type, long lds, void* out_bf16, l
 // du bf16 [n] = dh f32 [n] * quick_gelu'(u f16 [n])
 int dgelu_bf16(const float* dh, const void* u_f16, void* du_bf16, long n, cudaStream_t stream);
 // LayerNorm backward over the last dim.  dx_out (+)= dLN/dx; dgamma / dbeta (nullable) += their gradients.
+// dx_bf16 (nullable): bf16 copy of the final dx_out row, so that the next GEMM needs no separate cast pass.
 int layernorm_backward(const float* dy, const float* x, const float* gamma, float* dx_out, int accumulate,
-                       float* dgamma, float* dbeta, long rows, int hidden, float eps, int num_sms, cudaStream_t stream);
+                       float* dgamma, float* dbeta, void* dx_bf16, long rows, int hidden, float eps, int num_sms,
+                       cudaStream_t stream);
 // delta f32 [n_views*heads, seq] = sum over head_dim of dO * O;  do_bf16 = bf16(dO).  dO f32 / O f16: [n_views*seq, heads*64]
 int attention_delta(const float* d_out, const void* out_f16, float* delta, void* do_bf16, int n_views, int seq, int heads,
                     int num_sms, cudaStream_t stream);

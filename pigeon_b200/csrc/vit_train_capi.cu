@@ -20,9 +20,8 @@ namespace {
 struct BwdWs {
   float* g;        // f32 [rows, hidden]   gradient of the residual stream
   void* g16;       // bf16 [rows, hidden]
-  float* t32;      // f32 [rows, wide]     data-gradient GEMM outputs
+  float* t32;      // f32 [rows, hidden]   data-gradient GEMM outputs (dXn2 | dAO | dXn1 | dE)
   void* t16;       // bf16 [rows, wide]    dU | dqkv
-  void* u16;       // f16 [rows, inter]    recomputed fc1 pre-activation
   void* qkv_bf;    // bf16 [rows, 3 hidden]
   void* do_bf;     // bf16 [rows, hidden]
   float* delta;    // f32 [n_views*heads*tokens]
@@ -42,9 +41,8 @@ BwdWs carve_bwd(const pg_vit* h, int n_views, void* ws) {
   Carver cv(ws);
   w.g = reinterpret_cast<float*>(cv.take(rows * c.hidden * 4));
   w.g16 = cv.take(rows * c.hidden * 2);
-  w.t32 = reinterpret_cast<float*>(cv.take(rows * (size_t)wide * 4));
+  w.t32 = reinterpret_cast<float*>(cv.take(rows * (size_t)c.hidden * 4));
   w.t16 = cv.take(rows * (size_t)wide * 2);
-  w.u16 = cv.take(rows * (size_t)c.intermediate * 2);
   w.qkv_bf = cv.take(rows * (size_t)3 * c.hidden * 2);
   w.do_bf = cv.take(rows * c.hidden * 2);
   w.delta = reinterpret_cast<float*>(cv.take((size_t)n_views * c.heads * h->tokens * 4));
@@ -95,7 +93,7 @@ int pg_vit_forward_train(pg_vit* h, const void* pixels, int32_t pixels_f16, int3
   const int np = h->grid_patches * h->grid_patches;
   for (int l = 0; l < c.layers; ++l) {
     const pg_vit_saved_layer& s = sv->layers_host[l];
-    if (!s.x0 || !s.xn1 || !s.qkv || !s.lse2 || !s.ao || !s.x1 || !s.xn2 || !s.h) {
+    if (!s.x0 || !s.xn1 || !s.qkv || !s.lse2 || !s.ao || !s.x1 || !s.xn2 || !s.u || !s.h) {
       set_last_error("pg_vit_forward_train: layer %d has a null save buffer", l);
       return 1;
     }
@@ -133,7 +131,7 @@ int pg_vit_forward_train(pg_vit* h, const void* pixels, int32_t pixels_f16, int3
     p = GemmProblem{};
     p.M = (int)rows; p.N = c.intermediate; p.K = c.hidden;
     p.a = s.xn2; p.lda = c.hidden; p.w = L.w_fc1; p.ldw = c.hidden;
-    p.out = s.h; p.ldo = c.intermediate; p.bias = L.b_fc1; p.epi = EPI_F16_BIAS_QGELU;
+    p.out = s.h; p.ldo = c.intermediate; p.bias = L.b_fc1; p.epi = EPI_F16_BIAS_QGELU_SAVE; p.aux = s.u;
     if (gemm_f16(p, sms, stream)) return 1;
     p = GemmProblem{};
     p.M = (int)rows; p.N = c.hidden; p.K = c.intermediate;
@@ -194,16 +192,14 @@ int pg_vit_backward(pg_vit* h, const pg_vit_saved* sv, const float* d_emb, int32
     const bool train = B.d_w_qkv != nullptr;   // every layer in [lowest, layers) is trainable or above a trainable one
 
     // ---- MLP block: x2 = x1 + fc2(quick_gelu(fc1(LN2(x1))))
-    if (cast_to_bf16(w.g, SRC_F32, w.g16, rows * H, st)) return 1;
-    if (dgrad(w.g16, B.w_fc2_t, w.t32, rows, I, H, sms, st)) return 1;                         // dH = dX2 . W2
+    if (l == c.layers - 1 && cast_to_bf16(w.g, SRC_F32, w.g16, rows * H, st)) return 1;   // below, LN backward leaves g16
     {
-      GemmProblem p{};                                                                         // fc1 pre-activation, again
+      GemmProblem p{};                                                    // dU = (dX2 . W2) o quick_gelu'(U), fused epilogue
       p.M = (int)rows; p.N = I; p.K = H;
-      p.a = s.xn2; p.lda = H; p.w = L.w_fc1; p.ldw = H;
-      p.out = w.u16; p.ldo = I; p.bias = L.b_fc1; p.epi = EPI_F16_BIAS;
+      p.a = w.g16; p.lda = H; p.w = B.w_fc2_t; p.ldw = H;
+      p.out = w.t16; p.ldo = I; p.bias = nullptr; p.epi = EPI_BF16_DGELU; p.operand_bf16 = 1; p.aux = s.u;
       if (gemm_f16(p, sms, st)) return 1;
     }
-    if (dgelu_bf16(w.t32, w.u16, w.t16, rows * I, st)) return 1;                               // dU = dH o gelu'(U)
     if (train) {
       if (wgrad(w.g16, SRC_BF16, H, H, s.h, SRC_F16, I, I, rows, B.d_w_fc2, w, sms, st)) return 1;
       if (column_sum_accumulate(w.g, SRC_F32, H, B.d_b_fc2, rows, H, st)) return 1;
@@ -211,12 +207,11 @@ int pg_vit_backward(pg_vit* h, const pg_vit_saved* sv, const float* d_emb, int32
       if (column_sum_accumulate(w.t16, SRC_BF16, I, B.d_b_fc1, rows, I, st)) return 1;
     }
     if (dgrad(w.t16, B.w_fc1_t, w.t32, rows, H, I, sms, st)) return 1;                         // dXn2 = dU . W1
-    if (layernorm_backward(w.t32, s.x1, L.ln2_g, w.g, 1, train ? B.d_ln2_g : nullptr, train ? B.d_ln2_b : nullptr, rows, H,
-                           c.ln_eps, sms, st))
-      return 1;                                                                                // g = dX1
+    if (layernorm_backward(w.t32, s.x1, L.ln2_g, w.g, 1, train ? B.d_ln2_g : nullptr, train ? B.d_ln2_b : nullptr, w.g16,
+                           rows, H, c.ln_eps, sms, st))
+      return 1;                                                                                // g = dX1 (+ bf16 copy)
 
     // ---- attention block: x1 = x0 + out_proj(attention(qkv(LN1(x0))))
-    if (cast_to_bf16(w.g, SRC_F32, w.g16, rows * H, st)) return 1;
     if (dgrad(w.g16, B.w_o_t, w.t32, rows, H, H, sms, st)) return 1;                           // dAO = dX1 . Wo
     if (train) {
       if (wgrad(w.g16, SRC_BF16, H, H, s.ao, SRC_F16, H, H, rows, B.d_w_o, w, sms, st)) return 1;
@@ -230,14 +225,15 @@ int pg_vit_backward(pg_vit* h, const pg_vit_saved* sv, const float* d_emb, int32
       if (column_sum_accumulate(w.t16, SRC_BF16, 3 * H, B.d_b_qkv, rows, 3 * H, st)) return 1;
     }
     if (dgrad(w.t16, B.w_qkv_t, w.t32, rows, H, 3 * H, sms, st)) return 1;                     // dXn1 = dqkv . Wqkv
-    if (layernorm_backward(w.t32, s.x0, L.ln1_g, w.g, 1, train ? B.d_ln1_g : nullptr, train ? B.d_ln1_b : nullptr, rows, H,
-                           c.ln_eps, sms, st))
-      return 1;                                                                                // g = dX0
+    if (layernorm_backward(w.t32, s.x0, L.ln1_g, w.g, 1, train ? B.d_ln1_g : nullptr, train ? B.d_ln1_b : nullptr, w.g16,
+                           rows, H, c.ln_eps, sms, st))
+      return 1;                                                                                // g = dX0 (+ bf16 copy)
   }
 
   if (emb_train) {
     // pre_layrnorm backward: g = d(pre-LN output) -> t32 = dE
-    if (layernorm_backward(w.g, sv->e, h->w.pre_ln_g, w.t32, 0, gr->d_pre_ln_g, gr->d_pre_ln_b, rows, H, c.ln_eps, sms, st))
+    if (layernorm_backward(w.g, sv->e, h->w.pre_ln_g, w.t32, 0, gr->d_pre_ln_g, gr->d_pre_ln_b, nullptr, rows, H, c.ln_eps,
+                           sms, st))
       return 1;
     if (embed_backward(w.t32, gr->d_pos_emb, gr->d_class_emb, n_views, h->tokens, H, st)) return 1;
     // patch_embedding.weight [hidden, patch_k_pad] += dE[patch tokens]^T . im2col
@@ -300,11 +296,11 @@ int pg_attention_backward(const void* qkv, const void* out, const float* d_out, 
 }
 
 int pg_layernorm_backward(const float* dy, const float* x, const float* gamma, float* dx, int32_t accumulate, float* dgamma,
-                          float* dbeta, int64_t rows, int32_t hidden, float eps, void* stream) {
+                          float* dbeta, void* dx_bf16, int64_t rows, int32_t hidden, float eps, void* stream) {
   if (!dy || !x || !gamma || !dx) { set_last_error("pg_layernorm_backward: null argument"); return 1; }
   const int sms = sm_count();
   if (sms < 0) return 1;
-  return layernorm_backward(dy, x, gamma, dx, accumulate, dgamma, dbeta, rows, hidden, eps, sms,
+  return layernorm_backward(dy, x, gamma, dx, accumulate, dgamma, dbeta, dx_bf16, rows, hidden, eps, sms,
                             reinterpret_cast<cudaStream_t>(stream));
 }
 

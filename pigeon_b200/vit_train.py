@@ -74,7 +74,7 @@ class TowerTrainer:
         H, I = d.hidden, d.intermediate
         per_layer = [("x0", rows * H * 4), ("xn1", rows * H * 2), ("qkv", rows * 3 * H * 2),
                      ("lse2", n_views * d.heads * d.tokens * 4), ("ao", rows * H * 2), ("x1", rows * H * 4),
-                     ("xn2", rows * H * 2), ("h", rows * I * 2)]
+                     ("xn2", rows * H * 2), ("u", rows * I * 2), ("h", rows * I * 2)]
         top = [("im2col", n_views * (d.tokens - 1) * d.patch_k_pad * 2), ("e", rows * H * 4), ("x_out", rows * H * 4)]
         total = sum(_align(b) for _, b in top) + d.layers * sum(_align(b) for _, b in per_layer)
         dev = next(self.tower.parameters()).device
@@ -118,17 +118,25 @@ class TowerTrainer:
         d = self.dims
         dev = next(self.tower.parameters()).device
         emb_train, layers = self.layout()
-        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
-        g: Dict[str, torch.Tensor] = {}
+        shapes = []
         if emb_train:
-            g.update(patch_w=z(d.hidden, d.patch_k_pad), class_emb=z(d.hidden), pos_emb=z(d.tokens, d.hidden),
-                     pre_ln_g=z(d.hidden), pre_ln_b=z(d.hidden))
+            shapes += [("patch_w", (d.hidden, d.patch_k_pad)), ("class_emb", (d.hidden,)), ("pos_emb", (d.tokens, d.hidden)),
+                       ("pre_ln_g", (d.hidden,)), ("pre_ln_b", (d.hidden,))]
+        H, I = d.hidden, d.intermediate
         for l, t in enumerate(layers):
             if t:
-                H, I = d.hidden, d.intermediate
-                g.update({f"{l}.ln1_g": z(H), f"{l}.ln1_b": z(H), f"{l}.w_qkv": z(3 * H, H), f"{l}.b_qkv": z(3 * H),
-                          f"{l}.w_o": z(H, H), f"{l}.b_o": z(H), f"{l}.ln2_g": z(H), f"{l}.ln2_b": z(H),
-                          f"{l}.w_fc1": z(I, H), f"{l}.b_fc1": z(I), f"{l}.w_fc2": z(H, I), f"{l}.b_fc2": z(H)})
+                shapes += [(f"{l}.ln1_g", (H,)), (f"{l}.ln1_b", (H,)), (f"{l}.w_qkv", (3 * H, H)), (f"{l}.b_qkv", (3 * H,)),
+                           (f"{l}.w_o", (H, H)), (f"{l}.b_o", (H,)), (f"{l}.ln2_g", (H,)), (f"{l}.ln2_b", (H,)),
+                           (f"{l}.w_fc1", (I, H)), (f"{l}.b_fc1", (I,)), (f"{l}.w_fc2", (H, I)), (f"{l}.b_fc2", (H,))]
+        # ONE flat fp32 buffer (every tensor 16-byte aligned inside it): a single all-reduce averages the whole tower
+        offs, total = [], 0
+        for _, shp in shapes:
+            offs.append(total)
+            total += (int(torch.Size(shp).numel()) + 3) // 4 * 4
+        self._pending_flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        g: Dict[str, torch.Tensor] = {}
+        for (name, shp), o in zip(shapes, offs):
+            g[name] = self._pending_flat[o:o + int(torch.Size(shp).numel())].view(shp)
         self._pending = g
         return g
 
@@ -190,10 +198,9 @@ class TowerTrainer:
         if self._pending is None:
             return
         g, d = self._pending, self.dims
-        if world > 1:
-            for t in g.values():
-                torch.distributed.all_reduce(t)
-                t.mul_(1.0 / world)
+        if world > 1:                                  # DDP: average of the per-rank gradients (train_eval_loop.py:192)
+            torch.distributed.all_reduce(self._pending_flat)
+            self._pending_flat.mul_(1.0 / world)
         vm = self.tower.vision_model
 
         def put(p, t):

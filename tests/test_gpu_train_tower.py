@@ -88,17 +88,19 @@ def test_layernorm_backward(cuda, rows, hidden):
     dx = dx0.clone()
     dg = torch.full((hidden,), 0.5, device=cuda)
     db = torch.full((hidden,), -0.25, device=cuda)
-    check(lib.pg_layernorm_backward(ptr(dy), ptr(x), ptr(gamma), ptr(dx), 1, ptr(dg), ptr(db), rows, hidden, 1e-5, sp()),
-          "pg_layernorm_backward")
+    dx16 = torch.empty(rows, hidden, device=cuda, dtype=torch.bfloat16)
+    check(lib.pg_layernorm_backward(ptr(dy), ptr(x), ptr(gamma), ptr(dx), 1, ptr(dg), ptr(db), ptr(dx16), rows, hidden, 1e-5,
+                                    sp()), "pg_layernorm_backward")
     assert _rel(dx, dx0.double() + xr.grad) < 1e-5
+    assert torch.equal(dx16, dx.to(torch.bfloat16))
     assert _rel(dg - 0.5, gr.grad) < 1e-4 and _rel(db + 0.25, br.grad) < 1e-4
     dx2 = torch.full_like(dx, float("nan"))
-    check(lib.pg_layernorm_backward(ptr(dy), ptr(x), ptr(gamma), ptr(dx2), 0, None, None, rows, hidden, 1e-5, sp()),
+    check(lib.pg_layernorm_backward(ptr(dy), ptr(x), ptr(gamma), ptr(dx2), 0, None, None, None, rows, hidden, 1e-5, sp()),
           "pg_layernorm_backward")
     assert _rel(dx2, xr.grad) < 1e-5
 
 
-@pytest.mark.parametrize("n_views,seq,heads", [(2, 17, 4), (3, 257, 2), (2, 577, 16), (1, 128, 1), (1, 64, 2)])
+@pytest.mark.parametrize("n_views,seq,heads", [(2, 17, 4), (3, 257, 2), (2, 577, 16), (1, 128, 2), (1, 64, 2)])
 def test_attention_backward_matches_autograd(cuda, n_views, seq, heads):
     lib, check, ptr, sp = _lib()
     hidden = heads * 64
@@ -220,3 +222,16 @@ def test_reference_freeze_policy_and_optimizer_step(cuda):
     with torch.no_grad():
         ev = sg(pixel_values=px.to(cuda), labels=lab, labels_clf=clf)
     np.testing.assert_allclose(float(ev.loss), float(out1.loss), rtol=1e-4)
+
+
+def test_data_parallel_gradients_match_full_batch(cuda):
+    """2 ranks x half of the golden batch, NCCL gradient averaging == the reference's full-batch gradients."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "ddp_train_check.py")],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
