@@ -106,8 +106,8 @@ dgelu_kernel(const float* __restrict__ dh, const __half* __restrict__ u, __nv_bf
 // ------------------------------------------------------------------------------------------------ LayerNorm backward
 // One warp per row, row in registers as NV4 float4 per lane (same lane-strided mapping as the forward kernel).
 //   xhat = (x - mean) * rstd;  g = gamma * dy;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat))
-template <int NV4>
-__global__ void __launch_bounds__(256)
+template <int NV4, bool PARAM_GRADS>
+__global__ void __launch_bounds__(256, PARAM_GRADS ? 1 : 2)
 ln_backward_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                    float* __restrict__ dx_out, int accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta,
                    __nv_bfloat16* __restrict__ dx_bf16, long rows, float eps) {
@@ -115,9 +115,9 @@ ln_backward_kernel(const float* __restrict__ dy, const float* __restrict__ x, co
   __shared__ float red[8][128];   // reused per float4 slot when reducing dgamma / dbeta across the 8 warps
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long warps = ((long)gridDim.x * blockDim.x) >> 5;
-  float4 gsum[NV4], bsum[NV4];
+  float4 gsum[PARAM_GRADS ? NV4 : 1], bsum[PARAM_GRADS ? NV4 : 1];   // register accumulators only when gamma / beta train
 #pragma unroll
-  for (int i = 0; i < NV4; ++i) gsum[i] = bsum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < (PARAM_GRADS ? NV4 : 1); ++i) gsum[i] = bsum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
     float4 xv[NV4], dv[NV4];
     const float4* xr = reinterpret_cast<const float4*>(x + row * hidden);
@@ -140,7 +140,7 @@ ln_backward_kernel(const float* __restrict__ dy, const float* __restrict__ x, co
     for (int i = 0; i < NV4; ++i) {
       const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
       xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;       // xhat
-      if (dgamma != nullptr) {
+      if (PARAM_GRADS) {
         gsum[i].x += dv[i].x * xv[i].x; gsum[i].y += dv[i].y * xv[i].y;
         gsum[i].z += dv[i].z * xv[i].z; gsum[i].w += dv[i].w * xv[i].w;
         bsum[i].x += dv[i].x; bsum[i].y += dv[i].y; bsum[i].z += dv[i].z; bsum[i].w += dv[i].w;
@@ -173,7 +173,7 @@ ln_backward_kernel(const float* __restrict__ dy, const float* __restrict__ x, co
       }
     }
   }
-  if (dgamma != nullptr) {   // block-uniform
+  if (PARAM_GRADS) {
     for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
       for (int i = 0; i < NV4; ++i) {
@@ -321,9 +321,14 @@ int layernorm_backward(const float* dy, const float* x, const float* gamma, floa
   const long cap = (long)(num_sms > 0 ? num_sms : 148) * 8;
   if (blocks > cap) blocks = cap;
   ProfScope prof("train_ln_backward", stream);
-  PG_DISPATCH_NV4(hidden, (ln_backward_kernel<NV4><<<(int)blocks, 256, 0, stream>>>(
-                              dy, x, gamma, dx_out, accumulate, dgamma, dbeta, reinterpret_cast<__nv_bfloat16*>(dx_bf16), rows,
-                              eps)));
+  __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+  if (dgamma != nullptr) {
+    PG_DISPATCH_NV4(hidden, (ln_backward_kernel<NV4, true><<<(int)blocks, 256, 0, stream>>>(dy, x, gamma, dx_out, accumulate,
+                                                                                          dgamma, dbeta, d16, rows, eps)));
+  } else {
+    PG_DISPATCH_NV4(hidden, (ln_backward_kernel<NV4, false><<<(int)blocks, 256, 0, stream>>>(dy, x, gamma, dx_out, accumulate,
+                                                                                           dgamma, dbeta, d16, rows, eps)));
+  }
   return check_launch("layernorm_backward");
 }
 
