@@ -41,15 +41,18 @@ constexpr int kThreads = 192;
 // Two tilings of the same kernel:
 //   <64, 3, 2>  KV blocks of 64, three S buffers, 256 TMEM columns, 2 CTAs / SM   (S0 S1 S2 [0,192)  O [192,256))
 //   <32, 2, 4>  KV blocks of 32, two S buffers, 128 TMEM columns, 4 CTAs / SM     (S0 S1 [0,64)      O [64,128))
-template <int KV, int NBUF, int CTAS, int POLY = 0>
+template <int KV, int NBUF, int CTAS, int POLY = 0, int SLOTS = 6, bool HALVES = false>
 struct AttnCfg {
+  // HALVES: a 64-wide block is read from TMEM twice, 32 columns at a time (maximum sweep, then exponential sweep), so that the
+  // row never needs more than 32 logit registers (fits the 80-register budget of 4 CTAs per SM without spilling).
+  static constexpr bool kHalves = HALVES;
   // POLY = n > 0: every n-th group of four exponentials is evaluated on the FMA pipe (Cody-Waite + degree-4 minimax
   // polynomial, 2.9e-6 relative) instead of MUFU.EX2, to relieve the 16/clk/SM special-function unit.
   static constexpr int kPolyStride = POLY;
   static constexpr int kBlockKV = KV;
   static constexpr int kNumSBuf = NBUF;
   static constexpr int kCtasPerSm = CTAS;
-  static constexpr int kSlots = 6;
+  static constexpr int kSlots = SLOTS;
   static constexpr int kTileBytes = KV * kHeadDim * 2;
   static constexpr int kOCol = NBUF * KV;
   static constexpr int kTmemCols = (NBUF * KV + kHeadDim <= 128) ? 128 : 256;
@@ -262,9 +265,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
       mbar_wait(&s_full[j % kNumSBuf], (j / kNumSBuf) & 1);
       tc_fence_after();
 
-      uint32_t r[kBlockKV];
+      uint32_t r[Cfg::kHalves ? 32 : kBlockKV];
       float bm = -INFINITY;
-      if (!tail) {
+      if (!tail && Cfg::kHalves) {
+#pragma unroll
+        for (int h = 0; h < kBlockKV / 32; ++h) {
+          tmem_ld32(s_tmem + 32 * h, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+          tmem_ld_wait();
+          float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            b0 = fmaxf(b0, __uint_as_float(r[i]));
+            b1 = fmaxf(b1, __uint_as_float(r[i + 1]));
+            b2 = fmaxf(b2, __uint_as_float(r[i + 2]));
+            b3 = fmaxf(b3, __uint_as_float(r[i + 3]));
+          }
+          bm = fmaxf(bm, fmaxf(fmaxf(b0, b1), fmaxf(b2, b3)));
+        }
+      } else if (!tail) {
 #pragma unroll
         for (int h = 0; h < kBlockKV / 32; ++h) tmem_ld32(s_tmem + 32 * h, *reinterpret_cast<uint32_t(*)[32]>(&r[32 * h]));
         tmem_ld_wait();
@@ -317,7 +335,29 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs ar
       }
       const float mc = m * c;
 
-      if (!tail) {
+      if (!tail && Cfg::kHalves) {
+        const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
+        float2 l01 = make_float2(l0, l1), l23 = make_float2(l2, l3);
+#pragma unroll
+        for (int h = 0; h < kBlockKV / 32; ++h) {
+          tmem_ld32(s_tmem + 32 * h, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float2 x01 = ffma2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), c2, nmc2);
+            const float2 x23 = ffma2(make_float2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), c2, nmc2);
+            const float2 p01 = make_float2(ex2(x01.x), ex2(x01.y));
+            const float2 p23 = make_float2(ex2(x23.x), ex2(x23.y));
+            l01 = fadd2(l01, p01);
+            l23 = fadd2(l23, p23);
+            r[i >> 1] = pack_half2(p01.x, p01.y);
+            r[(i >> 1) + 1] = pack_half2(p23.x, p23.y);
+          }
+          // P of this half lands on S columns already consumed: [16h, 16h + 16) of the buffer
+          tmem_st16(s_tmem + 16 * h, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+        }
+        l0 = l01.x; l1 = l01.y; l2 = l23.x; l3 = l23.y;
+      } else if (!tail) {
         const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
         float2 l01 = make_float2(l0, l1), l23 = make_float2(l2, l3);
 #pragma unroll
@@ -433,6 +473,12 @@ int attention_f16(const void* qkv, void* out, int n_views, int seq, int heads, c
   // 0.436 ms per 128-view layer for the 64-wide / 3-buffer / 2-CTA tiling on the same box).  PG_ATTN_VARIANT=64 selects
   // the latter (A/B switch).
   const char* v = getenv("PG_ATTN_VARIANT");
+  if (v && v[0] == '6' && v[1] == '4' && v[2] == 's')   // experiment: 64-wide blocks, ONE S buffer, 128 TMEM columns, 4 CTAs/SM
+    return launch_attention<AttnCfg<64, 1, 4, 0, 4>>(qkv, out, n_views, seq, heads, stream, lse2);
+  if (v && v[0] == '6' && v[1] == '4' && v[2] == 'h')   // experiment: same, row processed in two 32-column halves (no spills)
+    return launch_attention<AttnCfg<64, 1, 4, 0, 4, true>>(qkv, out, n_views, seq, heads, stream, lse2);
+  if (v && v[0] == '3' && v[1] == '2' && v[2] == 'c')   // experiment: default tiling at 3 CTAs / SM (113 registers, no spills)
+    return launch_attention<AttnCfg<32, 2, 3>>(qkv, out, n_views, seq, heads, stream, lse2);
   if (v && v[0] == '6' && v[1] == '4') return launch_attention<AttnCfg<64, 3, 2>>(qkv, out, n_views, seq, heads, stream, lse2);
   const char* pe = getenv("PG_ATTN_POLY");     // experiment switch: "4" / "2" = every 4th / 2nd group on the FMA pipe
   if (pe && pe[0] == '4') return launch_attention<AttnCfg<32, 2, 4, 4>>(qkv, out, n_views, seq, heads, stream, lse2);

@@ -28,7 +28,7 @@ def timeit(fn, iters=10, warm=3):
 
 ref = None
 for rep in range(2):
-    for var, poly in (("64", ""), ("32", ""), ("32", "4"), ("32", "2")):
+    for var, poly in (("64", ""), ("32", ""), ("64s", ""), ("64h", ""), ("32c", "")):
         os.environ["PG_ATTN_VARIANT"] = var
         os.environ["PG_ATTN_POLY"] = poly
         out = ops.attention_f16(qkv, views, 577, 16)
