@@ -107,8 +107,20 @@ def train_fixture(tmp):
     labels_clf = torch.randint(0, C, (steps * acc, B), generator=g)
     out = {}
     with rs.chdir(tmp):
-        for name, smooth in (("smooth", True), ("index", False)):
-            sg = SuperGuessr(None, panorama=True, num_candidates=5, should_smooth_labels=smooth, embed_dim=D).train()
+        gm = torch.Generator().manual_seed(73)
+        labels_mt = torch.randn(steps * acc, B, 6, generator=gm)
+        labels_climate = torch.nn.functional.one_hot(torch.randint(0, 28, (steps * acc, B), generator=gm), 28).float()
+        labels_month = torch.randint(0, 12, (steps * acc, B), generator=gm)
+        out.update(labels_mt=labels_mt.numpy(), labels_climate=labels_climate.numpy(), labels_month=labels_month.numpy())
+        for name, smooth in (("smooth", True), ("index", False), ("multitask", True)):
+            mt = name == "multitask"
+            torch.manual_seed(74)      # the auxiliary heads keep nn.Linear's default init; the test rebuilds them from this seed
+            sg = SuperGuessr(None, panorama=True, num_candidates=5, should_smooth_labels=smooth, embed_dim=D,
+                             multi_task=mt).train()
+            if mt:
+                for hn in ("multi_task_head", "climate_layer", "month_layer"):
+                    out[f"mt_init_{hn}_w"] = getattr(sg, hn).weight.detach().numpy().copy()
+                    out[f"mt_init_{hn}_b"] = getattr(sg, hn).bias.detach().numpy().copy()
             with torch.no_grad():
                 sg.cell_layer.weight.copy_(W)
                 sg.cell_layer.bias.copy_(b)
@@ -116,21 +128,26 @@ def train_fixture(tmp):
             opt.zero_grad()
             losses = []
             for i in range(steps * acc):
-                o = sg(embedding=emb[i], labels=labels[i], labels_clf=labels_clf[i])
+                kw = dict(labels_multi_task=labels_mt[i], labels_climate=labels_climate[i], labels_month=labels_month[i]) if mt else {}
+                o = sg(embedding=emb[i], labels=labels[i], labels_clf=labels_clf[i], **kw)
                 o.loss.backward()
                 losses.append(float(o.loss))
                 if i % acc == acc - 1:                                            # :218-221
-                    if i == acc - 1:
+                    if i == acc - 1 and not mt:
                         out[f"{name}_grad_w_step1"] = sg.cell_layer.weight.grad.detach().numpy().copy()
                         out[f"{name}_grad_b_step1"] = sg.cell_layer.bias.grad.detach().numpy().copy()
                     opt.step()
                     opt.zero_grad()
-                    if i == acc - 1:
+                    if i == acc - 1 and not mt:
                         out[f"{name}_w_step1"] = sg.cell_layer.weight.detach().numpy().copy()
                         out[f"{name}_b_step1"] = sg.cell_layer.bias.detach().numpy().copy()
             out[f"{name}_losses"] = np.asarray(losses, dtype=np.float64)
             out[f"{name}_w_final"] = sg.cell_layer.weight.detach().numpy().copy()
             out[f"{name}_b_final"] = sg.cell_layer.bias.detach().numpy().copy()
+            if mt:
+                for hn in ("multi_task_head", "climate_layer", "month_layer"):
+                    out[f"mt_final_{hn}_w"] = getattr(sg, hn).weight.detach().numpy().copy()
+                    out[f"mt_final_{hn}_b"] = getattr(sg, hn).bias.detach().numpy().copy()
             out["centroids"] = sg.lla_geocells.detach().numpy().copy()
     np.savez_compressed(os.path.join(OUT, "train_head.npz"), emb=emb.numpy(), labels=labels.numpy(),
                         labels_clf=labels_clf.numpy(), w0=W.numpy(), b0=b.numpy(),

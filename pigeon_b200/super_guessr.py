@@ -309,7 +309,8 @@ class SuperGuessr(nn.Module):
         head = {id(self.cell_layer.weight), id(self.cell_layer.bias)}
         return [n for n, p in self.named_parameters() if p.requires_grad and id(p) not in head]
 
-    def _forward_train_tower(self, pixel_values: Tensor, labels: Optional[Tensor], labels_clf: Tensor) -> ModelOutput:
+    def _forward_train_tower(self, pixel_values: Tensor, labels: Optional[Tensor], labels_clf: Tensor,
+                             labels_multi_task=None, labels_climate=None, labels_month=None) -> ModelOutput:
         """Training-mode forward when tower parameters require grad (reference freeze policy :159-160): the batch is
         processed in chunks that fit the activation arena; each chunk runs tower forward -> head -> loss -> head
         backward -> tower backward, and gradients accumulate in pending buffers that `backward()` publishes (after the
@@ -334,6 +335,7 @@ class SuperGuessr(nn.Module):
         flat = torch.zeros(Cc * D + Cc, dtype=torch.float32, device=dev)
         lib = load()
         outs, loss_total = [], None
+        mt_out, mt_loss, mt_grads = [], [0, 0, 0], None
         with torch.no_grad():
             for lo in range(0, B, step):
                 hi = min(B, lo + step)
@@ -348,18 +350,35 @@ class SuperGuessr(nn.Module):
                 check(lib.pg_head_backward(ptr(dlog), ptr(h["pooled"]), ptr(w.detach()), n, Cc, D, 1,
                                            ptr(flat) if head_trains else None, ptr(flat[Cc * D:]) if head_trains else None,
                                            ptr(dpooled), current_stream_ptr()), "pg_head_backward")
+                if self.multi_task:
+                    sl = lambda t: None if t is None else t[lo:hi]
+                    mt = self._multi_task(h["pooled"], sl(labels_multi_task), sl(labels_climate), sl(labels_month), dev, True,
+                                          weight=n / B)
+                    mt_out.append(mt[:3])
+                    for i in range(3):
+                        mt_loss[i] = mt_loss[i] + mt[3 + i] * (n / B)
+                    dpooled += mt[6]
+                    mt_grads = mt[7] if mt_grads is None else [a + b_ for a, b_ in zip(mt_grads, mt[7])]
                 d_emb = (dpooled / V).repeat_interleave(V, dim=0) if V > 1 else dpooled      # backward of the view mean
                 tr.backward(d_emb)
                 part = loss.double() * (n / B)
                 loss_total = part if loss_total is None else loss_total + part
                 outs.append((h, emb))
         self._pend_head = flat
+        self._pend_mt = mt_grads
         cat = lambda k: torch.cat([h[k] for h, _ in outs])
         embedding = torch.cat([e for _, e in outs])
-        loss = loss_total if self.should_smooth_labels else loss_total.to(torch.float32)
+        loss_clf = loss_total if self.should_smooth_labels else loss_total.to(torch.float32)
         self.last_pooled = cat("pooled")
-        return ModelOutput(loss, loss, 0, 0, 0, cat("pred_lnglat"), cat("pred_cell"), None, None, None,
-                           TopK(cat("topk_val"), cat("topk_idx")), embedding if self.panorama else embedding[:, 0])
+        preds_mt = preds_climate = preds_month = None
+        loss = loss_clf
+        if self.multi_task:
+            mcat = lambda i: None if mt_out[0][i] is None else torch.cat([m[i] for m in mt_out])
+            preds_mt, preds_climate, preds_month = mcat(0), mcat(1), mcat(2)
+            loss = loss_clf + mt_loss[0] + mt_loss[1] + mt_loss[2]
+        return ModelOutput(loss, loss_clf, mt_loss[0], mt_loss[1], mt_loss[2], cat("pred_lnglat"), cat("pred_cell"), preds_mt,
+                           preds_climate, preds_month, TopK(cat("topk_val"), cat("topk_idx")),
+                           embedding if self.panorama else embedding[:, 0])
 
     def backward(self, loss: Optional[Tensor] = None, grad_scale: float = 1.0) -> None:
         """What `accelerator.backward(output.loss)` does in reference training/train_eval_loop.py:216 for the
@@ -383,6 +402,8 @@ class SuperGuessr(nn.Module):
                     w.grad.add_(flat[: Cc * D].view(Cc, D))
                     b.grad.add_(flat[Cc * D:])
             self._trainer.finalize(world)
+            self._publish_mt_grads(getattr(self, "_pend_mt", None), world)
+            self._pend_mt = None
             return
         if getattr(self, "_saved_dlogits", None) is None or self.last_pooled is None:
             raise PigeonB200Error("backward() needs a preceding training-mode forward with labels")
@@ -413,6 +434,54 @@ class SuperGuessr(nn.Module):
             check(lib.pg_head_backward(ptr(dlog), ptr(pooled), None, B, Cc, D, 0 if fresh else 1, ptr(w.grad), ptr(b.grad),
                                        None, current_stream_ptr()), "pg_head_backward")
         self._saved_dlogits = None
+        self._publish_mt_grads(getattr(self, "_saved_mt", None), world)
+        self._saved_mt = None
+
+    # ---------------------------------------------------------------------------------- multi-task heads (:315-348)
+    _MT_HEADS = ("multi_task_head", "climate_layer", "month_layer")
+
+    def _mt_params(self):
+        return [p for n in self._MT_HEADS if hasattr(self, n) for p in getattr(self, n).parameters() if p.requires_grad]
+
+    def _multi_task(self, output: Tensor, labels_multi_task, labels_climate, labels_month, dev, want_grad: bool,
+                    weight: float = 1.0):
+        """The three auxiliary Linear heads and their losses — thin PyTorch on the GPU, not a kernel target.  With
+        `want_grad`, torch autograd also returns d(weight * their losses) / d pooled and their parameter gradients."""
+        with (torch.enable_grad() if want_grad else torch.no_grad()):
+            x = output.detach().requires_grad_(want_grad)
+            preds_mt = self.multi_task_head(x)
+            preds_climate = self.climate_layer(x)
+            preds_month = None if self.yfcc else self.month_layer(x)
+            loss_reg = loss_climate = loss_month = 0
+            if not self.serving:
+                loss_reg = self.loss_fnc_mt(preds_mt, labels_multi_task.to(dev)) * REGRESSION_LOSS_SCALING
+                loss_climate = self.loss_fnc_climate(preds_climate, labels_climate.to(dev, torch.float32)) * CLIMATE_LOSS_SCALING
+                if not self.yfcc:
+                    loss_month = self.loss_fnc_month(preds_month, labels_month.to(dev)) * MONTHS_LOSS_SCALING
+            dx, pgrads = None, None
+            if want_grad:
+                params = self._mt_params()
+                g = torch.autograd.grad((loss_reg + loss_climate + loss_month) * weight, [x] + params)
+                dx, pgrads = g[0], list(g[1:])
+        det = lambda t: t.detach() if isinstance(t, Tensor) else t
+        return (det(preds_mt), det(preds_climate), det(preds_month), det(loss_reg), det(loss_climate), det(loss_month),
+                dx, pgrads)
+
+    def _publish_mt_grads(self, pgrads, world: int) -> None:
+        """Auxiliary-head gradients of this backward: averaged across ranks like DDP, then accumulated into `.grad`."""
+        if not pgrads:
+            return
+        if world > 1:
+            flat = torch.cat([g.reshape(-1) for g in pgrads])
+            torch.distributed.all_reduce(flat)
+            flat.mul_(1.0 / world)
+            out, o = [], 0
+            for g in pgrads:
+                out.append(flat[o:o + g.numel()].view_as(g))
+                o += g.numel()
+            pgrads = out
+        for p, g in zip(self._mt_params(), pgrads):
+            p.grad = g.clone() if p.grad is None else p.grad.add_(g)
 
     # ---------------------------------------------------------------------------------- forward (reference :350-483)
     def forward(self, pixel_values: Tensor = None, embedding: Tensor = None, heading: Tensor = None,
@@ -421,15 +490,14 @@ class SuperGuessr(nn.Module):
         self._assert_requirements(pixel_values, embedding, heading)
         want_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if want_grad:
-            if self.multi_task:
-                raise NotImplementedError("the B200 fine-tune step does not cover the multi-task heads (multi_task=True); "
-                                          "call .eval() / torch.no_grad() for inference")
             tower_trains = self.base_model is not None and any(p.requires_grad for p in self.base_model.parameters())
-            stray = [n for n in self._trainable_outside_head() if not n.startswith("base_model.")]
+            stray = [n for n in self._trainable_outside_head()
+                     if not n.startswith("base_model.") and n.split(".")[0] not in self._MT_HEADS]
             if stray:
                 raise NotImplementedError(f"no backward for trainable parameters {stray[:3]}")
             if tower_trains:
-                return self._forward_train_tower(pixel_values, labels, labels_clf)
+                return self._forward_train_tower(pixel_values, labels, labels_clf, labels_multi_task, labels_climate,
+                                                 labels_month)
         dev = self._device()
         with torch.no_grad():
             # host -> device (reference _move_to_cuda, :193-217)
@@ -468,16 +536,11 @@ class SuperGuessr(nn.Module):
 
             preds_mt = preds_climate = preds_month = None
             loss_reg = loss_climate = loss_month = 0
-            if self.multi_task:                                                 # :315-348 (thin PyTorch, not a kernel target)
-                preds_mt = self.multi_task_head(output)
-                preds_climate = self.climate_layer(output)
-                if not self.yfcc:
-                    preds_month = self.month_layer(output)
-                if not self.serving:
-                    loss_reg = self.loss_fnc_mt(preds_mt, labels_multi_task.to(dev)) * REGRESSION_LOSS_SCALING
-                    loss_climate = self.loss_fnc_climate(preds_climate, labels_climate.to(dev, torch.float32)) * CLIMATE_LOSS_SCALING
-                    if not self.yfcc:
-                        loss_month = self.loss_fnc_month(preds_month, labels_month.to(dev)) * MONTHS_LOSS_SCALING
+            self._saved_mt = None
+            if self.multi_task:                                                 # :315-348
+                (preds_mt, preds_climate, preds_month, loss_reg, loss_climate, loss_month, _, mt_grads) = self._multi_task(
+                    output, labels_multi_task, labels_climate, labels_month, dev, want_grad)
+                self._saved_mt = mt_grads
 
             if not self.training and self.serving:                              # :462-466
                 if self.multi_task:

@@ -119,3 +119,28 @@ def train_model(loaded_model: Any, dataset, on_embeddings: bool, yfcc: bool, tra
 def _labels_clf(ds):
     import numpy as np
     return np.asarray(ds['labels_clf'])
+
+
+def finetune_model(model: Any, dataset, multi_task: bool, heading: bool, yfcc: bool, early_stopping: Optional[int] = None,
+                   train_args=None, metrics: Optional[Callable] = None, **train_kwargs):
+    """reference training/train_modes.py:67-107.  `model`: a HuggingFace model name (loaded with CLIPVisionModel, needs the
+    checkpoint on disk) or an already built `SuperGuessr`."""
+    from .super_guessr import SuperGuessr
+    if isinstance(model, str):
+        if 'clip-vit' not in model:
+            raise Exception('Not a clip-vit model.')                                          # :96
+        from transformers import CLIPVisionModel
+        loaded = CLIPVisionModel.from_pretrained(model)
+        model = SuperGuessr(loaded.base_model, panorama=True, hierarchical=False, multi_task=multi_task, heading=heading,
+                            freeze_base=False, should_smooth_labels=True).to('cuda')           # :99-101
+    return train_model(model, dataset, False, yfcc, train_args, metrics, early_stopping, **train_kwargs)   # :105
+
+
+def finetune_on_embeddings(dataset, multi_task: bool, heading: bool, yfcc: bool, early_stopping: Optional[int] = None,
+                           train_args=None, metrics: Optional[Callable] = None, **model_kwargs):
+    """reference training/train_modes.py:110-133: the head (and auxiliary heads) trained on pre-computed embeddings."""
+    from .super_guessr import SuperGuessr
+    model = SuperGuessr(base_model=None, panorama=(yfcc == False), hierarchical=False, multi_task=multi_task,  # noqa: E712
+                        heading=heading, freeze_base=True, should_smooth_labels=True, yfcc=yfcc, **model_kwargs).to('cuda')
+    print(model)
+    return train_model(model, dataset, True, yfcc, train_args, metrics, early_stopping)

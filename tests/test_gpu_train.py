@@ -180,3 +180,40 @@ def test_training_forward_refuses_trainable_tower(cuda):
     sg = SuperGuessr(tower, panorama=False, geocells=np.zeros((10, 2))).to(cuda).train()
     with pytest.raises(NotImplementedError):
         sg(pixel_values=torch.zeros(1, 3, 56, 56, device=cuda), labels_clf=torch.tensor([1]))
+
+
+def test_multi_task_training_matches_reference_run(cuda, G):
+    """multi_task=True: the geocell head through the kernels, the three auxiliary heads through torch autograd on the GPU,
+    one AdamW over all of them == the unmodified reference trained by torch (tests/golden/train_head.npz, 'multitask')."""
+    from pigeon_b200 import SuperGuessr
+    from pigeon_b200.training import AdamW
+    meta = json.loads(str(G["meta"]))
+    n_micro, B, acc = meta["steps"] * meta["acc"], meta["B"], meta["acc"]
+    sg = SuperGuessr(None, panorama=True, num_candidates=5, should_smooth_labels=True, embed_dim=meta["D"], multi_task=True,
+                     geocells=G["centroids"]).to(cuda).train()
+    heads = ("multi_task_head", "climate_layer", "month_layer")
+    with torch.no_grad():
+        sg.cell_layer.weight.copy_(torch.tensor(G["w0"]))
+        sg.cell_layer.bias.copy_(torch.tensor(G["b0"]))
+        for hn in heads:
+            getattr(sg, hn).weight.copy_(torch.tensor(G[f"mt_init_{hn}_w"]))
+            getattr(sg, hn).bias.copy_(torch.tensor(G[f"mt_init_{hn}_b"]))
+    opt = AdamW(sg.parameters(), lr=meta["lr"])
+    opt.zero_grad()
+    for i in range(n_micro):
+        out = sg(embedding=torch.tensor(G["emb"][i]), labels=torch.tensor(G["labels"][i]),
+                 labels_clf=torch.tensor(G["labels_clf"][i]), labels_multi_task=torch.tensor(G["labels_mt"][i]),
+                 labels_climate=torch.tensor(G["labels_climate"][i]), labels_month=torch.tensor(G["labels_month"][i]))
+        np.testing.assert_allclose(float(out.loss), G["multitask_losses"][i], rtol=2e-5)
+        sg.backward(out.loss)
+        if i % acc == acc - 1:
+            opt.step()
+            opt.zero_grad()
+    pairs = [(sg.cell_layer.weight, G["multitask_w_final"], G["w0"]), (sg.cell_layer.bias, G["multitask_b_final"], G["b0"])]
+    for hn in heads:
+        pairs.append((getattr(sg, hn).weight, G[f"mt_final_{hn}_w"], G[f"mt_init_{hn}_w"]))
+        pairs.append((getattr(sg, hn).bias, G[f"mt_final_{hn}_b"], G[f"mt_init_{hn}_b"]))
+    for p, ref, p0 in pairs:
+        move = np.abs(ref - p0).max()
+        assert np.abs(p.detach().cpu().numpy() - ref).max() <= 2e-2 * move
+        assert np.median(np.abs(p.detach().cpu().numpy() - ref)) <= 1e-3 * move
