@@ -320,6 +320,7 @@ class SuperGuessr(nn.Module):
         if getattr(self, "_trainer", None) is None or self._trainer.tower is not self.base_model:
             self._trainer = TowerTrainer(self.base_model, max_views=getattr(self, "max_train_views", 64))
         tr = self._trainer
+        tr.layout()                                            # raises if a block is only partly trainable
         V = 4 if self.panorama else 1
         B = pixel_values.size(0)
         s = self.base_model.dims.image_size

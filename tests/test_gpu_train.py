@@ -169,16 +169,22 @@ def test_train_model_loop_matches_reference_run(cuda, G, name, smooth):
     assert torch.equal(o.preds_geocell.cpu(), ref_logits.argmax(-1))
 
 
-def test_training_forward_refuses_trainable_tower(cuda):
-    from pigeon_b200 import SuperGuessr
-    from pigeon_b200 import synthetic
+def test_training_forward_refuses_partly_frozen_block(cuda):
+    """A block is trainable or frozen as a whole (the reference freezes whole layers, super_guessr.py:159-160); anything
+    else fails loudly instead of silently dropping a gradient."""
+    from pigeon_b200 import PigeonB200Error, SuperGuessr, synthetic
     from pigeon_b200.super_guessr import CLIPVisionTower
     from pigeon_b200.vit_engine import VitDims
-    dims = VitDims(image_size=56, patch_size=14, hidden=128, heads=2, intermediate=256, layers=1)
+    dims = VitDims(image_size=56, patch_size=14, hidden=256, heads=4, intermediate=512, layers=1)
     tower = CLIPVisionTower(dims)
     tower.load_state_dict(synthetic.random_vit_state_dict(dims, seed=1), strict=True)
     sg = SuperGuessr(tower, panorama=False, geocells=np.zeros((10, 2))).to(cuda).train()
-    with pytest.raises(NotImplementedError):
+    tower.vision_model.encoder.layers[0].mlp.fc1.weight.requires_grad = False
+    with pytest.raises(PigeonB200Error):
+        sg(pixel_values=torch.zeros(1, 3, 56, 56, device=cuda), labels_clf=torch.tensor([1]))
+    with pytest.raises(NotImplementedError):                 # parameters the step has no backward for
+        sg.lla_geocells.requires_grad = True
+        tower.vision_model.encoder.layers[0].mlp.fc1.weight.requires_grad = True
         sg(pixel_values=torch.zeros(1, 3, 56, 56, device=cuda), labels_clf=torch.tensor([1]))
 
 

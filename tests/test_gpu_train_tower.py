@@ -189,9 +189,14 @@ def test_tower_backward_matches_reference_autograd(cuda, name):
     np.testing.assert_allclose(float(out.loss), float(z["loss"]), rtol=1e-3)
     sg.backward(out.loss)
     worst = _check_grads(sg, z, meta)
-    with open(os.path.join(os.environ.get("GRAFT_REPO_ROOT", "."), "gpurun_out", "parity.log"), "a") as f:
-        f.write(f"{name}: worst per-tensor relative gradient error {max(worst.values()):.3e} "
-                f"({max(worst, key=worst.get)}), median {float(np.median(list(worst.values()))):.3e}\n")
+    try:                                   # measured parity, picked up into profiles/ by hand; never fails the test
+        d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity.log"), "a") as f:
+            f.write(f"{name}: worst per-tensor relative gradient error {max(worst.values()):.3e} "
+                    f"({max(worst, key=worst.get)}), median {float(np.median(list(worst.values()))):.3e}\n")
+    except OSError:
+        pass
 
 
 def test_reference_freeze_policy_and_optimizer_step(cuda):
