@@ -1,5 +1,6 @@
 """Constants of the hot path, same names and values as the reference's config.py (file:line cited per block).
-Only what the inference path reads is mirrored; training schedules and dataset-creation paths are out of scope."""
+Only what the hot path and the fine-tune step read is mirrored; dataset-creation paths are out of scope."""
+from types import SimpleNamespace
 
 # OpenAI's pretrained implementation                                   (config.py:5-7)
 CLIP_MODEL = 'openai/clip-vit-large-patch14-336'
@@ -32,3 +33,8 @@ PROTO_MODEL_YFCC_PATH = 'saved_models/refiner/proto_yfcc.refiner'
 
 # Evaluation batch size (TRAIN_ARGS.per_device_eval_batch_size)        (config.py:98)
 EVAL_BATCH_SIZE = 256
+
+# Fine-tuning arguments (the fields training/train_eval_loop.py reads from TRAIN_ARGS)   (config.py:94-109)
+TRAIN_ARGS = SimpleNamespace(output_dir='saved_models', per_device_train_batch_size=256, per_device_eval_batch_size=256,
+                             num_train_epochs=1000, learning_rate=2e-5, logging_steps=1, gradient_accumulation_steps=1,
+                             seed=330)

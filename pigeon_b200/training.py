@@ -68,6 +68,8 @@ def train_model(loaded_model: Any, dataset, on_embeddings: bool, yfcc: bool, tra
     """reference training/train_eval_loop.py:164-253.  `train_args` needs `.learning_rate`,
     `.per_device_train_batch_size`, `.num_train_epochs`, optionally `.gradient_accumulation_steps`,
     `.per_device_eval_batch_size`.  Returns the trained model (the best one is saved to `save_path` if given)."""
+    if train_args is None:
+        from .config import TRAIN_ARGS as train_args
     model = loaded_model
     optimizer = AdamW(model.parameters(), lr=train_args.learning_rate)                       # :187
     train_ds = dataset['train']

@@ -1,12 +1,14 @@
 #!/usr/bin/env python
-"""Entry points of the hot path with the reference's CLI (run.py:21-93): `embed` and `evaluate`.
+"""Entry points of the hot path with the reference's CLI (run.py:21-93): `embed`, `evaluate` and `finetune`.
 
     python run.py evaluate HEAD.model -l DATASET_DIR [-b BASE.model] [--yfcc]
     python run.py embed CLIP.model -l DATASET_DIR
+    python run.py finetune openai/clip-vit-large-patch14-336 -l DATASET_DIR [-m] [--heading]     # tower + head (run.py:165-169)
+    python run.py finetune - -l EMBEDDING_DATASET_DIR --embeddings [-m]                          # head on embeddings (:171-175)
 
-`pretrain` / `finetune` (training) are outside the B200 inference path and raise NotImplementedError, like the
-reference does for its unsupported resume modes (run.py:166-173,189).  Datasets are HF `DatasetDict`s on disk, as in the
-reference (run.py:143-162); none are shipped with either repository.
+`pretrain` (CLIP contrastive pre-training through the HF Trainer) is outside the path and raises NotImplementedError, like
+the reference does for its unsupported resume modes (run.py:166-173,189).  Datasets are HF `DatasetDict`s on disk, as in
+the reference (run.py:143-162); none are shipped with either repository.
 """
 import argparse
 import logging
@@ -64,14 +66,23 @@ def main():
     p.add_argument('--yfcc', action='store_true')
     p.add_argument('--landmarks', action='store_true')
     p.add_argument('--heading', action='store_true')
+    p.add_argument('-m', '--multitask', action='store_true')
+    p.add_argument('--embeddings', action='store_true', help='finetune: train the head on pre-computed embeddings')
     args = p.parse_args()
-    if args.mode in ('pretrain', 'finetune'):
-        raise NotImplementedError(f'"{args.mode}" (training) is outside the B200 inference hot path')
+    if args.mode == 'pretrain':
+        raise NotImplementedError('"pretrain" (CLIP contrastive pre-training) is outside the B200 hot path')
     if args.load is None:
         raise NotImplementedError('A dataset must be given with -l (the reference regenerates it from un-shipped raw data).')
     from datasets import DatasetDict
     dataset = DatasetDict.load_from_disk(args.load.split(',')[0])
-    if args.mode == 'embed':
+    if args.mode == 'finetune':
+        from pigeon_b200.training import finetune_model, finetune_on_embeddings
+        ds = dataset.with_format('torch')
+        if args.embeddings:
+            finetune_on_embeddings(ds, multi_task=args.multitask, heading=args.heading, yfcc=args.yfcc)   # run.py:175
+        else:
+            finetune_model(args.name, ds, multi_task=args.multitask, heading=args.heading, yfcc=args.yfcc)  # run.py:169
+    elif args.mode == 'embed':
         model = CLIPEmbedding(args.name, load_checkpoint=True, panorama=not args.yfcc)    # run.py:126-129
         embed_images(model, dataset)
     else:

@@ -137,3 +137,99 @@ def test_packed_all_gather_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=120)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_preprocess_plan_matches_oracle_geometry():
+    """pg_preprocess_workspace_bytes is pure host arithmetic (resize geometry, Pillow's kernel support, the input rows the
+    vertical pass needs): its layout must follow from the oracle's restatement of the same formulas."""
+    import ctypes as C
+    from oracle import preprocess as op
+    from pigeon_b200 import _lib
+    lib = _lib.load()
+    size = 336
+    align = lambda x, a=256: (x + a - 1) // a * a
+    shapes = [(480, 640), (500, 375), (150, 210), (336, 400), (900, 1300), (337, 336), (2000, 3000), (64, 4000)]
+    desc = (_lib.Image * len(shapes))()
+    inter, ks = 0, 0
+    for i, (h, w) in enumerate(shapes):
+        desc[i] = _lib.Image(0x1000, h, w, 3 * w)              # fake device pointer: nothing is dereferenced
+        nh, nw = op.resized_shape(h, w, size)
+        top, left = (nh - size) // 2, (nw - size) // 2
+        kv, bv, _ = op.precompute_coeffs(h, nh)
+        kh, _, _ = op.precompute_coeffs(w, nw)
+        first, last = int(bv[top, 0]), int(bv[top + size - 1, 0] + bv[top + size - 1, 1])
+        inter += align((last - first) * size * 3)
+        ks = max(ks, kv, kh)
+    n = len(shapes)
+    expect = align(n * 64) + align(n * 2 * size * ks * 4) + align(n * 2 * size * 2 * 4) + inter
+    assert lib.pg_preprocess_workspace_bytes(desc, n, size) == expect
+    bad = (_lib.Image * 1)(_lib.Image(0x1000, 8, 40000, 120000))
+    assert lib.pg_preprocess_workspace_bytes(bad, 1, size) == 0 and b"exceeds" in lib.pg_last_error()
+
+
+def test_trainer_layout_and_optimizer_arguments():
+    """Host logic of the fine-tune step that needs no GPU: which blocks train (reference freeze policy,
+    models/super_guessr.py:159-160), partly frozen blocks are refused, AdamW validates its hyper-parameters."""
+    from pigeon_b200 import CLIPVisionTower, PigeonB200Error, VitDims
+    from pigeon_b200.training import AdamW
+    from pigeon_b200.vit_train import TowerTrainer
+    dims = VitDims(image_size=56, patch_size=14, hidden=256, heads=4, intermediate=512, layers=3)
+    tower = CLIPVisionTower(dims)
+    tr = TowerTrainer(tower)
+    assert tr.layout() == (True, [True, True, True]) and tr.any_trainable()
+    for p in tower.vision_model.encoder.layers[:-1].parameters():
+        p.requires_grad = False
+    assert tr.layout() == (True, [False, False, True])
+    for p in tower.parameters():
+        p.requires_grad = False
+    assert tr.layout() == (False, [False, False, False]) and not tr.any_trainable()
+    tower.vision_model.encoder.layers[1].mlp.fc2.bias.requires_grad = True
+    with pytest.raises(PigeonB200Error):
+        tr.layout()
+    tower.vision_model.encoder.layers[1].mlp.fc2.bias.requires_grad = False
+    tower.vision_model.embeddings.class_embedding.requires_grad = True
+    with pytest.raises(PigeonB200Error):
+        tr.layout()
+    w = torch.nn.Parameter(torch.zeros(4))
+    for kw in (dict(lr=-1.0), dict(betas=(1.0, 0.9)), dict(eps=-1e-8), dict(weight_decay=-0.1)):
+        with pytest.raises(ValueError):
+            AdamW([w], **kw)
+    opt = AdamW([w, torch.nn.Parameter(torch.zeros(2), requires_grad=False)], lr=1e-3)
+    assert len(opt.params) == 1
+    w.grad = torch.ones(4)
+    opt.zero_grad()
+    assert w.grad is None
+    w.grad = torch.ones(4)                               # CPU tensors: the optimizer has no CPU path
+    with pytest.raises(PigeonB200Error):
+        opt.step()
+
+
+GLOO_GRAD_WORKER = textwrap.dedent("""
+    import os, sys, numpy as np, torch, torch.distributed as dist
+    sys.path.insert(0, %r)
+    from pigeon_b200 import SuperGuessr
+    rank, world = int(sys.argv[1]), 2
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=sys.argv[2], RANK=str(rank), WORLD_SIZE="2")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sg = SuperGuessr(None, panorama=True, multi_task=True, embed_dim=128, geocells=np.zeros((10, 2)))
+    params = sg._mt_params()
+    assert len(params) == 6
+    grads = [torch.full_like(p, float(rank + 1)) for p in params]
+    sg._publish_mt_grads(grads, world)                  # DDP-style: mean over ranks, accumulated into .grad
+    sg._publish_mt_grads([torch.full_like(p, 2.0 * (rank + 1)) for p in params], world)
+    for p in params:
+        assert torch.allclose(p.grad, torch.full_like(p, 1.5 + 3.0)), p.grad.flatten()[:3]
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+""")
+
+
+def test_gradient_averaging_gloo_world2(tmp_path):
+    script = tmp_path / "g.py"
+    script.write_text(GLOO_GRAD_WORKER % ROOT)
+    port = str(31000 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), port], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
