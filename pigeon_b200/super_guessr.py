@@ -16,7 +16,7 @@ import torch
 from torch import Tensor, nn
 from torch.nn.parameter import Parameter
 
-from . import _lib, ops
+from . import _lib, _versions, ops
 from ._lib import PigeonB200Error, check, current_stream_ptr, load, ptr
 from .config import (CLIP_EMBED_DIM, CLIP_PRETRAINED_HEAD, CLIP_PRETRAINED_HEAD_YFCC, GEOCELL_PATH, GEOCELL_PATH_YFCC,
                      LABEL_SMOOTHING_CONSTANT)
@@ -118,7 +118,7 @@ class CLIPVisionTower(nn.Module):
         self._packed_version = None
 
     def _version(self):
-        return tuple((p.data_ptr(), p._version, getattr(p, "_pg_version", 0)) for p in self.parameters())
+        return tuple((p.data_ptr(), p._version, _versions.get(p)) for p in self.parameters())
 
     def engine(self) -> VitEngine:
         p0 = next(self.parameters())
@@ -265,7 +265,7 @@ class SuperGuessr(nn.Module):
 
     def _packed_head(self) -> Tensor:
         w = self.cell_layer.weight
-        key = (w.data_ptr(), w._version, getattr(w, "_pg_version", 0))
+        key = (w.data_ptr(), w._version, _versions.get(w))
         if self._w3 is None or self._w3_key != key:
             self._w3 = ops.head_pack_weight(w.detach())
             self._w3_key = key

@@ -13,6 +13,7 @@ from typing import Any, Callable, Dict, Iterable, Optional
 import torch
 from torch.utils.data import DataLoader
 
+from . import _versions
 from . import dist as pdist
 from ._lib import PigeonB200Error, check, current_stream_ptr, load, ptr
 from .loops import evaluate_model
@@ -55,7 +56,7 @@ class AdamW:
             check(self._lib.pg_adamw_step(ptr(p), ptr(p.grad), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(), self.lr,
                                           self.betas[0], self.betas[1], self.eps, self.weight_decay, st["step"], 1.0,
                                           current_stream_ptr()), "pg_adamw_step")
-            p._pg_version = getattr(p, "_pg_version", 0) + 1     # raw-pointer update: invalidate packed copies
+            _versions.bump(p)                                    # raw-pointer update: invalidate packed copies
 
 
 def _to_batch(data: Any) -> dict:

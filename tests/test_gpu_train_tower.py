@@ -240,3 +240,54 @@ def test_data_parallel_gradients_match_full_batch(cuda):
                         "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "ddp_train_check.py")],
                        capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_train_model_loop_with_trainable_tower(cuda):
+    """`train_model` (mirror of training/train_eval_loop.py:164-253) end to end on a tiny tower: host pixel batches from a
+    DataLoader, gradient accumulation, optimizer steps on tower + head, per-epoch evaluation, best-checkpoint saving."""
+    import tempfile
+    from pigeon_b200 import CLIPVisionTower, SuperGuessr, VitDims, synthetic
+    from pigeon_b200.training import train_model
+    dims = VitDims(image_size=56, patch_size=14, hidden=256, heads=4, intermediate=512, layers=2)
+    tower = CLIPVisionTower(dims)
+    tower.load_state_dict(synthetic.random_vit_state_dict(dims, seed=3, std=0.05), strict=True)
+    Cc, n = 12, 16
+    sg = SuperGuessr(tower, panorama=False, should_smooth_labels=True, num_candidates=5,
+                     geocells=synthetic.synthetic_geocells(Cc, 0)).to(cuda)
+    for p in sg.base_model.vision_model.encoder.layers[:-1].parameters():      # reference freeze policy
+        p.requires_grad = False
+    g = torch.Generator().manual_seed(8)
+    px = torch.randn(n, 3, 56, 56, generator=g)
+    labels = torch.tensor(synthetic.synthetic_geocells(n, 9))
+    labels_clf = torch.randint(0, Cc, (n,), generator=g)
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return n
+
+        def __getitem__(self, i):
+            if isinstance(i, str):
+                return {"labels": labels.numpy(), "labels_clf": labels_clf.numpy()}[i]
+            return dict(pixel_values=px[i], labels=labels[i], labels_clf=labels_clf[i])
+
+    class Args:
+        learning_rate = 1e-3
+        per_device_train_batch_size = 4
+        per_device_eval_batch_size = 8
+        num_train_epochs = 3
+        gradient_accumulation_steps = 2
+
+    before = {k: v.detach().clone() for k, v in sg.state_dict().items()}
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "best.model")
+        out = train_model(sg, {"train": DS(), "val": DS()}, False, False, Args(), None, patience=None, save_path=path)
+        assert out is sg and os.path.exists(path)
+        saved = torch.load(path, map_location="cpu")
+        assert set(saved) == set(before)
+    hist = sg.train_history
+    assert len(hist) == 3 and all(np.isfinite(hist)) and hist[-1] < hist[0]          # the training loss goes down
+    after = sg.state_dict()
+    changed = [k for k in before if not torch.equal(before[k], after[k])]
+    assert any("encoder.layers.1." in k for k in changed) and any("cell_layer" in k for k in changed)
+    assert any("embeddings" in k for k in changed)
+    assert not any("encoder.layers.0." in k for k in changed)                        # frozen layer untouched
