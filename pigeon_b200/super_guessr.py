@@ -117,7 +117,7 @@ class CLIPVisionTower(nn.Module):
     def _weights_changed(self):
         self._packed_version = None
 
-    def _version(self):
+    def _weights_version(self):
         return tuple((p.data_ptr(), p._version, _versions.get(p)) for p in self.parameters())
 
     def engine(self) -> VitEngine:
@@ -125,7 +125,7 @@ class CLIPVisionTower(nn.Module):
         if not p0.is_cuda:
             raise PigeonB200Error("CLIPVisionTower is on the CPU: move the model with .to('cuda') — the B200 path "
                                   "has no CPU implementation")
-        v = self._version()
+        v = self._weights_version()
         if self._engine is None or self._packed_version != v:
             sd = {k: t.detach() for k, t in self.state_dict().items()}
             if self._engine is None or self._engine.device != p0.device:

@@ -97,7 +97,7 @@ class TowerTrainer:
         self._saved, self._saved_layers, self._saved_views = saved, layers, n_views
 
     def _transposed_weights(self):
-        v = self.tower._version()
+        v = self.tower._weights_version()
         if self._wt is not None and self._wt_version == v:
             return self._wt
         out = []

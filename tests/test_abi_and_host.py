@@ -233,3 +233,22 @@ def test_gradient_averaging_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_state_dict_is_a_plain_weights_file(tmp_path):
+    """Checkpoints written from the mirror (`torch.save(model.state_dict())`, train_eval_loop.py:238) must load with
+    `weights_only=True` and carry exactly the reference's key names — nothing but tensors may ride along."""
+    from pigeon_b200 import CLIPVisionTower, SuperGuessr, VitDims, _versions, synthetic
+    dims = VitDims(image_size=56, patch_size=14, hidden=256, heads=4, intermediate=512, layers=2)
+    tower = CLIPVisionTower(dims)
+    sg = SuperGuessr(tower, panorama=False, geocells=synthetic.synthetic_geocells(12, 0))
+    v0 = tower._weights_version()
+    for p in sg.parameters():
+        _versions.bump(p)                                   # what AdamW.step() does after a raw-pointer update
+    assert tower._weights_version() != v0
+    path = tmp_path / "m.model"
+    torch.save(sg.state_dict(), path)
+    assert path.stat().st_size < 2 * sum(t.numel() * t.element_size() for t in sg.state_dict().values())
+    sd = torch.load(path, map_location="cpu", weights_only=True)
+    assert set(sd) == set(sg.state_dict())
+    assert "base_model.vision_model.encoder.layers.1.mlp.fc2.weight" in sd and "cell_layer.weight" in sd and "lla_geocells" in sd
