@@ -27,9 +27,10 @@ class CLIPEmbedding(torch.nn.Module):
         super().__init__()
         self.device = device
         if clip_model is None:
-            from transformers import CLIPProcessor, CLIPVisionModel
-            processor = processor or CLIPProcessor.from_pretrained(CLIP_MODEL)
+            from transformers import CLIPVisionModel
             clip_model = CLIPVisionModel.from_pretrained(CLIP_MODEL)
+        # :25 `CLIPProcessor.from_pretrained(CLIP_MODEL)` — here the GPU pre-processor (bit-identical output, no hub access),
+        # built on first use so that a model fed pre-processed tensors never needs it
         self.processor = processor
         self.clip_model = as_tower(clip_model)
         self.panorama = panorama
@@ -49,6 +50,10 @@ class CLIPEmbedding(torch.nn.Module):
         """:42-66 — accepts a pre-processed tensor or PIL image(s)."""
         with torch.no_grad():
             if isinstance(image, Tensor) == False:
+                if self.processor is None:
+                    from .preprocess import ClipImageProcessor
+                    dev = next(self.clip_model.parameters()).device
+                    self.processor = ClipImageProcessor(size=self.clip_model.dims.image_size, device=dev, dtype=torch.float16)
                 inputs = self.processor(images=image, return_tensors='pt')
                 pixel_values = inputs['pixel_values']
             else:

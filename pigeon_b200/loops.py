@@ -84,8 +84,17 @@ def compute_embeddings(name: str, model: Any, data: DataLoader, accelerator=None
     return all_outputs, all_indices
 
 
-def embed_images(loaded_model: Any, dataset, num_workers: int = 0, save_dir: Optional[str] = 'data/landmark_embeddings'):
-    """reference preprocessing/embed.py:45-83.  `dataset` maps split name -> dataset yielding (pixels, index)."""
+def raw_image_collate(batch):
+    """collate_fn for datasets that yield (uint8 RGB image of any size, index): the images stay a list, the model's GPU
+    pre-processor (pigeon_b200.preprocess) turns the whole batch into pixel_values in one launch."""
+    images, index = zip(*batch)
+    return list(images), torch.as_tensor(index)
+
+
+def embed_images(loaded_model: Any, dataset, num_workers: int = 0, save_dir: Optional[str] = 'data/landmark_embeddings',
+                 collate_fn=None):
+    """reference preprocessing/embed.py:45-83.  `dataset` maps split name -> dataset yielding (pixels, index); with
+    `collate_fn=raw_image_collate` the items may be raw uint8 images instead of CPU-pre-processed tensors."""
     loaded_model.eval()
     for split in ('train', 'val', 'test'):
         if split not in dataset:
@@ -94,7 +103,8 @@ def embed_images(loaded_model: Any, dataset, num_workers: int = 0, save_dir: Opt
         sampler = None
         if pdist.is_distributed():
             sampler = torch.utils.data.distributed.DistributedSampler(ds, shuffle=False)
-        loader = DataLoader(ds, EMBED_BATCH_SIZE_PER_GPU, shuffle=False, num_workers=num_workers, sampler=sampler, pin_memory=True)
+        loader = DataLoader(ds, EMBED_BATCH_SIZE_PER_GPU, shuffle=False, num_workers=num_workers, sampler=sampler,
+                            pin_memory=collate_fn is None, collate_fn=collate_fn)
         compute_embeddings(split, loaded_model, loader, save_dir=save_dir)
         if pdist.is_distributed():
             torch.distributed.barrier()                                              # accelerator.wait_for_everyone()

@@ -208,3 +208,33 @@ def test_bank_builder_matches_reference_prototypes(cuda):
     np.testing.assert_allclose(b["data_emb"], z["bank_data_emb"], rtol=2e-6, atol=2e-7)
     np.testing.assert_allclose(b["proto_emb"], z["bank_proto_emb"], rtol=1e-5, atol=1e-6)
     assert np.array_equal(b["proto_count"], z["bank_proto_count"])
+
+
+def test_checkpoint_round_trip_through_load_state(cuda, tmp_path):
+    """`torch.save(model.state_dict())` (train_eval_loop.py:238) -> a fresh model -> `load_state(path)`
+    (super_guessr.py:222-238, evaluate.py:45-46): same predictions bit for bit, unknown keys reported and skipped."""
+    from pigeon_b200 import CLIPVisionTower, SuperGuessr, VitDims, synthetic
+    dims = VitDims(image_size=56, patch_size=14, hidden=256, heads=4, intermediate=512, layers=2)
+    cells = synthetic.synthetic_geocells(40, 0)
+
+    def build(seed):
+        tower = CLIPVisionTower(dims)
+        tower.load_state_dict(synthetic.random_vit_state_dict(dims, seed=seed, std=0.05), strict=True)
+        return SuperGuessr(tower, panorama=True, freeze_base=True, num_candidates=5, geocells=cells).to(cuda).eval()
+
+    a, b = build(1), build(2)
+    with torch.no_grad():
+        a.cell_layer.weight.normal_(0, 0.05)
+    px = torch.randn(3, 12, 56, 56, generator=torch.Generator().manual_seed(3)).to(cuda)
+    lab = torch.tensor([1, 2, 3])
+    oa = a(pixel_values=px, labels_clf=lab)
+    ob = b(pixel_values=px, labels_clf=lab)
+    assert not torch.equal(oa.embedding, ob.embedding)
+    sd = a.state_dict()
+    sd["not_a_parameter"] = torch.zeros(1)
+    path = tmp_path / "head.model"
+    torch.save(sd, path)
+    b.load_state(str(path))                                  # prints the unknown key, copies the rest by name
+    ob = b(pixel_values=px, labels_clf=lab)
+    assert torch.equal(oa.embedding, ob.embedding) and torch.equal(oa.preds_geocell, ob.preds_geocell)
+    assert torch.equal(oa.top5_geocells.values, ob.top5_geocells.values) and float(oa.loss) == float(ob.loss)

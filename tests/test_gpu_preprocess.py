@@ -85,3 +85,33 @@ def test_preprocess_feeds_the_tower(cuda):
     a = sg(pixel_values=px, labels_clf=lab)
     b = sg(pixel_values=ref_px.to(cuda, torch.float16), labels_clf=lab)
     assert torch.equal(a.embedding, b.embedding) and torch.equal(a.preds_geocell, b.preds_geocell)
+
+
+def test_embed_images_from_raw_uint8(cuda, tmp_path):
+    """Bulk-embedding driver (preprocessing/embed.py:45-83) fed RAW images: GPU pre-processing + tower in the loop ==
+    embedding the oracle-pre-processed pixels; `.npy` outputs in the reference's format (embed.py:41-43)."""
+    from oracle import preprocess as op
+    from pigeon_b200 import CLIPEmbedding, synthetic
+    from pigeon_b200.loops import embed_images, raw_image_collate
+    from pigeon_b200.super_guessr import CLIPVisionTower
+    from pigeon_b200.vit_engine import VitDims
+    dims = VitDims(image_size=336, patch_size=14, hidden=256, heads=4, intermediate=512, layers=1)
+    tower = CLIPVisionTower(dims)
+    tower.load_state_dict(synthetic.random_vit_state_dict(dims, seed=6, std=0.05), strict=True)
+    model = CLIPEmbedding("unused", device="cuda", clip_model=tower)
+    imgs = [synthetic.synthetic_photo(360 + 13 * i, 500 - 11 * i, seed=20 + i) for i in range(5)]
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return len(imgs)
+
+        def __getitem__(self, i):
+            return imgs[i], i
+
+    embed_images(model, {"train": DS()}, save_dir=str(tmp_path), collate_fn=raw_image_collate)
+    got = np.load(tmp_path / "train.npy")
+    idx = np.load(tmp_path / "train_indices.npy")
+    assert got.shape == (5, 256) and idx.tolist() == [0, 1, 2, 3, 4]
+    ref_px = torch.from_numpy(np.stack([op.clip_preprocess(im) for im in imgs])).to(cuda, torch.float16)
+    ref = model(ref_px).cpu().numpy()
+    assert np.array_equal(got, ref)
