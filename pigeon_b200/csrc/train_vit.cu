@@ -59,31 +59,52 @@ __global__ void __launch_bounds__(256) cast_kernel(const T* __restrict__ src, __
 }
 
 // ------------------------------------------------------------------------------------------------ transpose
-// 32 x 32 tiles through shared memory; block (32, 8).
+// 64 x 64 tiles through shared memory, block (32, 8): every thread moves PAIRS (two adjacent source columns in, two
+// adjacent output columns = source rows out), so a warp reads 128-256 B and writes 128 B per instruction.
+template <typename T> struct Pair;
+template <> struct Pair<float> { using type = float2; };
+template <> struct Pair<__half> { using type = __half2; };
+template <> struct Pair<__nv_bfloat16> { using type = __nv_bfloat162; };
+__device__ __forceinline__ float2 pair_to_f32(float2 v) { return v; }
+__device__ __forceinline__ float2 pair_to_f32(__half2 v) { return __half22float2(v); }
+__device__ __forceinline__ float2 pair_to_f32(__nv_bfloat162 v) { return __bfloat1622float2(v); }
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 transpose_kernel(const T* __restrict__ src, long lds, __nv_bfloat16* __restrict__ out, long ldo, long rows, int cols,
                  int rowmap_div, int rowmap_mul, int rowmap_add) {
-  __shared__ float tile[32][33];
-  const long r0 = (long)blockIdx.x * 32;
-  const int c0 = blockIdx.y * 32;
+  using P = typename Pair<T>::type;
+  __shared__ float tile[64][65];               // tile[c][r]
+  const long r0 = (long)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const bool src_pairs = ((lds & 1) == 0) && ((reinterpret_cast<uintptr_t>(src) & (2 * sizeof(T) - 1)) == 0);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long r = r0 + threadIdx.y + 8 * i;
-    const int c = c0 + threadIdx.x;
-    float v = 0.f;
+  for (int i = 0; i < 8; ++i) {
+    const int rl = ty + 8 * i;
+    const long r = r0 + rl;
+    const int c = c0 + 2 * tx;
+    float2 v = make_float2(0.f, 0.f);
     if (r < rows && c < cols) {
       const long sr = rowmap_div > 0 ? (long)rowmap_mul * (r / rowmap_div) + (r % rowmap_div) + rowmap_add : r;
-      v = to_f32<T>(src[sr * lds + c]);
+      const T* p = src + sr * lds + c;
+      if (src_pairs && c + 1 < cols) v = pair_to_f32(*reinterpret_cast<const P*>(p));
+      else { v.x = to_f32<T>(p[0]); if (c + 1 < cols) v.y = to_f32<T>(p[1]); }
     }
-    tile[threadIdx.y + 8 * i][threadIdx.x] = v;
+    tile[2 * tx][rl] = v.x;
+    tile[2 * tx + 1][rl] = v.y;
   }
   __syncthreads();
+  const bool dst_pairs = ((ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = c0 + threadIdx.y + 8 * i;
-    const long r = r0 + threadIdx.x;
-    if (c < cols && r < rows) out[(long)c * ldo + r] = __float2bfloat16_rn(tile[threadIdx.x][threadIdx.y + 8 * i]);
+  for (int i = 0; i < 8; ++i) {
+    const int cl = ty + 8 * i;
+    const int c = c0 + cl;
+    const long r = r0 + 2 * tx;
+    if (c >= cols || r >= rows) continue;
+    __nv_bfloat16* q = out + (long)c * ldo + r;
+    if (dst_pairs && r + 1 < rows) *reinterpret_cast<__nv_bfloat162*>(q) = __floats2bfloat162_rn(tile[cl][2 * tx], tile[cl][2 * tx + 1]);
+    else { q[0] = __float2bfloat16_rn(tile[cl][2 * tx]); if (r + 1 < rows) q[1] = __float2bfloat16_rn(tile[cl][2 * tx + 1]); }
   }
 }
 
@@ -107,17 +128,22 @@ dgelu_kernel(const float* __restrict__ dh, const __half* __restrict__ u, __nv_bf
 // One warp per row, row in registers as NV4 float4 per lane (same lane-strided mapping as the forward kernel).
 //   xhat = (x - mean) * rstd;  g = gamma * dy;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat))
 template <int NV4, bool PARAM_GRADS>
-__global__ void __launch_bounds__(256, PARAM_GRADS ? 1 : 2)
+__global__ void __launch_bounds__(256, 2)
 ln_backward_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                    float* __restrict__ dx_out, int accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta,
                    __nv_bfloat16* __restrict__ dx_bf16, long rows, float eps) {
   constexpr int hidden = NV4 * 128;
-  __shared__ float red[8][128];   // reused per float4 slot when reducing dgamma / dbeta across the 8 warps
+  // PARAM_GRADS: warp-private gamma / beta gradient accumulators in shared memory, [warp][gamma|beta][NV4][lane] float4
+  // (64 KB at hidden 1024; registers would cost 64 per thread and halve the occupancy of this HBM-bound kernel)
+  extern __shared__ float4 acc_sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long warps = ((long)gridDim.x * blockDim.x) >> 5;
-  float4 gsum[PARAM_GRADS ? NV4 : 1], bsum[PARAM_GRADS ? NV4 : 1];   // register accumulators only when gamma / beta train
+  float4* my_g = acc_sm + (size_t)(warp * 2 + 0) * NV4 * 32 + lane;
+  float4* my_b = acc_sm + (size_t)(warp * 2 + 1) * NV4 * 32 + lane;
+  if (PARAM_GRADS) {
 #pragma unroll
-  for (int i = 0; i < (PARAM_GRADS ? NV4 : 1); ++i) gsum[i] = bsum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < NV4; ++i) my_g[i * 32] = my_b[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
     float4 xv[NV4], dv[NV4];
     const float4* xr = reinterpret_cast<const float4*>(x + row * hidden);
@@ -141,9 +167,11 @@ ln_backward_kernel(const float* __restrict__ dy, const float* __restrict__ x, co
       const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
       xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;       // xhat
       if (PARAM_GRADS) {
-        gsum[i].x += dv[i].x * xv[i].x; gsum[i].y += dv[i].y * xv[i].y;
-        gsum[i].z += dv[i].z * xv[i].z; gsum[i].w += dv[i].w * xv[i].w;
-        bsum[i].x += dv[i].x; bsum[i].y += dv[i].y; bsum[i].z += dv[i].z; bsum[i].w += dv[i].w;
+        float4 g = my_g[i * 32], b = my_b[i * 32];
+        g.x += dv[i].x * xv[i].x; g.y += dv[i].y * xv[i].y; g.z += dv[i].z * xv[i].z; g.w += dv[i].w * xv[i].w;
+        b.x += dv[i].x; b.y += dv[i].y; b.z += dv[i].z; b.w += dv[i].w;
+        my_g[i * 32] = g;
+        my_b[i * 32] = b;
       }
       dv[i].x *= gm.x; dv[i].y *= gm.y; dv[i].z *= gm.z; dv[i].w *= gm.w;       // g = gamma * dy
       s1 += (dv[i].x + dv[i].y) + (dv[i].z + dv[i].w);
@@ -174,22 +202,15 @@ ln_backward_kernel(const float* __restrict__ dy, const float* __restrict__ x, co
     }
   }
   if (PARAM_GRADS) {
-    for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+    // column c = 128 i + 4 lane + e lives in float4 slot (i, lane), component e, of every warp's accumulators
+    const float* flat = reinterpret_cast<const float*>(acc_sm);
+    for (int idx = threadIdx.x; idx < 2 * hidden; idx += 256) {
+      const int which = idx / hidden, c = idx - which * hidden;
+      float t = 0.f;
 #pragma unroll
-      for (int i = 0; i < NV4; ++i) {
-        const float4 v = pass == 0 ? gsum[i] : bsum[i];
-        __syncthreads();
-        red[warp][lane * 4 + 0] = v.x; red[warp][lane * 4 + 1] = v.y;
-        red[warp][lane * 4 + 2] = v.z; red[warp][lane * 4 + 3] = v.w;
-        __syncthreads();
-        if (threadIdx.x < 128) {
-          float t = 0.f;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
-          // float4 slot i of lane l covers columns 4 * (l + 32 i) .. + 3
-          atomicAdd((pass == 0 ? dgamma : dbeta) + 128 * i + threadIdx.x, t);
-        }
-      }
+      for (int w = 0; w < 8; ++w) t += flat[((size_t)(w * 2 + which) * NV4 * 32) * 4 + c];
+      atomicAdd((which == 0 ? dgamma : dbeta) + c, t);
     }
   }
 }
@@ -286,7 +307,7 @@ int transpose_to_bf16(const void* src, int src_type, long lds, void* out, long l
   if (rows <= 0 || cols <= 0) return 0;
   if (ldo < rows) { set_last_error("transpose_to_bf16: ldo %ld < rows %ld", ldo, rows); return 1; }
   ProfScope prof("train_transpose_bf16", stream);
-  const dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32)), block(32, 8);
+  const dim3 grid((unsigned)((rows + 63) / 64), (unsigned)((cols + 63) / 64)), block(32, 8);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   if (src_type == SRC_F32) transpose_kernel<float><<<grid, block, 0, stream>>>(reinterpret_cast<const float*>(src), lds, o, ldo, rows, cols, rowmap_div, rowmap_mul, rowmap_add);
   else if (src_type == SRC_F16) transpose_kernel<__half><<<grid, block, 0, stream>>>(reinterpret_cast<const __half*>(src), lds, o, ldo, rows, cols, rowmap_div, rowmap_mul, rowmap_add);
@@ -312,6 +333,15 @@ int dgelu_bf16(const float* dh, const void* u, void* du, long n, cudaStream_t st
     default: set_last_error("hidden size %d unsupported (need 128*{1,2,4,6,8})", (hidden)); return 1; \
   }
 
+template <int NV4>
+void launch_ln_backward_params(int blocks, size_t smem, cudaStream_t stream, const float* dy, const float* x,
+                               const float* gamma, float* dx_out, int accumulate, float* dgamma, float* dbeta,
+                               __nv_bfloat16* d16, long rows, float eps) {
+  auto kern = ln_backward_kernel<NV4, true>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<blocks, 256, smem, stream>>>(dy, x, gamma, dx_out, accumulate, dgamma, dbeta, d16, rows, eps);
+}
+
 int layernorm_backward(const float* dy, const float* x, const float* gamma, float* dx_out, int accumulate, float* dgamma,
                        float* dbeta, void* dx_bf16, long rows, int hidden, float eps, int num_sms, cudaStream_t stream) {
   if (hidden % 128) { set_last_error("layernorm_backward: hidden %d not a multiple of 128", hidden); return 1; }
@@ -323,8 +353,9 @@ int layernorm_backward(const float* dy, const float* x, const float* gamma, floa
   ProfScope prof("train_ln_backward", stream);
   __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
   if (dgamma != nullptr) {
-    PG_DISPATCH_NV4(hidden, (ln_backward_kernel<NV4, true><<<(int)blocks, 256, 0, stream>>>(dy, x, gamma, dx_out, accumulate,
-                                                                                          dgamma, dbeta, d16, rows, eps)));
+    const size_t smem = (size_t)8 * 2 * hidden * sizeof(float);
+    PG_DISPATCH_NV4(hidden, (launch_ln_backward_params<NV4>((int)blocks, smem, stream, dy, x, gamma, dx_out, accumulate,
+                                                            dgamma, dbeta, d16, rows, eps)));
   } else {
     PG_DISPATCH_NV4(hidden, (ln_backward_kernel<NV4, false><<<(int)blocks, 256, 0, stream>>>(dy, x, gamma, dx_out, accumulate,
                                                                                            dgamma, dbeta, d16, rows, eps)));
@@ -364,7 +395,7 @@ int embed_backward(const float* d_e, float* dpos, float* dcls, int n_views, int 
 
 int column_sum_accumulate(const void* x, int src_type, long ldx, float* out, long rows, int cols, cudaStream_t stream) {
   if (rows <= 0 || cols <= 0) return 0;
-  const int rpb = 512;
+  const int rpb = 128;
   const dim3 grid((cols + 255) / 256, (unsigned)((rows + rpb - 1) / rpb));
   ProfScope prof("train_column_sum", stream);
   if (src_type == SRC_F32) column_sum_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(x), ldx, out, rows, cols, rpb);

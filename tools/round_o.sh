@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 400 python -m pytest tests/test_gpu_train_tower.py -q -m gpu -x 2>&1 | tail -4
+timeout 400 python tools/train_bench.py --samples 128 --steps 2 --warmup 1 --all-trainable --out gpurun_out/train_bench_all_v2.json 2>&1 | grep -E "ms_per_step|transpose|ln_backward|column_sum|rror" | cut -c1-200 | cut -c150-
+timeout 400 python tools/train_bench.py --samples 128 --steps 2 --warmup 1 --out gpurun_out/train_bench_v5.json 2>&1 | grep -E "ms_per_step|ln_backward|rror" | cut -c150-330
