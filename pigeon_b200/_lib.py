@@ -77,6 +77,8 @@ SIGNATURES = {
                                   c_void_p]),
     "pg_gemm_ex": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32,
                              c_int32, c_int32, c_int32, c_void_p]),
+    "pg_gemm_tn": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                             c_void_p]),
     "pg_attention_f16_lse": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "pg_attention_backward_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "pg_attention_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,

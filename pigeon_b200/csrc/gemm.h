@@ -25,9 +25,13 @@ struct GemmProblem {
   const float* bias;
   int epi;
   int rowmap_div, rowmap_mul, rowmap_add;
-  int operand_bf16;     // A and W hold bf16 instead of fp16 (backward GEMMs); outputs are unaffected
+  int operand_bf16;     // 0: A, W fp16;  1: both bf16 (backward GEMMs);  2: A bf16, W fp16;  3: A fp16, W bf16
   const float* resid;   // EPI_F32_BIAS_RESID: residual read from here instead of `out` (same ldo); nullptr = in place
   void* aux;            // fp16 [M, ldo]: pre-activation read by EPI_BF16_DGELU / written by EPI_F16_BIAS_QGELU_SAVE
+  // Both operands stored with the CONTRACTION index outermost: a = [K, lda] (M contiguous), w = [K, ldw] (N contiguous),
+  // i.e. D = a^T w — the weight-gradient form (dW = dY^T X) fed straight from row-major activations as MN-major UMMA
+  // operands.  2-CTA kernel only (M > 128, N % 256 == 0, M % 64 == 0).
+  int mn_major;
 };
 
 // Enqueues the GEMM on `stream`. Returns 0 on success; on failure the message is in pg::last_error().

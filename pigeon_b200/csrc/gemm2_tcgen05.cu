@@ -17,6 +17,8 @@
 #include "ptx.cuh"
 #include "tma_host.h"
 
+#include <stdlib.h>
+
 namespace pg {
 
 namespace {
@@ -155,8 +157,17 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t full_leader = mapa(smem_u32(&full_bar[stage]), 0);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
           else        mbar_arrive_cluster(full_leader);
-          tma_load_2d_2sm(smem_a + stage * kABytes, &tmap_a, full_leader, kb * BLOCK_K, a_row);
-          tma_load_2d_2sm(smem_b + stage * kBBytes, &tmap_b, full_leader, kb * BLOCK_K, b_row);
+          if (!args.mn_major) {
+            tma_load_2d_2sm(smem_a + stage * kABytes, &tmap_a, full_leader, kb * BLOCK_K, a_row);
+            tma_load_2d_2sm(smem_b + stage * kBBytes, &tmap_b, full_leader, kb * BLOCK_K, b_row);
+          } else {
+            // operand tiles [64 contraction rows x 64 M/N columns] (128 B per row, swizzled): two per operand and CTA
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              tma_load_2d_2sm(smem_a + stage * kABytes + c * (kABytes / 2), &tmap_a, full_leader, a_row + c * 64, kb * BLOCK_K);
+              tma_load_2d_2sm(smem_b + stage * kBBytes + c * (kBBytes / 2), &tmap_b, full_leader, b_row + c * 64, kb * BLOCK_K);
+            }
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -164,7 +175,8 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader && lane == 0) {
-      const uint32_t idesc = make_idesc_f16(2 * BLOCK_M_CTA, BLOCK_N, 0, 0) | args.idesc_fmt;
+      const uint32_t mn = args.mn_major ? 1u : 0u;
+      const uint32_t idesc = make_idesc_f16(2 * BLOCK_M_CTA, BLOCK_N, mn, mn) | args.idesc_fmt;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -178,11 +190,20 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * kABytes);
           const uint32_t b_addr = smem_u32(smem_b + stage * kBBytes);
+          if (!mn) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t a_desc = make_smem_desc(a_addr + k * UMMA_K * 2, 16, 1024, kLayoutSw128);
-            const uint64_t b_desc = make_smem_desc(b_addr + k * UMMA_K * 2, 16, 1024, kLayoutSw128);
-            umma_ss_2sm(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t a_desc = make_smem_desc(a_addr + k * UMMA_K * 2, 16, 1024, kLayoutSw128);
+              const uint64_t b_desc = make_smem_desc(b_addr + k * UMMA_K * 2, 16, 1024, kLayoutSw128);
+              umma_ss_2sm(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {   // 16 contraction rows of 128 B per step
+              const uint64_t a_desc = make_smem_desc(a_addr + k * UMMA_K * 128, args.mn_lbo, args.mn_sbo, kLayoutSw128);
+              const uint64_t b_desc = make_smem_desc(b_addr + k * UMMA_K * 128, args.mn_lbo, args.mn_sbo, kLayoutSw128);
+              umma_ss_2sm(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0);
+            }
           }
           tc_commit_2sm(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -226,8 +247,14 @@ template <int EPI>
 int launch2(const GemmProblem& p, int num_sms, cudaStream_t stream) {
   constexpr bool f16_out = EpiTraits<EPI>::kF16Out || EPI == EPI_BF16_DGELU;   // 2-byte output elements
   CUtensorMap ta, tb;
-  if (make_tmap_f16_2d(&ta, p.a, p.M, p.K, p.lda, BLOCK_M_CTA, BLOCK_K)) return 1;
-  if (make_tmap_f16_2d(&tb, p.w, p.N, p.K, p.ldw, BLOCK_N_CTA, BLOCK_K)) return 1;
+  if (p.mn_major) {   // tensors are [K, M] and [K, N]; box = 64 contraction rows x 64 columns
+    if (p.M % 64) { set_last_error("gemm2: MN-major operands need M %% 64 == 0"); return 1; }
+    if (make_tmap_f16_2d(&ta, p.a, p.K, p.M, p.lda, BLOCK_K, 64)) return 1;
+    if (make_tmap_f16_2d(&tb, p.w, p.K, p.N, p.ldw, BLOCK_K, 64)) return 1;
+  } else {
+    if (make_tmap_f16_2d(&ta, p.a, p.M, p.K, p.lda, BLOCK_M_CTA, BLOCK_K)) return 1;
+    if (make_tmap_f16_2d(&tb, p.w, p.N, p.K, p.ldw, BLOCK_N_CTA, BLOCK_K)) return 1;
+  }
   auto kern = gemm2_f16_kernel<EPI>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -239,9 +266,14 @@ int launch2(const GemmProblem& p, int num_sms, cudaStream_t stream) {
   a.M = p.M; a.N = p.N; a.K = p.K; a.out = p.out; a.ldo = p.ldo; a.bias = p.bias;
   a.vec_ok = (p.ldo % (f16_out ? 8 : 4)) == 0;
   a.rowmap_div = p.rowmap_div > 0 ? p.rowmap_div : 1; a.rowmap_mul = p.rowmap_mul; a.rowmap_add = p.rowmap_add;
-  a.idesc_fmt = p.operand_bf16 ? ((1u << 7) | (1u << 10)) : 0u;
+  // operand_bf16: 0 = fp16 x fp16, 1 = bf16 x bf16, 2 = A bf16 / W fp16, 3 = A fp16 / W bf16
+  a.idesc_fmt = ((p.operand_bf16 == 1 || p.operand_bf16 == 2) ? (1u << 7) : 0u) | ((p.operand_bf16 == 1 || p.operand_bf16 == 3) ? (1u << 10) : 0u);
   a.resid = p.resid ? p.resid : reinterpret_cast<const float*>(p.out);
   a.aux = p.aux;
+  a.mn_major = p.mn_major ? 1 : 0;
+  a.mn_lbo = 8192; a.mn_sbo = 1024;   // chunk stride along M/N (64 columns = one swizzled 128-byte row set), 8-row group stride
+  if (const char* e = getenv("PG_MN_LBO")) a.mn_lbo = (uint32_t)atoi(e);
+  if (const char* e = getenv("PG_MN_SBO")) a.mn_sbo = (uint32_t)atoi(e);
   if ((EPI == EPI_BF16_DGELU || EPI == EPI_F16_BIAS_QGELU_SAVE) && (!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15))) {
     set_last_error("gemm: this epilogue needs a 16-byte aligned aux buffer"); return 1;
   }

@@ -21,6 +21,8 @@ struct GemmArgs {
   uint32_t idesc_fmt;  // A/B format bits of the instruction descriptor (0 = fp16, bf16 otherwise)
   const float* resid;  // residual source of EPI_F32_BIAS_RESID (== out when updating in place)
   void* aux;           // EPI_BF16_DGELU: fc1 pre-activation (fp16, read);  EPI_F16_BIAS_QGELU_SAVE: where to keep it (written)
+  int mn_major;        // operands are [K, M] / [K, N] (MN-major UMMA operands), see GemmProblem::mn_major
+  uint32_t mn_lbo, mn_sbo;   // descriptor strides of the MN-major operand tiles (bytes)
 };
 
 __device__ __forceinline__ float quick_gelu(float v) {

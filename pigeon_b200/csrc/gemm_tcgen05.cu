@@ -185,9 +185,11 @@ int launch(const GemmProblem& p, int num_sms, cudaStream_t stream) {
   a.M = p.M; a.N = p.N; a.K = p.K; a.out = p.out; a.ldo = p.ldo; a.bias = p.bias;
   a.vec_ok = (p.ldo % (f16_out ? 8 : 4)) == 0;
   a.rowmap_div = p.rowmap_div > 0 ? p.rowmap_div : 1; a.rowmap_mul = p.rowmap_mul; a.rowmap_add = p.rowmap_add;
-  a.idesc_fmt = p.operand_bf16 ? ((1u << 7) | (1u << 10)) : 0u;
+  // operand_bf16: 0 = fp16 x fp16, 1 = bf16 x bf16, 2 = A bf16 / W fp16, 3 = A fp16 / W bf16
+  a.idesc_fmt = ((p.operand_bf16 == 1 || p.operand_bf16 == 2) ? (1u << 7) : 0u) | ((p.operand_bf16 == 1 || p.operand_bf16 == 3) ? (1u << 10) : 0u);
   a.resid = p.resid ? p.resid : reinterpret_cast<const float*>(p.out);
   a.aux = p.aux;
+  a.mn_major = 0; a.mn_lbo = a.mn_sbo = 0;
   if ((EPI == EPI_BF16_DGELU || EPI == EPI_F16_BIAS_QGELU_SAVE) && (!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15))) {
     set_last_error("gemm: this epilogue needs a 16-byte aligned aux buffer"); return 1;
   }
@@ -225,6 +227,10 @@ int gemm_f16(const GemmProblem& p, int num_sms, cudaStream_t stream) {
   }
   // Wide tiles when N is a multiple of 256 (all ViT-L projections); 128-wide otherwise (head, small tests).
   const bool wide = (p.N % 256 == 0);
+  if (p.mn_major) {
+    if (!(wide && p.M > 128 && num_sms >= 2)) { set_last_error("gemm: MN-major operands need N %% 256 == 0 and M > 128"); return 1; }
+    return gemm2_f16(p, num_sms, stream);
+  }
   if (wide && p.M > 128 && num_sms >= 2 && use_2cta()) return gemm2_f16(p, num_sms, stream);
   switch (p.epi) {
     case EPI_F16_BIAS:       return wide ? launch<256, EPI_F16_BIAS>(p, num_sms, stream)       : launch<128, EPI_F16_BIAS>(p, num_sms, stream);

@@ -39,19 +39,39 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ------------------------------------------------------------------------------------------------ casts
+template <typename T> struct Vec8;   // 8 source elements in one or two 16-byte loads
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+template <> struct Vec8<__half> {
+  static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
+    const uint4 a = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+      v[2 * k] = f.x; v[2 * k + 1] = f.y;
+    }
+  }
+};
+
+// 8 elements per thread and iteration: 16/32-byte loads, one 16-byte store (src and out 16-byte aligned, checked by the host)
 template <typename T>
 __global__ void __launch_bounds__(256) cast_kernel(const T* __restrict__ src, __nv_bfloat16* __restrict__ out, long n) {
-  const long stride = (long)gridDim.x * 256 * 4;
-  for (long i = ((long)blockIdx.x * 256 + threadIdx.x) * 4; i < n; i += stride) {
-    if (i + 4 <= n) {
-      float v[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = to_f32<T>(src[i + k]);
-      __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&a);
-      pk.y = *reinterpret_cast<uint32_t*>(&b);
-      *reinterpret_cast<uint2*>(out + i) = pk;
+  const long stride = (long)gridDim.x * 256 * 8;
+  for (long i = ((long)blockIdx.x * 256 + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      float v[8];
+      Vec8<T>::load(src + i, v);
+      uint4 pk;
+      __nv_bfloat162 b0 = __floats2bfloat162_rn(v[0], v[1]), b1 = __floats2bfloat162_rn(v[2], v[3]);
+      __nv_bfloat162 b2 = __floats2bfloat162_rn(v[4], v[5]), b3 = __floats2bfloat162_rn(v[6], v[7]);
+      pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+      pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+      *reinterpret_cast<uint4*>(out + i) = pk;
     } else {
       for (long k = i; k < n; ++k) out[k] = __float2bfloat16_rn(to_f32<T>(src[k]));
     }
@@ -294,8 +314,12 @@ column_sum_kernel(const T* __restrict__ x, long ldx, float* __restrict__ out, lo
 
 int cast_to_bf16(const void* src, int src_type, void* out, long n, cudaStream_t stream) {
   if (n <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out)) & 15) {
+    set_last_error("cast_to_bf16: buffers must be 16-byte aligned");
+    return 1;
+  }
   ProfScope prof("train_cast_bf16", stream);
-  const int grid = grid_1d(n, 1024);
+  const int grid = grid_1d(n, 2048);
   if (src_type == SRC_F32) cast_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(src), reinterpret_cast<__nv_bfloat16*>(out), n);
   else if (src_type == SRC_F16) cast_kernel<__half><<<grid, 256, 0, stream>>>(reinterpret_cast<const __half*>(src), reinterpret_cast<__nv_bfloat16*>(out), n);
   else { set_last_error("cast_to_bf16: bad source type %d", src_type); return 1; }

@@ -61,16 +61,28 @@ int dgrad(const void* a, const void* w_t, float* out, long M, int N, int K, int 
   return gemm_f16(p, sms, st);
 }
 
-// dw f32 [M, N] += left^T . right, with left [rows, M] and right [rows, N] given in any supported type:
-// both are transposed to bf16 [*, rows_p] and multiplied on the tensor cores (contraction over the rows).
+// dw f32 [M, N] += left^T . right, with left [rows, M] and right [rows, N] row-major in any supported type.
+// Fast path: both operands as bf16 [rows, *] straight into the GEMM as MN-major UMMA operands (a cast where the saved
+// activation is fp16 — tcgen05 kind::f16 wants A and B of one type — and no transposes).  Otherwise (N % 256 != 0, the
+// patch embedding, or gathered rows): transpose both to bf16 [*, rows_p] and use the K-major kernel.
 int wgrad(const void* left, int left_type, long ld_left, int M, const void* right, int right_type, long ld_right, int N,
           long rows, float* dw, const BwdWs& w, int sms, cudaStream_t st, int map_div = 0, int map_mul = 0, int map_add = 0) {
-  if (transpose_to_bf16(left, left_type, ld_left, w.at, w.rows_p, rows, M, map_div, map_mul, map_add, st)) return 1;
-  if (transpose_to_bf16(right, right_type, ld_right, w.bt, w.rows_p, rows, N, 0, 0, 0, st)) return 1;
   GemmProblem p{};
   p.M = M; p.N = N; p.K = (int)rows;
-  p.a = w.at; p.lda = (int)w.rows_p; p.w = w.bt; p.ldw = (int)w.rows_p;
   p.out = dw; p.ldo = N; p.bias = nullptr; p.epi = EPI_F32_BIAS_RESID; p.operand_bf16 = 1;
+  const bool direct = map_div == 0 && N % 256 == 0 && M % 64 == 0 && M > 128 && ld_left == M && ld_right == N &&
+                      ld_left % 8 == 0 && ld_right % 8 == 0;
+  if (direct) {
+    const void* l = left;
+    const void* r = right;
+    if (left_type != SRC_BF16) { if (cast_to_bf16(left, left_type, w.at, rows * M, st)) return 1; l = w.at; }
+    if (right_type != SRC_BF16) { if (cast_to_bf16(right, right_type, w.bt, rows * N, st)) return 1; r = w.bt; }
+    p.a = l; p.lda = M; p.w = r; p.ldw = N; p.mn_major = 1;
+    return gemm_f16(p, sms, st);
+  }
+  if (transpose_to_bf16(left, left_type, ld_left, w.at, w.rows_p, rows, M, map_div, map_mul, map_add, st)) return 1;
+  if (transpose_to_bf16(right, right_type, ld_right, w.bt, w.rows_p, rows, N, 0, 0, 0, st)) return 1;
+  p.a = w.at; p.lda = (int)w.rows_p; p.w = w.bt; p.ldw = (int)w.rows_p;
   return gemm_f16(p, sms, st);
 }
 
@@ -253,7 +265,18 @@ int pg_gemm_ex(const void* a, int32_t lda, const void* w, int32_t ldw, void* out
   if (sms < 0) return 1;
   GemmProblem p{};
   p.M = M; p.N = N; p.K = K; p.a = a; p.lda = lda; p.w = w; p.ldw = ldw; p.out = out; p.ldo = ldo; p.bias = bias;
-  p.epi = epilogue; p.operand_bf16 = operand_bf16 ? 1 : 0; p.resid = resid;
+  p.epi = epilogue; p.operand_bf16 = operand_bf16; p.resid = resid;
+  return gemm_f16(p, sms, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int pg_gemm_tn(const void* a, int32_t lda, const void* w, int32_t ldw, float* out, int32_t ldo, int32_t M, int32_t N,
+               int32_t K, int32_t accumulate, int32_t operand_bf16, void* stream) {
+  if (!a || !w || !out) { set_last_error("pg_gemm_tn: null argument"); return 1; }
+  const int sms = sm_count();
+  if (sms < 0) return 1;
+  GemmProblem p{};
+  p.M = M; p.N = N; p.K = K; p.a = a; p.lda = lda; p.w = w; p.ldw = ldw; p.out = out; p.ldo = ldo; p.bias = nullptr;
+  p.epi = accumulate ? EPI_F32_BIAS_RESID : EPI_F32_BIAS; p.operand_bf16 = operand_bf16; p.mn_major = 1;
   return gemm_f16(p, sms, reinterpret_cast<cudaStream_t>(stream));
 }
 
