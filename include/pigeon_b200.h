@@ -255,8 +255,8 @@ enum {
 /* D[M,N] = A[M,K] (fp16, row stride lda) * W[N,K]^T (fp16, row stride ldw), fp32 accumulate on tcgen05. */
 int pg_gemm_f16(const void* a, int32_t lda, const void* w, int32_t ldw, void* out, int32_t ldo, const float* bias,
                 int32_t M, int32_t N, int32_t K, int32_t epilogue, void* stream);
-/* pg_gemm_f16 with bf16 operands (operand_bf16: 0 = fp16 x fp16, 1 = bf16 x bf16, 2 = a bf16 / w fp16, 3 = a fp16 / w bf16)
- * and, for PG_EPI_F32_BIAS_RESID, an out-of-place residual source
+/* pg_gemm_f16 with bf16 operands (operand_bf16 != 0: BOTH a and w are bf16 — the tensor cores reject mixed pairs) and,
+ * for PG_EPI_F32_BIAS_RESID, an out-of-place residual source
  * `resid` f32 [M, ldo] (NULL = update `out` in place). */
 int pg_gemm_ex(const void* a, int32_t lda, const void* w, int32_t ldw, void* out, int32_t ldo, const float* bias,
                const float* resid, int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t operand_bf16, void* stream);

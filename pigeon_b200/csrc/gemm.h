@@ -25,7 +25,7 @@ struct GemmProblem {
   const float* bias;
   int epi;
   int rowmap_div, rowmap_mul, rowmap_add;
-  int operand_bf16;     // 0: A, W fp16;  1: both bf16 (backward GEMMs);  2: A bf16, W fp16;  3: A fp16, W bf16
+  int operand_bf16;     // A and W both hold bf16 instead of fp16 (backward GEMMs; mixed pairs are illegal on the tensor cores)
   const float* resid;   // EPI_F32_BIAS_RESID: residual read from here instead of `out` (same ldo); nullptr = in place
   void* aux;            // fp16 [M, ldo]: pre-activation read by EPI_BF16_DGELU / written by EPI_F16_BIAS_QGELU_SAVE
   // Both operands stored with the CONTRACTION index outermost: a = [K, lda] (M contiguous), w = [K, ldw] (N contiguous),

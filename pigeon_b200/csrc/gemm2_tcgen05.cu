@@ -266,8 +266,8 @@ int launch2(const GemmProblem& p, int num_sms, cudaStream_t stream) {
   a.M = p.M; a.N = p.N; a.K = p.K; a.out = p.out; a.ldo = p.ldo; a.bias = p.bias;
   a.vec_ok = (p.ldo % (f16_out ? 8 : 4)) == 0;
   a.rowmap_div = p.rowmap_div > 0 ? p.rowmap_div : 1; a.rowmap_mul = p.rowmap_mul; a.rowmap_add = p.rowmap_add;
-  // operand_bf16: 0 = fp16 x fp16, 1 = bf16 x bf16, 2 = A bf16 / W fp16, 3 = A fp16 / W bf16
-  a.idesc_fmt = ((p.operand_bf16 == 1 || p.operand_bf16 == 2) ? (1u << 7) : 0u) | ((p.operand_bf16 == 1 || p.operand_bf16 == 3) ? (1u << 10) : 0u);
+  // A and B of one type: tcgen05 kind::f16 traps (illegal instruction) on a bf16 x fp16 pair
+  a.idesc_fmt = p.operand_bf16 ? ((1u << 7) | (1u << 10)) : 0u;
   a.resid = p.resid ? p.resid : reinterpret_cast<const float*>(p.out);
   a.aux = p.aux;
   a.mn_major = p.mn_major ? 1 : 0;

@@ -265,7 +265,7 @@ int pg_gemm_ex(const void* a, int32_t lda, const void* w, int32_t ldw, void* out
   if (sms < 0) return 1;
   GemmProblem p{};
   p.M = M; p.N = N; p.K = K; p.a = a; p.lda = lda; p.w = w; p.ldw = ldw; p.out = out; p.ldo = ldo; p.bias = bias;
-  p.epi = epilogue; p.operand_bf16 = operand_bf16; p.resid = resid;
+  p.epi = epilogue; p.operand_bf16 = operand_bf16 ? 1 : 0; p.resid = resid;
   return gemm_f16(p, sms, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -276,7 +276,7 @@ int pg_gemm_tn(const void* a, int32_t lda, const void* w, int32_t ldw, float* ou
   if (sms < 0) return 1;
   GemmProblem p{};
   p.M = M; p.N = N; p.K = K; p.a = a; p.lda = lda; p.w = w; p.ldw = ldw; p.out = out; p.ldo = ldo; p.bias = nullptr;
-  p.epi = accumulate ? EPI_F32_BIAS_RESID : EPI_F32_BIAS; p.operand_bf16 = operand_bf16; p.mn_major = 1;
+  p.epi = accumulate ? EPI_F32_BIAS_RESID : EPI_F32_BIAS; p.operand_bf16 = operand_bf16 ? 1 : 0; p.mn_major = 1;
   return gemm_f16(p, sms, reinterpret_cast<cudaStream_t>(stream));
 }
 

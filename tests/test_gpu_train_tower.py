@@ -291,3 +291,24 @@ def test_train_model_loop_with_trainable_tower(cuda):
     assert any("encoder.layers.1." in k for k in changed) and any("cell_layer" in k for k in changed)
     assert any("embeddings" in k for k in changed)
     assert not any("encoder.layers.0." in k for k in changed)                        # frozen layer untouched
+
+
+@pytest.mark.parametrize("M,N,K,bf16", [(512, 512, 640, 1), (1024, 4096, 2308, 1), (3072, 1024, 577, 0), (256, 256, 70, 1)])
+def test_gemm_tn_mn_major_operands(cuda, M, N, K, bf16):
+    """pg_gemm_tn: D (+)= a^T w with a [K, M], w [K, N] — the weight-gradient product straight from row-major operands."""
+    lib, check, ptr, sp = _lib()
+    dt = torch.bfloat16 if bf16 else torch.float16
+    g = torch.Generator().manual_seed(M + K)
+    a = (torch.randn(K, M, generator=g) * 1e-3).to(cuda, dt)
+    w = (torch.randn(K, N, generator=g) * 0.3).to(cuda, dt)
+    ref = a.double().t() @ w.double()
+    out = torch.full((M, N), float("nan"), device=cuda)
+    check(lib.pg_gemm_tn(ptr(a), M, ptr(w), N, ptr(out), N, M, N, K, 0, bf16, sp()), "pg_gemm_tn")
+    assert _rel(out, ref) < 1e-5
+    acc0 = torch.randn(M, N, generator=g).to(cuda) * 1e-3
+    out = acc0.clone()
+    check(lib.pg_gemm_tn(ptr(a), M, ptr(w), N, ptr(out), N, M, N, K, 1, bf16, sp()), "pg_gemm_tn")
+    assert _rel(out, acc0.double() + ref) < 1e-5
+    from pigeon_b200 import PigeonB200Error
+    with pytest.raises(PigeonB200Error):                       # shapes the MN-major path does not take
+        check(lib.pg_gemm_tn(ptr(a), M, ptr(w), N, ptr(out), N, M, 200, K, 0, bf16, sp()), "pg_gemm_tn")

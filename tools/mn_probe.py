@@ -26,7 +26,7 @@ for lbo, sbo in ((8192, 1024), (1024, 8192), (1024, 1024), (8192, 8192), (128, 1
         err = str(e)[:80]
     print(f"LBO={lbo:5d} SBO={sbo:5d}: rel err {err}", flush=True)
 
-os.environ.pop("PG_MN_LBO"); os.environ.pop("PG_MN_SBO")
+os.environ.pop("PG_MN_LBO"); os.environ.pop("PG_MN_SBO")   # library defaults from here on
 w16 = w.to(torch.float16)
 ref2 = a.double().t() @ w16.double()
 for mode, (aa, ww, rr) in {1: (a, w, ref), 0: (a.to(torch.float16), w16, None)}.items():   # mixed types (2, 3) trap: illegal instruction
