@@ -97,7 +97,7 @@ int pg_vit_forward(pg_vit* h, const void* pixels, int32_t pixels_f16, int32_t n_
   float* x; void* xn; void* u;
   const size_t need = vit_carve(h, n_views, workspace, &x, &xn, &u);
   if (workspace_bytes < need) { set_last_error("pg_vit_forward: workspace %zu < required %zu", workspace_bytes, need); return 1; }
-  if (reinterpret_cast<uintptr_t>(workspace) & 1023) { set_last_error("pg_vit_forward: workspace must be 1024-byte aligned"); return 1; }
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) { set_last_error("pg_vit_forward: workspace must be 256-byte aligned"); return 1; }
   const pg_vit_config& c = h->cfg;
   const long rows = (long)n_views * h->tokens;
   const int np = h->grid_patches * h->grid_patches;

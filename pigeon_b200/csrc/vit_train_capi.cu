@@ -173,7 +173,7 @@ int pg_vit_backward(pg_vit* h, const pg_vit_saved* sv, const float* d_emb, int32
   const long rows = (long)n_views * h->tokens;
   const int np = h->grid_patches * h->grid_patches;
   const int H = c.hidden, I = c.intermediate;
-  if (reinterpret_cast<uintptr_t>(workspace) & 1023) { set_last_error("pg_vit_backward: workspace must be 1024-byte aligned"); return 1; }
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) { set_last_error("pg_vit_backward: workspace must be 256-byte aligned"); return 1; }
   const BwdWs w = carve_bwd(h, n_views, workspace);
   if (workspace_bytes < w.total) { set_last_error("pg_vit_backward: workspace %zu < required %zu", workspace_bytes, w.total); return 1; }
 
@@ -301,8 +301,8 @@ int pg_attention_backward(const void* qkv, const void* out, const float* d_out, 
   if (!qkv || !out || !d_out || !lse2 || !dqkv_bf16 || !workspace) { set_last_error("pg_attention_backward: null argument"); return 1; }
   if (n_views <= 0) return 0;
   if (workspace_bytes < pg_attention_backward_workspace_bytes(n_views, seq, heads) ||
-      (reinterpret_cast<uintptr_t>(workspace) & 1023)) {
-    set_last_error("pg_attention_backward: workspace too small or not 1024-byte aligned");
+      (reinterpret_cast<uintptr_t>(workspace) & 255)) {
+    set_last_error("pg_attention_backward: workspace too small or not 256-byte aligned");
     return 1;
   }
   const int sms = sm_count();
