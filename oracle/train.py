@@ -55,3 +55,20 @@ def adamw_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_de
     denom = np.sqrt(v) / f(np.sqrt(bc2)) + f(eps)
     p = p + f(-(lr / bc1)) * (m / denom)
     return p.astype(f), m.astype(f), v.astype(f)
+
+
+def tower_gradients(sd, pixel_values, d_emb, *, patch: int, heads: int, layers: int, eps: float = 1e-5):
+    """Gradients of the vision tower for a given upstream gradient `d_emb` [n, hidden] with respect to the token-mean
+    embedding (models/super_guessr.py:395-398): what `loss.backward()` (training/train_eval_loop.py:216) propagates into
+    HF CLIPVisionTransformer, obtained by differentiating the oracle's own fp32 restatement of its forward (oracle/vit.py)
+    with torch autograd on the CPU.  Returns (embedding [n, hidden], {stripped parameter name: gradient}).
+    Pinned against tests/golden/train_tower_small.npz (gradients of the unmodified reference model)."""
+    import torch
+    from . import vit as ovit
+    names = [k for k, v in ovit._strip(sd).items() if v.is_floating_point() and "post_layernorm" not in k and "position_ids" not in k]
+    leaf = {k: v.detach().clone().float().requires_grad_(True) for k, v in ovit._strip(sd).items() if k in names}
+    with torch.enable_grad():
+        h = ovit.vit_last_hidden_state.__wrapped__(leaf, pixel_values.float(), patch=patch, heads=heads, layers=layers, eps=eps)
+        emb = h.mean(dim=1)
+        grads = torch.autograd.grad(emb, [leaf[k] for k in names], grad_outputs=torch.as_tensor(d_emb, dtype=torch.float32))
+    return emb.detach(), {k: g for k, g in zip(names, grads)}

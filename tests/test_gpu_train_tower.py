@@ -312,3 +312,53 @@ def test_gemm_tn_mn_major_operands(cuda, M, N, K, bf16):
     from pigeon_b200 import PigeonB200Error
     with pytest.raises(PigeonB200Error):                       # shapes the MN-major path does not take
         check(lib.pg_gemm_tn(ptr(a), M, ptr(w), N, ptr(out), N, M, 200, K, 0, bf16, sp()), "pg_gemm_tn")
+
+
+def test_tower_backward_at_real_geometry_vs_oracle(cuda):
+    """ViT-L/14-336 (24 layers, 577 tokens, 1024 hidden), 2 views: pg_vit_forward_train / pg_vit_backward against
+    oracle/train.tower_gradients (fp32 autograd through the oracle's restated forward, itself pinned to the reference's
+    gradients by tests/test_oracle_golden.py).  Every trainable parameter of the tower is compared."""
+    import time
+    from oracle import train as otrain
+    from pigeon_b200 import CLIPVisionTower, VitDims, synthetic
+    from pigeon_b200.vit_train import TowerTrainer
+    dims = VitDims()
+    sd = synthetic.random_vit_state_dict(dims, seed=0)
+    tower = CLIPVisionTower(dims)
+    tower.load_state_dict(sd, strict=True)
+    tower.to(cuda)
+    g = torch.Generator().manual_seed(11)
+    px = torch.randn(2, 3, 336, 336, generator=g)
+    d_emb = torch.randn(2, dims.hidden, generator=g) * 1e-4
+    tr = TowerTrainer(tower, max_views=2)
+    emb = tr.forward(px.to(cuda).half())
+    tr.backward(d_emb.to(cuda))
+    tr.finalize(1)
+    t0 = time.time()
+    ref_emb, ref = otrain.tower_gradients(sd, px.half().float(), d_emb, patch=dims.patch_size, heads=dims.heads,
+                                          layers=dims.layers)
+    assert _rel(emb.cpu(), ref_emb) < 1e-3
+    worst = {}
+    for name, p in tower.named_parameters():
+        key = name.replace("vision_model.", "", 1)
+        if key not in ref:
+            continue
+        assert p.grad is not None, name
+        r = ref[key].double()
+        if r.norm().item() < 1e-12:
+            continue
+        err = (p.grad.detach().cpu().double() - r).norm().item() / r.norm().item()
+        if "k_proj.bias" in key:                      # mathematically zero gradient (softmax shift invariance): noise / noise
+            continue
+        worst[key] = err
+        assert err < REL, (key, err)
+    assert len(worst) >= 24 * 14
+    try:
+        d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity.log"), "a") as f:
+            f.write(f"vit_large_336 tower backward (24 layers, 577 tokens, 2 views) vs fp32 CPU oracle: worst per-tensor relative "
+                    f"gradient error {max(worst.values()):.3e} ({max(worst, key=worst.get)}), median "
+                    f"{float(np.median(list(worst.values()))):.3e}; oracle took {time.time() - t0:.0f} s\n")
+    except OSError:
+        pass
