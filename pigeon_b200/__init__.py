@@ -3,6 +3,8 @@
     CLIPEmbedding  (reference models/clip_embedder.py)   ViT-L/14-336 forward + token mean
     SuperGuessr    (reference models/super_guessr.py)    geocell head: Linear + softmax + argmax + top-k (+ CE loss)
     ProtoRefiner   (reference models/proto_refiner.py)   prototype retrieval refinement
+    train_model, AdamW (reference training/train_eval_loop.py:164-253)   fine-tune step: head and tower backward
+    ClipImageProcessor (the reference's CLIPProcessor call sites)        image pre-processing on the GPU
 
 Host code is Python/PyTorch plumbing over a C-ABI CUDA library (include/pigeon_b200.h); see DESIGN.md.
 """
@@ -21,4 +23,10 @@ def __getattr__(name):  # lazy: these import pandas / transformers-sized depende
     if name == "CLIPEmbedding":
         from .clip_embedder import CLIPEmbedding
         return CLIPEmbedding
+    if name in ("train_model", "AdamW", "finetune_model", "finetune_on_embeddings"):
+        from . import training
+        return getattr(training, name)
+    if name == "ClipImageProcessor":
+        from .preprocess import ClipImageProcessor
+        return ClipImageProcessor
     raise AttributeError(name)
