@@ -1,68 +1,58 @@
-"""CLIPEmbedding — CLIP ViT-L/14-336 image embedder, B200 execution behind the reference's interface.
+"""CLIPEmbedding — the reference's CLIP ViT-L/14-336 image embedder (models/clip_embedder.py) with the B200 tower behind it.
 
-Mirror of reference models/clip_embedder.py: `CLIPEmbedding(model_name, device='cuda', load_checkpoint=False,
-panorama=False)`, `forward(image) -> Tensor[N, 1024]` = mean over all tokens of last_hidden_state
-(:63-65), no_grad, not trainable.
+Same constructor arguments (`model_name, device='cuda', load_checkpoint=False, panorama=False`), same call
+(`embedder(image) -> Tensor[N, hidden]`), same result: the mean over ALL tokens of `last_hidden_state`
+(reference :63-65) — computed by the fused CUDA path, never trainable, never on the CPU.
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Optional
 
 import torch
 from torch import Tensor
 
 from .config import CLIP_MODEL
 from .model_utils import load_state_dict
-from .super_guessr import CLIPVisionTower, as_tower
-from .vit_engine import VitDims
+from .super_guessr import as_tower
 
 
 class CLIPEmbedding(torch.nn.Module):
     def __init__(self, model_name: str, device: str = 'cuda', load_checkpoint: bool = False, panorama: bool = False,
                  clip_model=None, processor=None):
-        """Arguments as in the reference (:11-23).
-
-        Extension for offline use (the reference downloads `CLIP_MODEL` from the hub, :25-26): `clip_model=` a
-        `CLIPVisionTower` or HF `CLIPVisionModel` to wrap, `processor=` a callable like HF `CLIPProcessor`."""
+        """Reference arguments (:11-23) plus two keyword extensions for offline use — the reference pulls `CLIP_MODEL`
+        and its processor from the hub (:25-26): `clip_model` (a `CLIPVisionTower` or a HF `CLIPVisionModel` to wrap) and
+        `processor` (any callable with the `CLIPProcessor(images=..., return_tensors='pt')` convention; by default the GPU
+        pre-processor of `pigeon_b200.preprocess`, whose output is bit-identical, built on first use)."""
         super().__init__()
-        self.device = device
         if clip_model is None:
             from transformers import CLIPVisionModel
             clip_model = CLIPVisionModel.from_pretrained(CLIP_MODEL)
-        # :25 `CLIPProcessor.from_pretrained(CLIP_MODEL)` — here the GPU pre-processor (bit-identical output, no hub access),
-        # built on first use so that a model fed pre-processed tensors never needs it
-        self.processor = processor
-        self.clip_model = as_tower(clip_model)
-        self.panorama = panorama
-
-        if load_checkpoint:                                                  # :29-32
-            state_dict = torch.load(model_name, map_location=torch.device('cuda'))
-            load_state_dict(self.clip_model.base_model, state_dict, embedder=True)
+        tower = as_tower(clip_model)
+        if load_checkpoint:                                   # :29-32, keys are stored under 'base_model.'
+            load_state_dict(tower.base_model, torch.load(model_name, map_location='cuda'), embedder=True)
             print('Loaded embedder from checkpoint:', model_name)
-
-        if type(device) == str:                                              # :34-37
-            self.clip_model = self.clip_model.to(self.device)
-        else:
-            self.clip_model = self.clip_model.cuda(self.device)
+        self.device = device
+        self.panorama = panorama
+        self.processor = processor
+        self.clip_model = tower.to(device) if isinstance(device, str) else tower.cuda(device)     # :34-37
         self.eval()
 
-    def _get_embedding(self, image) -> Tensor:
-        """:42-66 — accepts a pre-processed tensor or PIL image(s)."""
-        with torch.no_grad():
-            if isinstance(image, Tensor) == False:
-                if self.processor is None:
-                    from .preprocess import ClipImageProcessor
-                    dev = next(self.clip_model.parameters()).device
-                    self.processor = ClipImageProcessor(size=self.clip_model.dims.image_size, device=dev, dtype=torch.float16)
-                inputs = self.processor(images=image, return_tensors='pt')
-                pixel_values = inputs['pixel_values']
-            else:
-                pixel_values = image
-            if type(self.device) == str:
-                pixel_values = pixel_values.to(self.device)
-            else:
-                pixel_values = pixel_values.cuda(self.device)
-            return self.clip_model.embed(pixel_values)                       # ViT forward + torch.mean(dim=1), fused
+    def _pixels(self, image) -> Tensor:
+        """Pre-processed tensors pass through; anything else (PIL images, uint8 arrays, lists of them) goes through the
+        processor (:48-56)."""
+        if isinstance(image, Tensor):
+            return image
+        if self.processor is None:
+            from .preprocess import ClipImageProcessor
+            self.processor = ClipImageProcessor(size=self.clip_model.dims.image_size,
+                                                device=next(self.clip_model.parameters()).device, dtype=torch.float16)
+        return self.processor(images=image, return_tensors='pt')['pixel_values']
 
-    def forward(self, image: Dict) -> Tensor:
+    @torch.no_grad()
+    def _get_embedding(self, image) -> Tensor:
+        pixels = self._pixels(image)
+        pixels = pixels.to(self.device) if isinstance(self.device, str) else pixels.cuda(self.device)
+        return self.clip_model.embed(pixels)                  # tower forward + token mean in one pass (:63-65)
+
+    def forward(self, image) -> Tensor:
         return self._get_embedding(image)
