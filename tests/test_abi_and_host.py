@@ -252,3 +252,20 @@ def test_state_dict_is_a_plain_weights_file(tmp_path):
     sd = torch.load(path, map_location="cpu", weights_only=True)
     assert set(sd) == set(sg.state_dict())
     assert "base_model.vision_model.encoder.layers.1.mlp.fc2.weight" in sd and "cell_layer.weight" in sd and "lla_geocells" in sd
+
+
+def test_docs_only_name_entry_points_that_exist():
+    """DESIGN.md / INTEGRATION.md / README.md may only cite C entry points and structs the header declares
+    (`pg_vit_{create,destroy}` brace groups are expanded; a trailing-underscore prefix such as `pg_profile_*` is a family)."""
+    header = open(os.path.join(ROOT, "include", "pigeon_b200.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", code)) | set(re.findall(r"typedef struct (pg_\w+)", code))
+    for doc in ("DESIGN.md", "INTEGRATION.md", "README.md"):
+        text = open(os.path.join(ROOT, doc)).read()
+        names = set()
+        for m in re.finditer(r"pg_([a-z0-9_]*)\{([a-z0-9_,]+)\}", text):
+            names |= {f"pg_{m.group(1)}{alt}" for alt in m.group(2).split(",")}
+        text = re.sub(r"pg_[a-z0-9_]*\{[a-z0-9_,]+\}", " ", text)
+        names |= set(re.findall(r"\bpg_[a-z0-9_]+\b", text))
+        unknown = {n for n in names if n not in declared and not (n.endswith("_") and any(d.startswith(n) for d in declared))}
+        assert not unknown, (doc, sorted(unknown))
