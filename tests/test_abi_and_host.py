@@ -92,6 +92,18 @@ def test_module_surface_matches_reference_signatures():
     assert ModelOutput._fields == ("loss", "loss_clf", "loss_reg", "loss_climate", "loss_month", "preds_LLH",
                                    "preds_geocell", "preds_mt", "preds_climate", "preds_month", "top5_geocells",
                                    "embedding")                                                 # models/utils.py:7-9
+    from pigeon_b200 import loops, training
+    tm = list(inspect.signature(training.train_model).parameters)[:8]
+    assert tm == ["loaded_model", "dataset", "on_embeddings", "yfcc", "train_args", "metrics", "patience",
+                  "should_profile"]                                                             # train_eval_loop.py:164-166
+    ev = list(inspect.signature(loops.evaluate_model).parameters)[:8]
+    assert ev == ["model", "dataset", "metrics", "train_args", "refiner", "yfcc", "writer", "step"]   # :35-37
+    fm = list(inspect.signature(training.finetune_model).parameters)[:7]
+    assert fm == ["model", "dataset", "multi_task", "heading", "yfcc", "early_stopping", "train_args"]   # train_modes.py:67-69
+    fe = list(inspect.signature(training.finetune_on_embeddings).parameters)[:6]
+    assert fe == ["dataset", "multi_task", "heading", "yfcc", "early_stopping", "train_args"]           # train_modes.py:110-112
+    opt = list(inspect.signature(training.AdamW.__init__).parameters)[1:6]
+    assert opt == ["params", "lr", "betas", "eps", "weight_decay"]                               # torch.optim.AdamW
 
 
 def test_tower_state_dict_uses_hf_key_names_and_roundtrips():
