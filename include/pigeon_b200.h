@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 1
+#define PG_ABI_VERSION 2
 
 /* ---------------------------------------------------------------------------------------------------
  * Library
@@ -270,6 +270,11 @@ int pg_layernorm_f16(const float* x, void* y, const float* gamma, const float* b
                      float eps, void* stream);
 /* softmax(q k^T / 8) v per (view, head); qkv fp16 [n_views*seq, 3*heads*64] -> out fp16 [n_views*seq, heads*64]. */
 int pg_attention_f16(const void* qkv, void* out, int32_t n_views, int32_t seq, int32_t heads, void* stream);
+/* Measurement aid: the same op with the kernel chosen explicitly.  variant 0 = "pair" kernel (persistent, two query tiles per
+ * CTA, KV blocks of 128, Q in tensor memory; poly = eighths of the exponentials evaluated on the FMA pipe, < 0 = default),
+ * variant 1 = first-generation kernel (one tile per CTA, KV blocks of 32).  lse2 may be NULL. */
+int pg_attention_f16_variant(const void* qkv, void* out, float* lse2, int32_t n_views, int32_t seq, int32_t heads,
+                             int32_t variant, int32_t poly, void* stream);
 /* Same, also writing lse2 f32 [n_views*heads, seq] (log2-sum-exp of the scaled logits) for the backward pass. */
 int pg_attention_f16_lse(const void* qkv, void* out, float* lse2, int32_t n_views, int32_t seq, int32_t heads, void* stream);
 /* Backward of the attention core: qkv f16 [n_views*seq, 3*heads*64], d_out f32 and out f16 [n_views*seq, heads*64],

@@ -25,6 +25,7 @@ SOURCES = [
     "gemm_tcgen05.cu",
     "gemm2_tcgen05.cu",
     "attention_tcgen05.cu",
+    "attention_pair_tcgen05.cu",
     "vit_misc.cu",
     "head.cu",
     "refiner.cu",
@@ -59,6 +60,12 @@ def _digest() -> str:
         h.update(f.name.encode())
         h.update(f.read_bytes())
     return h.hexdigest()
+
+
+def is_current() -> bool:
+    """True when libpigeon_b200.so exists and was built from exactly the sources in the tree."""
+    stamp = OBJ_DIR / "digest.txt"
+    return LIB_PATH.exists() and stamp.exists() and stamp.read_text() == _digest()
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:

@@ -115,7 +115,11 @@ SIGNATURES = {
                               c_int32, c_int32, c_void_p]),
     "pg_layernorm_f16": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p]),
     "pg_attention_f16": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    "pg_attention_f16_variant": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                           c_void_p]),
 }
+
+ABI_VERSION = 2   # == PG_ABI_VERSION in include/pigeon_b200.h; bumped whenever a signature or struct changes
 
 EPI_F16_BIAS, EPI_F16_BIAS_QGELU, EPI_F32_BIAS_RESID, EPI_F32_BIAS = 0, 1, 2, 3
 
@@ -132,10 +136,17 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     if _lib is not None:
         return _lib
     path = lib_path()
-    if not path.exists():
-        if not build_if_missing:
-            raise PigeonB200Error(f"{path} is missing: run `python -m pigeon_b200._build` (needs nvcc)")
-        _build.build()
+    if build_if_missing:
+        # build() is content-hash idempotent: it returns at once when the binary matches the sources and rebuilds a stale
+        # one (the .so is git-ignored, so a pull can leave an old binary beside new sources).  Without nvcc an existing,
+        # hash-matching binary is used as it is; a stale or missing one is an error, never a silent mismatch.
+        try:
+            _build.build()
+        except RuntimeError as e:
+            if not path.exists() or not _build.is_current():
+                raise PigeonB200Error(f"{path} is missing or older than its sources and cannot be rebuilt: {e}") from e
+    elif not path.exists():
+        raise PigeonB200Error(f"{path} is missing: run `python -m pigeon_b200._build` (needs nvcc)")
     try:
         lib = C.CDLL(str(path))
     except OSError as e:  # pragma: no cover - environment problem
@@ -147,8 +158,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
             raise PigeonB200Error(f"{path} does not export {name}; rebuild with `python -m pigeon_b200._build --force`") from e
         fn.restype = res
         fn.argtypes = args
-    if lib.pg_abi_version() != 1:
-        raise PigeonB200Error(f"ABI version mismatch: library {lib.pg_abi_version()} != binding 1")
+    if lib.pg_abi_version() != ABI_VERSION:
+        raise PigeonB200Error(f"ABI version mismatch: library {lib.pg_abi_version()} != binding {ABI_VERSION}")
     _lib = lib
     return lib
 

@@ -9,6 +9,16 @@ namespace pg {
 int attention_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream,
                   float* lse2 = nullptr);
 
+// Second-generation forward kernel (attention_pair_tcgen05.cu): persistent, two query tiles per CTA, KV blocks of 128.
+// poly = eighths of the exponentials evaluated on the FMA pipe (0..3).  attention_f16 dispatches to it by default.
+int attention_pair_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream, float* lse2,
+                       int poly);
+
+// Explicit kernel choice for A/B measurements: variant 0 = pair kernel (poly in eighths, < 0 = default), 1 = first-generation
+// kernel (poly 0 / 4 / 2 = none / every 4th / every 2nd group).
+int attention_f16_variant(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream, float* lse2,
+                          int variant, int poly);
+
 // Backward of the attention core (attention_bwd_tcgen05.cu).
 //   qkv f16 / qkv_bf16 [n_views*seq, 3*heads*64] (same values, two operand types), d_out_bf16 [n_views*seq, heads*64],
 //   lse2 / delta f32 [n_views*heads, seq]  ->  dqkv bf16 [n_views*seq, 3*heads*64]

@@ -27,7 +27,9 @@
 #include "ptx.cuh"
 #include "tma_host.h"
 
+#include <atomic>
 #include <stdlib.h>
+#include <string.h>
 
 namespace pg {
 
@@ -445,11 +447,14 @@ int launch_attention(const void* qkv, void* out, int n_views, int seq, int heads
   CUtensorMap tm;
   if (make_tmap_f16_2d(&tm, qkv, (uint64_t)n_views * seq, 3 * hidden, 3 * hidden, Cfg::kBlockKV, kHeadDim)) return 1;
   auto kern = attention_kernel<Cfg>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<int> attr_set_dev[64];   // per device (the attribute is per context)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set_dev[dev].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { set_last_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
-    attr_set = true;
+    attr_set_dev[dev].store(1, std::memory_order_release);
   }
   AttnArgs a;
   a.seq = seq;
@@ -467,22 +472,53 @@ int launch_attention(const void* qkv, void* out, int n_views, int seq, int heads
 
 }  // namespace
 
+// Variant switches are read ONCE per process (PG_ATTN_VARIANT: "pair" (default) | "legacy" | "64" | "64s" | "64h" | "32c";
+// PG_ATTN_POLY: eighths of the exponentials on the FMA pipe for the pair kernel, or 4 / 2 = every 4th / 2nd group for
+// the legacy kernel).
+struct AttnSwitches {
+  int variant = 0;   // 0 pair, 1 legacy 32/2/4, 2 "64", 3 "64s", 4 "64h", 5 "32c"
+  int poly = -1;
+  AttnSwitches() {
+    const char* v = getenv("PG_ATTN_VARIANT");
+    if (v) {
+      if (!strcmp(v, "legacy") || !strcmp(v, "32")) variant = 1;
+      else if (!strcmp(v, "64")) variant = 2;
+      else if (!strcmp(v, "64s")) variant = 3;
+      else if (!strcmp(v, "64h")) variant = 4;
+      else if (!strcmp(v, "32c")) variant = 5;
+    }
+    const char* pe = getenv("PG_ATTN_POLY");
+    if (pe && pe[0] >= '0' && pe[0] <= '9') poly = pe[0] - '0';
+  }
+};
+
+int attention_f16_variant(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream, float* lse2,
+                          int variant, int poly) {
+  if (n_views <= 0) return 0;
+  if (variant == 0) return attention_pair_f16(qkv, out, n_views, seq, heads, stream, lse2, poly < 0 ? 2 : poly);
+  if (n_views > 65535) { set_last_error("attention (legacy kernel): n_views %d > 65535 (grid.z)", n_views); return 1; }
+  if (poly == 4) return launch_attention<AttnCfg<32, 2, 4, 4>>(qkv, out, n_views, seq, heads, stream, lse2);
+  if (poly == 2) return launch_attention<AttnCfg<32, 2, 4, 2>>(qkv, out, n_views, seq, heads, stream, lse2);
+  return launch_attention<AttnCfg<32, 2, 4>>(qkv, out, n_views, seq, heads, stream, lse2);
+}
+
 int attention_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream, float* lse2) {
   if (n_views <= 0) return 0;
-  // Default tiling: KV blocks of 32, 2 S buffers, 128 TMEM columns -> 4 co-resident CTAs per SM (measured 0.379 ms vs
-  // 0.436 ms per 128-view layer for the 64-wide / 3-buffer / 2-CTA tiling on the same box).  PG_ATTN_VARIANT=64 selects
-  // the latter (A/B switch).
-  const char* v = getenv("PG_ATTN_VARIANT");
-  if (v && v[0] == '6' && v[1] == '4' && v[2] == 's')   // experiment: 64-wide blocks, ONE S buffer, 128 TMEM columns, 4 CTAs/SM
-    return launch_attention<AttnCfg<64, 1, 4, 0, 4>>(qkv, out, n_views, seq, heads, stream, lse2);
-  if (v && v[0] == '6' && v[1] == '4' && v[2] == 'h')   // experiment: same, row processed in two 32-column halves (no spills)
-    return launch_attention<AttnCfg<64, 1, 4, 0, 4, true>>(qkv, out, n_views, seq, heads, stream, lse2);
-  if (v && v[0] == '3' && v[1] == '2' && v[2] == 'c')   // experiment: default tiling at 3 CTAs / SM (113 registers, no spills)
-    return launch_attention<AttnCfg<32, 2, 3>>(qkv, out, n_views, seq, heads, stream, lse2);
-  if (v && v[0] == '6' && v[1] == '4') return launch_attention<AttnCfg<64, 3, 2>>(qkv, out, n_views, seq, heads, stream, lse2);
-  const char* pe = getenv("PG_ATTN_POLY");     // experiment switch: "4" / "2" = every 4th / 2nd group on the FMA pipe
-  if (pe && pe[0] == '4') return launch_attention<AttnCfg<32, 2, 4, 4>>(qkv, out, n_views, seq, heads, stream, lse2);
-  if (pe && pe[0] == '2') return launch_attention<AttnCfg<32, 2, 4, 2>>(qkv, out, n_views, seq, heads, stream, lse2);
+  static const AttnSwitches sw;
+  if (sw.variant != 0 && n_views > 65535) {
+    set_last_error("attention (legacy kernel): n_views %d > 65535 (grid.z)", n_views);
+    return 1;
+  }
+  switch (sw.variant) {
+    case 0: return attention_pair_f16(qkv, out, n_views, seq, heads, stream, lse2, sw.poly < 0 ? 2 : sw.poly);
+    case 2: return launch_attention<AttnCfg<64, 3, 2>>(qkv, out, n_views, seq, heads, stream, lse2);
+    case 3: return launch_attention<AttnCfg<64, 1, 4, 0, 4>>(qkv, out, n_views, seq, heads, stream, lse2);
+    case 4: return launch_attention<AttnCfg<64, 1, 4, 0, 4, true>>(qkv, out, n_views, seq, heads, stream, lse2);
+    case 5: return launch_attention<AttnCfg<32, 2, 3>>(qkv, out, n_views, seq, heads, stream, lse2);
+    default: break;
+  }
+  if (sw.poly == 4) return launch_attention<AttnCfg<32, 2, 4, 4>>(qkv, out, n_views, seq, heads, stream, lse2);
+  if (sw.poly == 2) return launch_attention<AttnCfg<32, 2, 4, 2>>(qkv, out, n_views, seq, heads, stream, lse2);
   return launch_attention<AttnCfg<32, 2, 4>>(qkv, out, n_views, seq, heads, stream, lse2);
 }
 

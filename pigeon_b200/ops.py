@@ -44,12 +44,19 @@ def layernorm_f16(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     return y
 
 
-def attention_f16(qkv: torch.Tensor, n_views: int, seq: int, heads: int) -> torch.Tensor:
-    """qkv fp16 [n_views*seq, 3*heads*64] -> fp16 [n_views*seq, heads*64]."""
+def attention_f16(qkv: torch.Tensor, n_views: int, seq: int, heads: int, variant: int | None = None,
+                  poly: int = -1) -> torch.Tensor:
+    """qkv fp16 [n_views*seq, 3*heads*64] -> fp16 [n_views*seq, heads*64].
+
+    `variant` (A/B measurements only): 0 = pair kernel, 1 = first-generation kernel; None = the library default."""
     _need_cuda(qkv)
     assert qkv.dtype == torch.float16 and qkv.shape == (n_views * seq, 3 * heads * 64)
     out = torch.empty((n_views * seq, heads * 64), dtype=torch.float16, device=qkv.device)
-    check(load().pg_attention_f16(ptr(qkv), ptr(out), n_views, seq, heads, current_stream_ptr()), "pg_attention_f16")
+    if variant is None:
+        check(load().pg_attention_f16(ptr(qkv), ptr(out), n_views, seq, heads, current_stream_ptr()), "pg_attention_f16")
+    else:
+        check(load().pg_attention_f16_variant(ptr(qkv), ptr(out), None, n_views, seq, heads, variant, poly,
+                                              current_stream_ptr()), "pg_attention_f16_variant")
     return out
 
 

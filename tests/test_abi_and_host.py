@@ -23,7 +23,8 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/pigeon_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.pg_abi_version() == 1
+    m = re.search(r"#define PG_ABI_VERSION (\d+)", header)
+    assert m and lib.pg_abi_version() == int(m.group(1)) == _lib.ABI_VERSION
 
 
 def test_no_gpu_fails_loudly():

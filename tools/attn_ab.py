@@ -1,4 +1,10 @@
-"""A/B of the attention tilings on one box: same inputs, alternating variants."""
+"""Correctness + A/B timing of the attention kernels on one box.
+
+    python tools/attn_ab.py check            # every variant vs a torch fp32 softmax at several geometries (exit 1 on mismatch)
+    python tools/attn_ab.py time [views]     # alternating timings of the variants on the same inputs (L2 flushed)
+
+Variants: (0, p) = pair kernel with p eighths of the exponentials on the FMA pipe, (1, 0) = first-generation kernel.
+"""
 import os
 import sys
 
@@ -8,12 +14,57 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pigeon_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda:0")
-flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-views = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-qkv = torch.randn(views * 577, 3072, device=dev).half()
+VARIANTS = [(1, 0), (0, 0), (0, 1), (0, 2), (0, 3)]
+
+
+def reference(qkv, n_views, seq, heads):
+    x = qkv.float().view(n_views, seq, 3, heads, 64)
+    q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    att = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1)
+    return (att @ v).permute(0, 2, 1, 3).reshape(n_views * seq, heads * 64)
+
+
+def check():
+    bad = 0
+    geoms = [(1, 128, 1), (1, 64, 2), (2, 577, 2), (3, 200, 1), (1, 577, 16), (2, 65, 1), (1, 129, 1), (1, 17, 4),
+             (3, 577, 3), (2, 256, 5), (40, 577, 16)]
+    for (n_views, seq, heads) in geoms:
+        g = torch.Generator(device="cpu").manual_seed(seq * 3 + heads)
+        qkv = (torch.randn(n_views * seq, 3 * heads * 64, generator=g) * 1.5).half().to(dev)
+        ref = reference(qkv, n_views, seq, heads)
+        for (var, poly) in VARIANTS:
+            if var == 1 and poly:
+                continue
+            out = ops.attention_f16(qkv, n_views, seq, heads, variant=var, poly=poly)
+            torch.cuda.synchronize()
+            err = ((out.float() - ref).norm() / ref.norm()).item()
+            ok = err < 2e-3 and bool(torch.isfinite(out.float()).all())
+            bad += not ok
+            print(f"geom {(n_views, seq, heads)} variant {var} poly {poly}: rel err {err:.2e} {'ok' if ok else 'FAIL'}", flush=True)
+    # growing logits: the exact-maximum / rescale path
+    n_views, seq, heads = 2, 577, 2
+    g = torch.Generator(device="cpu").manual_seed(77)
+    x = torch.randn(n_views, seq, 3, heads, 64, generator=g)
+    x[:, :, 1] *= (0.25 + 6.0 * torch.arange(seq) / seq).view(1, seq, 1, 1)
+    qkv = x.reshape(n_views * seq, 3 * heads * 64).half().to(dev)
+    ref = reference(qkv, n_views, seq, heads)
+    for (var, poly) in VARIANTS:
+        out = ops.attention_f16(qkv, n_views, seq, heads, variant=var, poly=poly)
+        err = ((out.float() - ref).norm() / ref.norm()).item()
+        ok = err < 2e-3 and bool(torch.isfinite(out.float()).all())
+        bad += not ok
+        print(f"growing logits variant {var} poly {poly}: rel err {err:.2e} {'ok' if ok else 'FAIL'}", flush=True)
+    # run-to-run determinism of the default variant
+    a = ops.attention_f16(qkv, n_views, seq, heads, variant=0)
+    b = ops.attention_f16(qkv, n_views, seq, heads, variant=0)
+    if not torch.equal(a, b):
+        bad += 1
+        print("pair kernel is not run-to-run deterministic: FAIL")
+    return bad
 
 
 def timeit(fn, iters=10, warm=3):
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     for _ in range(warm):
         fn()
     ts = []
@@ -26,14 +77,17 @@ def timeit(fn, iters=10, warm=3):
     return sorted(ts)[len(ts) // 2]
 
 
-ref = None
-for rep in range(2):
-    for var, poly in (("64", ""), ("32", ""), ("64s", ""), ("64h", ""), ("32c", "")):
-        os.environ["PG_ATTN_VARIANT"] = var
-        os.environ["PG_ATTN_POLY"] = poly
-        out = ops.attention_f16(qkv, views, 577, 16)
-        if ref is None:
-            ref = out.clone()
-        ms = timeit(lambda: ops.attention_f16(qkv, views, 577, 16))
-        err = ((out.float() - ref.float()).norm() / ref.float().norm()).item()
-        print(f"variant KV={var} poly={poly or 0}: {ms:.4f} ms  ({4.0 * 577 * 577 * 64 * 16 * views / ms / 1e9:.0f} TF/s)  rel diff vs KV=64: {err:.2e}", flush=True)
+def time_variants(views):
+    qkv = torch.randn(views * 577, 3072, device=dev).half()
+    flops = 4.0 * 577 * 577 * 64 * 16 * views
+    for rep in range(2):
+        for (var, poly) in VARIANTS:
+            ms = timeit(lambda: ops.attention_f16(qkv, views, 577, 16, variant=var, poly=poly))
+            print(f"views {views} variant {var} poly {poly}: {ms:.4f} ms  {flops / ms / 1e9:.0f} TF/s", flush=True)
+
+
+if __name__ == "__main__":
+    mode = sys.argv[1] if len(sys.argv) > 1 else "check"
+    if mode == "check":
+        sys.exit(1 if check() else 0)
+    time_variants(int(sys.argv[2]) if len(sys.argv) > 2 else 128)
