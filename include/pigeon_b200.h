@@ -57,6 +57,13 @@ typedef struct pg_vit_layer {
   const float* ln2_g; const float* ln2_b;       /* layer_norm2 [hidden] */
   const void* w_fc1; const float* b_fc1;        /* mlp.fc1 [intermediate, hidden] */
   const void* w_fc2; const float* b_fc2;        /* mlp.fc2 [hidden, intermediate] */
+  /* Optional (all six or none; NULL = pg_vit_forward runs the LayerNorm kernels): LayerNorm folded into the GEMM after it.
+   *   w_*_ln   fp16 = W * gamma (column-wise), same shape as W;   cs_* f32 [out] = row sums of the fp16 values of w_*_ln;
+   *   b_*_ln   f32 [out] = b + W beta.
+   * With them the forward feeds the RAW fp16 residual row to the tensor cores and applies
+   * rstd * (acc - mu * cs) + b_ln in the epilogue; (mu, rstd) come from moments the previous epilogue left behind. */
+  const void* w_qkv_ln; const float* b_qkv_ln; const float* cs_qkv;
+  const void* w_fc1_ln; const float* b_fc1_ln; const float* cs_fc1;
 } pg_vit_layer;
 
 typedef struct pg_vit_weights {
@@ -214,6 +221,9 @@ typedef struct pg_refiner_bank {
 } pg_refiner_bank;
 
 size_t pg_refiner_workspace_bytes(int64_t B, int32_t topk, int32_t D, int32_t num_cells);
+/* Measurement aid: scan schedule of pg_refiner_forward for this process: 0 = automatic (cell-major when geocells are shared
+ * by >= 2 (query, candidate) pairs on average), 1 = query-major, 2 = cell-major.  Same results either way. */
+int pg_refiner_set_schedule(int32_t mode);
 /* emb f32 [B, V, D]; init_lnglat f64 [B, 2]; cand_idx i64 [B, cand_stride]; cand_prob f32 [B, cand_stride];
  * only the first `topk` candidates of each row are used (topk <= cand_stride).
  *   -> out_lnglat f32 [B, 2], out_cell i64 [B]   (ProtoRefiner.forward's preds_LLH, preds_geocell)

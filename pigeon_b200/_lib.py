@@ -29,7 +29,8 @@ class Image(C.Structure):
 
 class VitLayer(C.Structure):
     _fields_ = [(n, c_void_p) for n in ("ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_g", "ln2_b",
-                                        "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
+                                        "w_fc1", "b_fc1", "w_fc2", "b_fc2", "w_qkv_ln", "b_qkv_ln", "cs_qkv",
+                                        "w_fc1_ln", "b_fc1_ln", "cs_fc1")]
 
 
 class VitSavedLayer(C.Structure):
@@ -107,6 +108,7 @@ SIGNATURES = {
     "pg_refiner_forward": (c_int32, [C.POINTER(RefinerBank), c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
                                      c_int32, c_int32, c_float, c_double, c_void_p, c_size_t, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pg_refiner_set_schedule": (c_int32, [c_int32]),
     "pg_bank_build": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "pg_profile_begin": (None, []),
     "pg_profile_end": (c_int32, []),

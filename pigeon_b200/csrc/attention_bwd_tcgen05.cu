@@ -400,10 +400,14 @@ int run_backward(const void* qkv_f16, const void* qkv_bf16, const void* d_out_bf
 int attention_backward(const void* qkv_f16, const void* qkv_bf16, const void* d_out_bf16, const float* lse2,
                        const float* delta, void* dqkv_bf16, int n_views, int seq, int heads, cudaStream_t stream) {
   if (n_views <= 0) return 0;
-  const char* v = getenv("PG_ATTN_BWD");   // A/B switch: "64" = single-buffered 64-wide blocks, 4 row warps; "32" = two 32-wide buffers
-  if (v && v[0] == '6')
+  // A/B switch, read once per process: "64" = single-buffered 64-wide blocks, 4 row warps; "32" = two 32-wide buffers
+  static const int variant = [] {
+    const char* v = getenv("PG_ATTN_BWD");
+    return (v && v[0] == '6') ? 64 : (v && v[0] == '3') ? 32 : 0;
+  }();
+  if (variant == 64)
     return run_backward<BwdCfg<64, 1>>(qkv_f16, qkv_bf16, d_out_bf16, lse2, delta, dqkv_bf16, n_views, seq, heads, stream);
-  if (v && v[0] == '3')
+  if (variant == 32)
     return run_backward<BwdCfg<32, 2>>(qkv_f16, qkv_bf16, d_out_bf16, lse2, delta, dqkv_bf16, n_views, seq, heads, stream);
   // default: 64-wide blocks, EIGHT row warps (two per TMEM lane quarter) -> 16 row warps per SM with two CTAs
   return run_backward<BwdCfg<64, 1, 8>>(qkv_f16, qkv_bf16, d_out_bf16, lse2, delta, dqkv_bf16, n_views, seq, heads, stream);

@@ -8,7 +8,7 @@
 // Why a second kernel: the first one (attention_tcgen05.cu) issued S = Q K^T as 128 x 32 x 16 MMAs with both operands in
 // shared memory (320 B/clk of operand reads against the 128 B/clk the SM delivers), synchronised softmax and MMA warps every
 // 32 columns and was MUFU-bound at one ex2 per logit; ncu put it at 23 % tensor pipe.  This one:
-//   * persistent, ONE CTA per SM, 448 threads; a CTA works on "jobs" of TWO 128-row query tiles (slots 0 / 1) that ping-pong:
+//   * persistent, ONE CTA per SM, 512 threads; a CTA works on "jobs" of TWO 128-row query tiles (slots 0 / 1) that ping-pong:
 //     while the softmax warps of one slot work, the tensor pipe serves the other.  Two tiles of the same (view, head) share one
 //     K/V stream; the odd last tiles (577 = 4 * 128 + 65) of two neighbouring heads are paired with separate streams.
 //   * KV blocks of 128: S_i = Q_i K_j^T is 4 MMAs of 128 x 128 x 16, P_i V_j 8 MMAs of 128 x 64 x 16; Q lives in TENSOR MEMORY
@@ -23,13 +23,14 @@
 //
 // TMEM columns: S0 [0,128) S1 [128,256) (P_i aliases the first 64 columns of S_i as packed fp16) O0 [256,320) O1 [320,384)
 // Q0 [384,416) Q1 [416,448).
-// Warps: 0-3 softmax slot 0, 4-7 softmax slot 1, 8-11 epilogue, 12 TMA producer, 13 TMEM allocator + MMA issuer.
+// Warps: 0-3 softmax slot 0, 4-7 softmax slot 1, 8-11 epilogue, 12 TMA producer, 13 TMEM allocator + MMA issuer, 14-15 idle.
 #include "attention.h"
 #include "prof.h"
 #include "ptx.cuh"
 #include "tma_host.h"
 
 #include <atomic>
+#include <type_traits>
 
 namespace pg {
 
@@ -39,12 +40,11 @@ constexpr int kHeadDim = 64;
 constexpr int kBlock = 128;                            // query rows per tile and kv rows per block
 constexpr int kTileBytes = kBlock * kHeadDim * 2;      // 16 KB: one Q, K or V tile
 constexpr int kSlots = 8;                              // K/V ring
-constexpr int kThreads = 448;
+constexpr int kThreads = 512;                        // 16 warps: setmaxnreg is a per-warpgroup (4 warps) operation
 constexpr int kWarpEpi = 8, kWarpTma = 12, kWarpMma = 13;
 constexpr uint32_t kColS = 0, kColO = 256, kColQ = 384;
 constexpr int kTmemCols = 512;
 constexpr float kSumLimit = 32768.f;                   // block sum that triggers the exact-maximum path (P < 2^15)
-constexpr float kRescaleThreshold = 8.0f;              // log2 domain, ragged last block
 
 struct Bars {
   uint64_t kv_full[kSlots], kv_empty[kSlots];
@@ -193,6 +193,34 @@ __device__ __forceinline__ void exp_chunk(const uint32_t* r, uint32_t* pk, float
   }
 }
 
+// Ragged chunk: only the first `rem` of the 16 columns are valid keys; P = 0 for the others.
+__device__ __forceinline__ void exp_chunk_masked(const uint32_t* r, uint32_t* pk, int rem, float c, float nmc, float& acc) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float p0 = (2 * k < rem) ? ex2(fmaf(__uint_as_float(r[2 * k]), c, nmc)) : 0.f;
+    const float p1 = (2 * k + 1 < rem) ? ex2(fmaf(__uint_as_float(r[2 * k + 1]), c, nmc)) : 0.f;
+    acc += p0 + p1;
+    pk[k] = pack_half2(p0, p1);
+  }
+}
+
+// One lane of a converged warp (the single-thread roles run warp-uniform so that descriptors and addresses stay in uniform
+// registers; only the tcgen05 / TMA instructions themselves are issued under this predicate).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(p));
+  return p != 0;
+}
+
+template <int I>
+using Slot = std::integral_constant<int, I>;
+
 template <int POLY>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairArgs args) {
@@ -240,32 +268,44 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_ptr;
 
-  // register budget: 448 threads start with 128 each; the softmax warps hold a whole row of P (64 packed registers) plus
-  // the logits in flight and take the share the single-thread roles do not need (8*160 + 4*96 + 56 + 72 = 14*128 per lane).
-  if (warp == kWarpTma) {
-    // ---------------------------------------------------------------- TMA producer
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (lane == 0 && blockIdx.x < n_jobs) {
+  // register budget: 512 threads start with 128 each; the softmax warps hold a whole row of P (64 packed registers) plus
+  // the logits in flight and take the share the other roles do not need (8*168 + 4*96 + 4*80 = 16*128 per lane).
+  // setmaxnreg must be executed with the SAME value by all four warps of a warpgroup: warps 12-15 (TMA, MMA, two idle)
+  // form one.
+  if (warp >= kWarpTma) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+  if (warp > kWarpMma) {
+    // idle warps of the last warpgroup
+  } else if (warp == kWarpTma) {
+    // ---------------------------------------------------------------- TMA producer (warp-uniform, one elected lane issues)
+    if (blockIdx.x < n_jobs) {
       int slot = 0;
       uint32_t phase = 0;
-      uint32_t nq[2] = {0, 0};
+      uint32_t nq0 = 0, nq1 = 0;
       auto load_kv = [&](int col, int row) {
         mbar_wait(&bars->kv_empty[slot], phase ^ 1);
-        mbar_arrive_expect_tx(&bars->kv_full[slot], kTileBytes);
-        tma_load_2d(smem_kv + slot * kTileBytes, &tmap_qkv, &bars->kv_full[slot], col, row);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bars->kv_full[slot], kTileBytes);
+          tma_load_2d(smem_kv + slot * kTileBytes, &tmap_qkv, &bars->kv_full[slot], col, row);
+        }
+        __syncwarp();
         if (++slot == kSlots) { slot = 0; phase ^= 1; }
       };
-      auto load_q = [&](int i, const Job& jb) {
-        mbar_wait(&bars->qs_empty[i], (nq[i] & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars->qs_full[i], kTileBytes);
-        tma_load_2d(smem_q + i * kTileBytes, &tmap_qkv, &bars->qs_full[i], (i ? jb.h1 : jb.h0) * kHeadDim,
-                    jb.view * S + (i ? jb.t1 : jb.t0) * kBlock);
-        ++nq[i];
+      auto load_q = [&](auto I_, const Job& jb) {
+        constexpr int I = decltype(I_)::value;
+        uint32_t& nq = I ? nq1 : nq0;
+        mbar_wait(&bars->qs_empty[I], (nq & 1) ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bars->qs_full[I], kTileBytes);
+          tma_load_2d(smem_q + I * kTileBytes, &tmap_qkv, &bars->qs_full[I], (I ? jb.h1 : jb.h0) * kHeadDim,
+                      jb.view * S + (I ? jb.t1 : jb.t0) * kBlock);
+        }
+        __syncwarp();
+        ++nq;
       };
       {
         const Job j0 = decode_job(blockIdx.x, args);
-        load_q(0, j0);
-        if (j0.a1) load_q(1, j0);
+        load_q(Slot<0>{}, j0);
+        if (j0.a1) load_q(Slot<1>{}, j0);
       }
       for (int job = blockIdx.x; job < n_jobs; job += stride) {
         const Job jb = decode_job(job, args);
@@ -276,8 +316,8 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
         auto next_q = [&]() {   // the next job's Q tiles, once this job's first blocks are on their way
           if (!has_next) return;
           const Job jn = decode_job(job + stride, args);
-          load_q(0, jn);
-          if (jn.a1) load_q(1, jn);
+          load_q(Slot<0>{}, jn);
+          if (jn.a1) load_q(Slot<1>{}, jn);
         };
         // order = the MMA warp's acquisition order
         if (jb.shared) {
@@ -303,115 +343,135 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
       }
     }
   } else if (warp == kWarpMma) {
-    // ---------------------------------------------------------------- MMA issuer
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-    if (lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer (warp-uniform, one elected lane issues)
+    {
       int slot = 0;
       uint32_t phase = 0;
-      uint32_t n_p[2] = {0, 0};     // p_ready phases consumed
-      uint32_t n_j[2] = {0, 0};     // jobs started per slot
-      const uint32_t kv_base = smem_u32(smem_kv);
+      uint32_t n_p0 = 0, n_p1 = 0;     // p_ready phases consumed
+      uint32_t n_j0 = 0, n_j1 = 0;     // jobs started per slot
+      // descriptor of ring slot s, k-step k: base + s * (16 KB >> 4) + k * (32 B >> 4) for K (K-major rows of 128 B),
+      // base + s * 1024 + k * (16 rows * 128 B >> 4) for V (MN-major: row = kv index)
+      const uint64_t k_desc0 = make_smem_desc(smem_u32(smem_kv), 16, 1024, kLayoutSw128);
+      const uint64_t v_desc0 = make_smem_desc(smem_u32(smem_kv), 1024, 1024, kLayoutSw128);
+      const uint32_t idesc_s = make_idesc_f16(kBlock, kBlock, 0, 0);
+      const uint32_t idesc_s_last = make_idesc_f16(kBlock, last_n, 0, 0);
+      const uint32_t idesc_pv = make_idesc_f16(kBlock, kHeadDim, 0, 1);    // B (= V) is MN-major
       auto acquire = [&]() -> int {
         mbar_wait(&bars->kv_full[slot], phase);
         tc_fence_after();
-        const int s = slot;
+        const int sl = slot;
         if (++slot == kSlots) { slot = 0; phase ^= 1; }
-        return s;
+        return sl;
       };
-      auto release = [&](int s) { tc_commit(&bars->kv_empty[s]); };
-      auto issue_s = [&](int i, int s, int j) {
-        const int n = (j == nb - 1) ? last_n : kBlock;
-        const uint32_t idesc = make_idesc_f16(kBlock, n, 0, 0);
-        const uint32_t k_addr = kv_base + s * kTileBytes;
+      auto release = [&](int sl) {
+        if (elect_one()) tc_commit(&bars->kv_empty[sl]);
+        __syncwarp();
+      };
+      auto issue_s = [&](auto I_, int sl, int j) {
+        constexpr int I = decltype(I_)::value;
+        if (elect_one()) {
+          const uint32_t idesc = (j == nb - 1) ? idesc_s_last : idesc_s;
+          const uint64_t kd = k_desc0 + (uint64_t)(sl * (kTileBytes >> 4));
 #pragma unroll
-        for (int k = 0; k < kHeadDim / 16; ++k)
-          umma_ts(tmem_base + kColS + 128 * i, tmem_base + kColQ + 32 * i + 8 * k,
-                  make_smem_desc(k_addr + k * 32, 16, 1024, kLayoutSw128), idesc, k != 0);
-        tc_commit(&bars->s_full[i]);
+          for (int k = 0; k < kHeadDim / 16; ++k)
+            umma_ts(tmem_base + kColS + 128 * I, tmem_base + kColQ + 32 * I + 8 * k, kd + 2 * k, idesc, k != 0);
+          tc_commit(&bars->s_full[I]);
+        }
+        __syncwarp();
       };
-      auto issue_pv = [&](int i, int s, int j) {
-        const int kext = (j == nb - 1) ? last_n : kBlock;                 // contraction extent = kv rows of this block
-        const uint32_t idesc = make_idesc_f16(kBlock, kHeadDim, 0, 1);    // B (= V) is MN-major
-        const uint32_t v_addr = kv_base + s * kTileBytes;
-        for (int k = 0; k < kext / 16; ++k)
-          umma_ts(tmem_base + kColO + 64 * i, tmem_base + kColS + 128 * i + 8 * k,
-                  make_smem_desc(v_addr + k * 2048, 1024, 1024, kLayoutSw128), idesc, (j | k) != 0);
-        tc_commit(&bars->pv_done[i]);
-        if (j == nb - 1) tc_commit(&bars->o_full[i]);
+      auto issue_pv = [&](auto I_, int sl, int j) {
+        constexpr int I = decltype(I_)::value;
+        if (elect_one()) {
+          const uint64_t vd = v_desc0 + (uint64_t)(sl * (kTileBytes >> 4));
+          const uint32_t d = tmem_base + kColO + 64 * I, a = tmem_base + kColS + 128 * I;
+          umma_ts(d, a, vd, idesc_pv, j != 0);
+          if (j == nb - 1) {
+            for (int k = 1; k < last_n / 16; ++k) umma_ts(d, a + 8 * k, vd + 128 * k, idesc_pv, 1);
+          } else {
+#pragma unroll
+            for (int k = 1; k < kBlock / 16; ++k) umma_ts(d, a + 8 * k, vd + 128 * k, idesc_pv, 1);
+          }
+          tc_commit(&bars->pv_done[I]);
+          if (j == nb - 1) tc_commit(&bars->o_full[I]);
+        }
+        __syncwarp();
       };
-      auto wait_p = [&](int i, int j) {
-        mbar_wait(&bars->p_ready[i], n_p[i] & 1);
-        ++n_p[i];
-        if (j == 0) mbar_wait(&bars->o_free[i], (n_j[i] & 1) ^ 1);   // the previous job's O_i was read out
+      auto wait_p = [&](auto I_, int j) {
+        constexpr int I = decltype(I_)::value;
+        uint32_t& n_p = I ? n_p1 : n_p0;
+        const uint32_t n_j = I ? n_j1 : n_j0;
+        mbar_wait(&bars->p_ready[I], n_p & 1);
+        ++n_p;
+        if (j == 0) mbar_wait(&bars->o_free[I], (n_j & 1) ^ 1);   // the previous job's O_i was read out
         tc_fence_after();
       };
 
       for (int job = blockIdx.x; job < n_jobs; job += stride) {
         const Job jb = decode_job(job, args);
-        mbar_wait(&bars->q_ready[0], n_j[0] & 1);
-        if (jb.a1) mbar_wait(&bars->q_ready[1], n_j[1] & 1);
+        mbar_wait(&bars->q_ready[0], n_j0 & 1);
+        if (jb.a1) mbar_wait(&bars->q_ready[1], n_j1 & 1);
         tc_fence_after();
         if (jb.shared) {
           const int ks = acquire();
-          issue_s(0, ks, 0);
-          issue_s(1, ks, 0);
+          issue_s(Slot<0>{}, ks, 0);
+          issue_s(Slot<1>{}, ks, 0);
           release(ks);
           for (int j = 0; j < nb; ++j) {
-            wait_p(0, j);
+            wait_p(Slot<0>{}, j);
             const int vs = acquire();
-            issue_pv(0, vs, j);
+            issue_pv(Slot<0>{}, vs, j);
             int kn = 0;
             if (j + 1 < nb) {
               kn = acquire();
-              issue_s(0, kn, j + 1);
+              issue_s(Slot<0>{}, kn, j + 1);
             }
-            wait_p(1, j);
-            issue_pv(1, vs, j);
+            wait_p(Slot<1>{}, j);
+            issue_pv(Slot<1>{}, vs, j);
             release(vs);
             if (j + 1 < nb) {
-              issue_s(1, kn, j + 1);
+              issue_s(Slot<1>{}, kn, j + 1);
               release(kn);
             }
           }
         } else {
-          int s = acquire();
-          issue_s(0, s, 0);
-          release(s);
+          int sl = acquire();
+          issue_s(Slot<0>{}, sl, 0);
+          release(sl);
           if (jb.a1) {
-            s = acquire();
-            issue_s(1, s, 0);
-            release(s);
+            sl = acquire();
+            issue_s(Slot<1>{}, sl, 0);
+            release(sl);
           }
           for (int j = 0; j < nb; ++j) {
-            wait_p(0, j);
-            s = acquire();
-            issue_pv(0, s, j);
-            release(s);
+            wait_p(Slot<0>{}, j);
+            sl = acquire();
+            issue_pv(Slot<0>{}, sl, j);
+            release(sl);
             if (j + 1 < nb) {
-              s = acquire();
-              issue_s(0, s, j + 1);
-              release(s);
+              sl = acquire();
+              issue_s(Slot<0>{}, sl, j + 1);
+              release(sl);
             }
             if (jb.a1) {
-              wait_p(1, j);
-              s = acquire();
-              issue_pv(1, s, j);
-              release(s);
+              wait_p(Slot<1>{}, j);
+              sl = acquire();
+              issue_pv(Slot<1>{}, sl, j);
+              release(sl);
               if (j + 1 < nb) {
-                s = acquire();
-                issue_s(1, s, j + 1);
-                release(s);
+                sl = acquire();
+                issue_s(Slot<1>{}, sl, j + 1);
+                release(sl);
               }
             }
           }
         }
-        ++n_j[0];
-        if (jb.a1) ++n_j[1];
+        ++n_j0;
+        if (jb.a1) ++n_j1;
       }
     }
   } else if (warp < kWarpEpi) {
     // ---------------------------------------------------------------- softmax warps: thread = query row = TMEM lane
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     const int i = warp >> 2;        // slot
     const int wq = warp & 3;        // lane quarter
     const int row = wq * 32 + lane;
@@ -484,99 +544,87 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
           copy_q();
           q_done = true;
         }
-        const bool tail = (j == nb - 1) && (last_valid < kBlock);
         if (!warp_active) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->p_ready[i]);
           ++n_blk;
           continue;
         }
-
-        if (!tail) {
-          uint32_t pk[64];
-          float bs;
-          bool do_max = (j == 0);
-          for (;;) {
-            if (do_max) {
-              float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
+        // valid key columns of this block: nfull whole 16-column chunks + `rem` columns of one ragged chunk (last block only)
+        const int ncols = (j == nb - 1) ? last_valid : kBlock;
+        const int nfull = ncols >> 4, rem = ncols & 15;
+        uint32_t pk[64], pkm[8];
+        float bs;
+        bool do_max = (j == 0);
+        for (;;) {
+          if (do_max) {   // exact row maximum of the block (first block of a job, or a block whose sum overflowed)
+            float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
 #pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                uint32_t r[32];
-                tmem_ld32(s_tmem + 32 * h, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int x = 0; x < 32; x += 8) {
-                  b0 = fmax3(b0, __uint_as_float(r[x]), __uint_as_float(r[x + 1]));
-                  b1 = fmax3(b1, __uint_as_float(r[x + 2]), __uint_as_float(r[x + 3]));
-                  b2 = fmax3(b2, __uint_as_float(r[x + 4]), __uint_as_float(r[x + 5]));
-                  b3 = fmax3(b3, __uint_as_float(r[x + 6]), __uint_as_float(r[x + 7]));
-                }
+            for (int ch = 0; ch < 8; ++ch) {
+              if (ch < nfull) {
+                uint32_t r[16];
+                tmem_ld16p(s_tmem + 16 * ch, r);
+                tmem_ld_wait16(r);
+                b0 = fmax3(b0, __uint_as_float(r[0]), __uint_as_float(r[1]));
+                b1 = fmax3(b1, __uint_as_float(r[2]), __uint_as_float(r[3]));
+                b2 = fmax3(b2, __uint_as_float(r[4]), __uint_as_float(r[5]));
+                b3 = fmax3(b3, __uint_as_float(r[6]), __uint_as_float(r[7]));
+                b0 = fmax3(b0, __uint_as_float(r[8]), __uint_as_float(r[9]));
+                b1 = fmax3(b1, __uint_as_float(r[10]), __uint_as_float(r[11]));
+                b2 = fmax3(b2, __uint_as_float(r[12]), __uint_as_float(r[13]));
+                b3 = fmax3(b3, __uint_as_float(r[14]), __uint_as_float(r[15]));
               }
-              const float m_new = fmaxf(fmaxf(m, fmaxf(b0, b1)), fmaxf(b2, b3));
-              if (j > 0) rescale(m_new);
-              m = m_new;
             }
-            const float mc = m * c;
-            const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
-            float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-            uint32_t ra[16], rb[16];
-            tmem_ld16p(s_tmem, ra);
+            if (rem) {
+              uint32_t r[16];
+              tmem_ld16p(s_tmem + 16 * nfull, r);
+              tmem_ld_wait16(r);
 #pragma unroll
-            for (int ch = 0; ch < 8; ch += 2) {
-              tmem_ld_wait16(ra);
-              tmem_ld16p(s_tmem + 16 * (ch + 1), rb);
-              exp_chunk<POLY>(ra, pk + 8 * ch, c2, nmc2, acc0, acc1);
-              tmem_ld_wait16(rb);
-              if (ch + 2 < 8) tmem_ld16p(s_tmem + 16 * (ch + 2), ra);
-              exp_chunk<POLY>(rb, pk + 8 * (ch + 1), c2, nmc2, acc0, acc1);
+              for (int x = 0; x < 16; ++x)
+                if (x < rem) b0 = fmaxf(b0, __uint_as_float(r[x]));
             }
-            bs = (acc0.x + acc0.y) + (acc1.x + acc1.y);
-            if (!do_max && __any_sync(0xffffffffu, !(bs < kSumLimit))) {   // some P may not fit fp16: exact path
-              do_max = true;
-              continue;
-            }
-            break;
-          }
-          l += bs;
-          // P (packed fp16) over the first 64 columns of S_i: every logit of the block is already in registers
-#pragma unroll
-          for (int h = 0; h < 4; ++h) tmem_st16p(s_tmem + 16 * h, pk + 16 * h);
-        } else {
-          // ragged last block: masked, exact maximum with lazy rescale (P <= 2^8)
-          float bm = -INFINITY;
-          for (int c0 = 0; c0 < last_n; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld16p(s_tmem + c0, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int x = 0; x < 16; ++x)
-              if (c0 + x < last_valid) bm = fmaxf(bm, __uint_as_float(r[x]));
-          }
-          const float m_new = fmaxf(m, bm);
-          if (j == 0) {
-            m = m_new;
-          } else if (__any_sync(0xffffffffu, (m_new - m) * c > kRescaleThreshold)) {
-            rescale(m_new);
+            const float m_new = fmaxf(fmaxf(m, fmaxf(b0, b1)), fmaxf(b2, b3));
+            if (j > 0) rescale(m_new);
             m = m_new;
           }
           const float mc = m * c;
-          float l0 = 0.f, l1 = 0.f;
-          for (int c0 = 0; c0 < last_n; c0 += 16) {   // reload the chunk (P of earlier chunks never reaches it)
-            uint32_t r[16], pk[8];
-            tmem_ld16p(s_tmem + c0, r);
-            tmem_ld_wait();
+          const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
+          float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+          uint32_t ra[16], rb[16];
+          if (nfull > 0) tmem_ld16p(s_tmem, ra);
 #pragma unroll
-            for (int x = 0; x < 16; x += 2) {
-              const float p0 = (c0 + x < last_valid) ? ex2(fmaf(__uint_as_float(r[x]), c, -mc)) : 0.f;
-              const float p1 = (c0 + x + 1 < last_valid) ? ex2(fmaf(__uint_as_float(r[x + 1]), c, -mc)) : 0.f;
-              l0 += p0;
-              l1 += p1;
-              pk[x >> 1] = pack_half2(p0, p1);
+          for (int ch = 0; ch < 8; ch += 2) {   // software-pipelined: the next chunk's load is in flight during the arithmetic
+            if (ch < nfull) {
+              tmem_ld_wait16(ra);
+              if (ch + 1 < nfull) tmem_ld16p(s_tmem + 16 * (ch + 1), rb);
+              exp_chunk<POLY>(ra, pk + 8 * ch, c2, nmc2, acc0, acc1);
             }
-            tmem_st8p(s_tmem + (c0 >> 1), pk);
+            if (ch + 1 < nfull) {
+              tmem_ld_wait16(rb);
+              if (ch + 2 < nfull) tmem_ld16p(s_tmem + 16 * (ch + 2), ra);
+              exp_chunk<POLY>(rb, pk + 8 * (ch + 1), c2, nmc2, acc0, acc1);
+            }
           }
-          l += l0 + l1;
+          bs = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+          if (rem) {
+            tmem_ld16p(s_tmem + 16 * nfull, ra);
+            tmem_ld_wait16(ra);
+            exp_chunk_masked(ra, pkm, rem, c, -mc, bs);
+          }
+          if (!do_max && __any_sync(0xffffffffu, !(bs < kSumLimit))) {   // some P may not fit fp16: exact path
+            do_max = true;
+            continue;
+          }
+          break;
         }
+        l += bs;
+        // P (packed fp16) over the first columns of S_i: every logit of the block is already in registers
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          if (2 * h + 2 <= nfull) tmem_st16p(s_tmem + 16 * h, pk + 16 * h);
+          else if (2 * h + 1 <= nfull) tmem_st8p(s_tmem + 16 * h, pk + 16 * h);
+        }
+        if (rem) tmem_st8p(s_tmem + 8 * nfull, pkm);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -648,7 +696,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
   }
 }
 
-std::atomic<int> g_attr_set[64][4];   // per device and kernel variant: dynamic shared memory opt-in done
+std::atomic<int> g_attr_set[64][5];   // per device and kernel variant: dynamic shared memory opt-in done
 
 template <int POLY>
 int launch_pair(int variant, const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream,
@@ -691,7 +739,7 @@ int launch_pair(int variant, const void* qkv, void* out, int n_views, int seq, i
 
 }  // namespace
 
-// poly: share of the exponentials evaluated on the FMA pipe, in eighths (0, 1, 2, 3 or 4 of every 8 pairs).
+// poly: share of the exponentials evaluated on the FMA pipe, in eighths (0, 1, 2, 3 or 4 of every 8 pairs; other values = 2).
 int attention_pair_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream, float* lse2,
                        int poly) {
   if (n_views <= 0) return 0;
@@ -699,6 +747,7 @@ int attention_pair_f16(const void* qkv, void* out, int n_views, int seq, int hea
     case 0: return launch_pair<0x00>(0, qkv, out, n_views, seq, heads, stream, lse2);
     case 1: return launch_pair<0x08>(1, qkv, out, n_views, seq, heads, stream, lse2);
     case 3: return launch_pair<0x4A>(3, qkv, out, n_views, seq, heads, stream, lse2);
+    case 4: return launch_pair<0xAA>(4, qkv, out, n_views, seq, heads, stream, lse2);
     default: return launch_pair<0x88>(2, qkv, out, n_views, seq, heads, stream, lse2);
   }
 }

@@ -6,6 +6,7 @@
 
 #include <stdlib.h>
 
+#include <atomic>
 #include <new>
 #include <vector>
 
@@ -68,7 +69,14 @@ int pg_vit_create(const pg_vit_config* cfg, const pg_vit_weights* w, pg_vit** ou
 
 void pg_vit_destroy(pg_vit* h) { delete h; }
 
-static size_t vit_carve(const pg_vit* h, int n_views, void* ws, float** x, void** xn, void** u) {
+static bool vit_ln_folded(const pg_vit* h) {
+  for (const pg_vit_layer& L : h->layers)
+    if (!L.w_qkv_ln || !L.b_qkv_ln || !L.cs_qkv || !L.w_fc1_ln || !L.b_fc1_ln || !L.cs_fc1) return false;
+  return true;
+}
+
+static size_t vit_carve(const pg_vit* h, int n_views, void* ws, float** x, void** xn, void** u, void** x16 = nullptr,
+                        float** stats = nullptr) {
   const size_t rows = (size_t)n_views * h->tokens;
   const int wide = h->cfg.intermediate > 3 * h->cfg.hidden ? h->cfg.intermediate : 3 * h->cfg.hidden;
   size_t u_elems = rows * (size_t)wide;
@@ -78,6 +86,12 @@ static size_t vit_carve(const pg_vit* h, int n_views, void* ws, float** x, void*
   *x = reinterpret_cast<float*>(c.take(rows * h->cfg.hidden * sizeof(float)));  // residual stream, fp32
   *xn = c.take(rows * h->cfg.hidden * 2);  // LayerNorm output / attention output (fp16), time-shared
   *u = c.take(u_elems * 2);                // im2col | qkv | fc1 activations (fp16), time-shared
+  if (vit_ln_folded(h)) {                  // LayerNorm folded into the GEMMs: raw fp16 residual row + its moments
+    void* p16 = c.take(rows * h->cfg.hidden * 2);
+    float* st = reinterpret_cast<float*>(c.take(rows * (h->cfg.hidden / 128) * 2 * sizeof(float)));
+    if (x16) *x16 = p16;
+    if (stats) *stats = st;
+  }
   return c.off;
 }
 
@@ -94,8 +108,9 @@ int pg_vit_forward(pg_vit* h, const void* pixels, int32_t pixels_f16, int32_t n_
   const int sms = sm_count();
   if (sms < 0) return 1;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  float* x; void* xn; void* u;
-  const size_t need = vit_carve(h, n_views, workspace, &x, &xn, &u);
+  float* x; void* xn; void* u; void* x16 = nullptr; float* stats = nullptr;
+  const size_t need = vit_carve(h, n_views, workspace, &x, &xn, &u, &x16, &stats);
+  const bool folded = vit_ln_folded(h);
   if (workspace_bytes < need) { set_last_error("pg_vit_forward: workspace %zu < required %zu", workspace_bytes, need); return 1; }
   if (reinterpret_cast<uintptr_t>(workspace) & 255) { set_last_error("pg_vit_forward: workspace must be 256-byte aligned"); return 1; }
   const pg_vit_config& c = h->cfg;
@@ -113,10 +128,42 @@ int pg_vit_forward(pg_vit* h, const void* pixels, int32_t pixels_f16, int32_t n_
     if (gemm_f16(p, sms, stream)) return 1;
   }
   if (embed_preln(x, h->w.class_emb, h->w.pos_emb, h->w.pre_ln_g, h->w.pre_ln_b, rows, h->tokens, c.hidden, c.ln_eps,
-                  sms, stream))
+                  sms, stream, nullptr, folded ? x16 : nullptr, folded ? stats : nullptr))
     return 1;
 
-  for (int l = 0; l < c.layers; ++l) {
+  // LayerNorm folded into the GEMMs either side of it (5 launches per layer, no normalised copy in HBM): the residual
+  // epilogues leave the raw fp16 row and its (sum, sum of squares) behind, the consumers apply rstd * (acc - mu * colsum).
+  for (int l = 0; folded && l < c.layers; ++l) {
+    const pg_vit_layer& L = h->layers[l];
+    GemmProblem p{};
+    p.M = (int)rows; p.N = 3 * c.hidden; p.K = c.hidden;
+    p.a = x16; p.lda = c.hidden; p.w = L.w_qkv_ln; p.ldw = c.hidden;
+    p.out = u; p.ldo = 3 * c.hidden; p.bias = L.b_qkv_ln; p.epi = EPI_F16_LN_BIAS;
+    p.stats = stats; p.colsum = L.cs_qkv; p.ln_eps = c.ln_eps;
+    if (gemm_f16(p, sms, stream)) return 1;
+    if (attention_f16(u, xn, n_views, h->tokens, c.heads, stream)) return 1;
+    p = GemmProblem{};
+    p.M = (int)rows; p.N = c.hidden; p.K = c.hidden;
+    p.a = xn; p.lda = c.hidden; p.w = L.w_o; p.ldw = c.hidden;
+    p.out = x; p.ldo = c.hidden; p.bias = L.b_o; p.epi = EPI_F32_BIAS_RESID_STATS;
+    p.aux = x16; p.stats = stats;
+    if (gemm_f16(p, sms, stream)) return 1;
+    p = GemmProblem{};
+    p.M = (int)rows; p.N = c.intermediate; p.K = c.hidden;
+    p.a = x16; p.lda = c.hidden; p.w = L.w_fc1_ln; p.ldw = c.hidden;
+    p.out = u; p.ldo = c.intermediate; p.bias = L.b_fc1_ln; p.epi = EPI_F16_LN_BIAS_QGELU;
+    p.stats = stats; p.colsum = L.cs_fc1; p.ln_eps = c.ln_eps;
+    if (gemm_f16(p, sms, stream)) return 1;
+    p = GemmProblem{};
+    p.M = (int)rows; p.N = c.hidden; p.K = c.intermediate;
+    p.a = u; p.lda = c.intermediate; p.w = L.w_fc2; p.ldw = c.intermediate;
+    p.out = x; p.ldo = c.hidden; p.bias = L.b_fc2;
+    if (l + 1 < c.layers) { p.epi = EPI_F32_BIAS_RESID_STATS; p.aux = x16; p.stats = stats; }
+    else p.epi = EPI_F32_BIAS_RESID;
+    if (gemm_f16(p, sms, stream)) return 1;
+  }
+
+  for (int l = 0; !folded && l < c.layers; ++l) {
     const pg_vit_layer& L = h->layers[l];
     if (layernorm_f16(x, xn, L.ln1_g, L.ln1_b, rows, c.hidden, c.ln_eps, sms, stream)) return 1;
     GemmProblem p{};
@@ -247,9 +294,24 @@ size_t pg_refiner_workspace_bytes(int64_t B, int32_t topk, int32_t D, int32_t nu
   return c.off;
 }
 
-static bool refiner_query_major_forced() {
-  const char* e = getenv("PG_REFINER_QUERY_MAJOR");  // debugging / A-B switch, read per call
-  return e && e[0] == '1';
+// Scan schedule of pg_refiner_forward: 0 = automatic (cell-major when geocells are shared by >= 2 pairs on average),
+// 1 = query-major, 2 = cell-major.  Process-wide A/B switch (pg_refiner_set_schedule); the environment variable
+// PG_REFINER_QUERY_MAJOR=1 only sets the initial value, once.
+static std::atomic<int> g_refiner_schedule{-1};
+static int refiner_schedule() {
+  int v = g_refiner_schedule.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("PG_REFINER_QUERY_MAJOR");
+    v = (e && e[0] == '1') ? 1 : 0;
+    g_refiner_schedule.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+int pg_refiner_set_schedule(int32_t mode) {
+  if (mode < 0 || mode > 2) { set_last_error("pg_refiner_set_schedule: mode %d not in {0, 1, 2}", mode); return 1; }
+  g_refiner_schedule.store(mode, std::memory_order_relaxed);
+  return 0;
 }
 
 int pg_refiner_forward(const pg_refiner_bank* bank, const float* emb, int64_t B, int32_t V, const double* init_lnglat,
@@ -287,7 +349,8 @@ int pg_refiner_forward(const pg_refiner_bank* bank, const float* emb, int64_t B,
   if (refiner_pool(emb, q, B, V, bank->dim, stream)) return 1;
   // cell-major (each touched prototype segment read once) as soon as cells are shared by several pairs on average;
   // the query-major kernel (one warp per pair) for small batches where the sort would dominate
-  const bool cell_major = !refiner_query_major_forced() && (long)B * topk >= 2L * bank->num_cells;
+  const int sched = refiner_schedule();
+  const bool cell_major = sched == 2 || (sched == 0 && (long)B * topk >= 2L * bank->num_cells);
   if (cell_major) {
     if (refiner_scan_cell_major(rb, q, reinterpret_cast<const long long*>(cand_idx), cand_stride, B, topk, sort_ws, bl,
                                 bll, bp, sms, stream)) return 1;

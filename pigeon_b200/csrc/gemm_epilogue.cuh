@@ -23,6 +23,10 @@ struct GemmArgs {
   void* aux;           // EPI_BF16_DGELU: fc1 pre-activation (fp16, read);  EPI_F16_BIAS_QGELU_SAVE: where to keep it (written)
   int mn_major;        // operands are [K, M] / [K, N] (MN-major UMMA operands), see GemmProblem::mn_major
   uint32_t mn_lbo, mn_sbo;   // descriptor strides of the MN-major operand tiles (bytes)
+  float* stats;         // LayerNorm-folded epilogues: float2 [M, stats_slots] partial (sum, sum of squares) per 128 columns
+  int stats_slots;      // producer: N / 128; consumer: K / 128
+  const float* colsum;  // consumer: fp32 [N] row sums of the folded weight
+  float ln_eps;
 };
 
 __device__ __forceinline__ float quick_gelu(float v) {
@@ -54,7 +58,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
 // update are fetched ONE CHUNK AHEAD so that their HBM latency hides behind the current chunk's work.
 template <int EPI>
 struct EpiTraits {
-  static constexpr bool kF16Out = (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_QGELU || EPI == EPI_F16_BIAS_QGELU_SAVE);
+  static constexpr bool kF16Out = (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_QGELU || EPI == EPI_F16_BIAS_QGELU_SAVE ||
+                                   EPI == EPI_F16_LN_BIAS || EPI == EPI_F16_LN_BIAS_QGELU);
+  static constexpr bool kResid = (EPI == EPI_F32_BIAS_RESID || EPI == EPI_F32_BIAS_RESID_STATS);
+  static constexpr bool kStats = (EPI == EPI_F32_BIAS_RESID_STATS);                           // LayerNorm producer
+  static constexpr bool kLn = (EPI == EPI_F16_LN_BIAS || EPI == EPI_F16_LN_BIAS_QGELU);       // LayerNorm consumer
   static constexpr int CHUNK = kF16Out ? 64 : 32;
   static constexpr int kElt = kF16Out ? 2 : 4;   // EPI_BF16_DGELU stages fp32 (CHUNK 32) and stores 2-byte elements
 };
@@ -78,9 +86,36 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
   constexpr bool kF16Out = EpiTraits<EPI>::kF16Out;
   constexpr int CHUNK = EpiTraits<EPI>::CHUNK;
   constexpr int kElt = EpiTraits<EPI>::kElt;
-  constexpr bool kResid = (EPI == EPI_F32_BIAS_RESID);
+  constexpr bool kResid = EpiTraits<EPI>::kResid;
+  constexpr bool kStats = EpiTraits<EPI>::kStats;
+  constexpr bool kLn = EpiTraits<EPI>::kLn;
   const int sub = lane >> 3, c16 = lane & 7;
   float4 res[8], res_next[8];
+  // LayerNorm consumer: statistics of this thread's A row (= output row) from the producer's per-128-column partials
+  float ln_a = 1.f, ln_b = 0.f;   // out = ln_a * acc + ln_b * colsum + bias
+  if (kLn) {
+    const int row = warp_row0 + lane;
+    float s1 = 0.f, s2 = 0.f;
+    if (row < args.M) {
+      const float2* st = reinterpret_cast<const float2*>(args.stats) + (long)row * args.stats_slots;
+      for (int k = 0; k < args.stats_slots; ++k) {
+        const float2 p = st[k];
+        s1 += p.x;
+        s2 += p.y;
+      }
+    }
+    const float inv_k = 1.0f / (float)args.K;
+    const float mu = s1 * inv_k;
+    const float var = fmaxf(s2 * inv_k - mu * mu, 0.f);
+    ln_a = rsqrtf(var + args.ln_eps);
+    ln_b = -ln_a * mu;
+  }
+  // LayerNorm producer: running (sum, sum of squares) of the fp16-rounded new residual values, per row piece of this lane
+  float st_s[8], st_q[8];
+  if (kStats) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st_s[i] = st_q[i] = 0.f;
+  }
   {
     const int col0 = tile_col0 + c_begin;
     if (kResid && args.vec_ok && col0 + CHUNK <= args.N) load_residual<EPI>(args, res, warp_row0, col0, lane);
@@ -103,6 +138,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
     float v[CHUNK];
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) v[i] = __uint_as_float(r[i]);
+    if (kLn) {   // LayerNorm folded: rstd * acc - rstd * mu * colsum   (N is a multiple of the chunk: checked at launch)
+      const float4* c4 = reinterpret_cast<const float4*>(args.colsum + col0);
+#pragma unroll
+      for (int i = 0; i < CHUNK / 4; ++i) {
+        const float4 cs = __ldg(c4 + i);
+        v[4 * i + 0] = fmaf(ln_a, v[4 * i + 0], ln_b * cs.x);
+        v[4 * i + 1] = fmaf(ln_a, v[4 * i + 1], ln_b * cs.y);
+        v[4 * i + 2] = fmaf(ln_a, v[4 * i + 2], ln_b * cs.z);
+        v[4 * i + 3] = fmaf(ln_a, v[4 * i + 3], ln_b * cs.w);
+      }
+    }
     if (args.bias != nullptr) {
       if (in_n) {
         const float4* b4 = reinterpret_cast<const float4*>(args.bias + col0);
@@ -152,7 +198,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
       }
       __syncwarp();
     }
-    if (EPI == EPI_F16_BIAS_QGELU || kSave) {
+    if (EPI == EPI_F16_BIAS_QGELU || EPI == EPI_F16_LN_BIAS_QGELU || kSave) {
       if (kSave && !fast) {   // ragged tail: scalar stores of the pre-activation
         const int row = warp_row0 + lane;
         if (row < args.M) {
@@ -212,6 +258,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
             val.w = __float_as_uint(__uint_as_float(val.w) + res[i].w);
           }
           *reinterpret_cast<uint4*>(gp) = val;
+          if (kStats) {   // fp16 copy of the new residual values (the next GEMM's A operand) and their moments
+            const __half2 h01 = __floats2half2_rn(__uint_as_float(val.x), __uint_as_float(val.y));
+            const __half2 h23 = __floats2half2_rn(__uint_as_float(val.z), __uint_as_float(val.w));
+            uint2 hv;
+            hv.x = *reinterpret_cast<const uint32_t*>(&h01);
+            hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+            *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(args.aux) + (orow * args.ldo + col0) * 2 + c16 * 8) = hv;
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            st_s[i] += (f01.x + f01.y) + (f23.x + f23.y);
+            st_q[i] += fmaf(f01.x, f01.x, f01.y * f01.y) + fmaf(f23.x, f23.x, f23.y * f23.y);
+          }
         }
       }
     } else {
@@ -247,6 +304,21 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
     if (kResid) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) res[i] = res_next[i];
+    }
+    if (kStats && ((col0 + CHUNK) & 127) == 0) {   // 128 columns complete: combine the 8 lanes of each row, publish
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float a = st_s[i], b = st_q[i];
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        const int grow = warp_row0 + i * 4 + sub;
+        if (c16 == 0 && grow < args.M)
+          reinterpret_cast<float2*>(args.stats)[(long)grow * args.stats_slots + (col0 >> 7)] = make_float2(a, b);
+        st_s[i] = st_q[i] = 0.f;
+      }
     }
   }
 }

@@ -20,6 +20,7 @@
 #include "prof.h"
 #include "tma_host.h"
 
+#include <atomic>
 #include <stdlib.h>
 
 namespace pg {
@@ -175,11 +176,14 @@ int launch(const GemmProblem& p, int num_sms, cudaStream_t stream) {
   if (make_tmap_f16_2d(&ta, p.a, p.M, p.K, p.lda, BLOCK_M, BLOCK_K)) return 1;
   if (make_tmap_f16_2d(&tb, p.w, p.N, p.K, p.ldw, BLOCK_N, BLOCK_K)) return 1;
   auto kern = gemm_f16_kernel<BLOCK_N, EPI>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
+  static std::atomic<int> attr_set[64];   // per template instantiation and device (the attribute is per context)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { set_last_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
-    attr_set = true;
+    attr_set[dev].store(1, std::memory_order_release);
   }
   GemmArgs a;
   a.M = p.M; a.N = p.N; a.K = p.K; a.out = p.out; a.ldo = p.ldo; a.bias = p.bias;
@@ -190,14 +194,27 @@ int launch(const GemmProblem& p, int num_sms, cudaStream_t stream) {
   a.resid = p.resid ? p.resid : reinterpret_cast<const float*>(p.out);
   a.aux = p.aux;
   a.mn_major = 0; a.mn_lbo = a.mn_sbo = 0;
-  if ((EPI == EPI_BF16_DGELU || EPI == EPI_F16_BIAS_QGELU_SAVE) && (!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15))) {
+  if ((EPI == EPI_BF16_DGELU || EPI == EPI_F16_BIAS_QGELU_SAVE || EPI == EPI_F32_BIAS_RESID_STATS) &&
+      (!p.aux || (reinterpret_cast<uintptr_t>(p.aux) & 15))) {
     set_last_error("gemm: this epilogue needs a 16-byte aligned aux buffer"); return 1;
+  }
+  a.stats = p.stats; a.colsum = p.colsum; a.ln_eps = p.ln_eps; a.stats_slots = 0;
+  if (EpiTraits<EPI>::kStats) {
+    if (!p.stats || (p.N % 128) || !a.vec_ok || (p.ldo % 8)) { set_last_error("gemm: LayerNorm-producer epilogue needs stats, N %% 128 == 0 and ldo %% 8 == 0"); return 1; }
+    a.stats_slots = p.N / 128;
+  }
+  if (EpiTraits<EPI>::kLn) {
+    if (!p.stats || !p.colsum || (p.K % 128) || (p.N % 64) || (reinterpret_cast<uintptr_t>(p.colsum) & 15)) {
+      set_last_error("gemm: LayerNorm-consumer epilogue needs stats, a 16-byte aligned colsum, K %% 128 == 0 and N %% 64 == 0"); return 1;
+    }
+    a.stats_slots = p.K / 128;
   }
   const int m_blocks = (p.M + BLOCK_M - 1) / BLOCK_M, n_blocks = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int tiles = m_blocks * n_blocks;
   const int grid = tiles < num_sms ? tiles : num_sms;
   static const char* const kNames[] = {"gemm_f16_bias", "gemm_f16_bias_qgelu", "gemm_f32_bias_resid", "gemm_f32_bias", "gemm_f32_rowmap",
-                                       "gemm_bf16_dgelu", "gemm_f16_bias_qgelu_save"};
+                                       "gemm_bf16_dgelu", "gemm_f16_bias_qgelu_save", "gemm_f32_bias_resid_stats", "gemm_f16_ln_bias",
+                                       "gemm_f16_ln_bias_qgelu"};
   ProfScope prof(kNames[EPI], stream);
   kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, a);
   cudaError_t e = cudaGetLastError();
@@ -241,6 +258,12 @@ int gemm_f16(const GemmProblem& p, int num_sms, cudaStream_t stream) {
     case EPI_BF16_DGELU:     return wide ? launch<256, EPI_BF16_DGELU>(p, num_sms, stream)     : launch<128, EPI_BF16_DGELU>(p, num_sms, stream);
     case EPI_F16_BIAS_QGELU_SAVE:
       return wide ? launch<256, EPI_F16_BIAS_QGELU_SAVE>(p, num_sms, stream) : launch<128, EPI_F16_BIAS_QGELU_SAVE>(p, num_sms, stream);
+    case EPI_F32_BIAS_RESID_STATS:
+      return wide ? launch<256, EPI_F32_BIAS_RESID_STATS>(p, num_sms, stream) : launch<128, EPI_F32_BIAS_RESID_STATS>(p, num_sms, stream);
+    case EPI_F16_LN_BIAS:
+      return wide ? launch<256, EPI_F16_LN_BIAS>(p, num_sms, stream) : launch<128, EPI_F16_LN_BIAS>(p, num_sms, stream);
+    case EPI_F16_LN_BIAS_QGELU:
+      return wide ? launch<256, EPI_F16_LN_BIAS_QGELU>(p, num_sms, stream) : launch<128, EPI_F16_LN_BIAS_QGELU>(p, num_sms, stream);
     default: set_last_error("gemm: unknown epilogue %d", p.epi); return 1;
   }
 }

@@ -109,7 +109,8 @@ __global__ void layernorm_f16_kernel(const float* __restrict__ x, __half* __rest
 template <int NV4>
 __global__ void embed_preln_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
                                    const float* __restrict__ g, const float* __restrict__ b, long rows, int tokens,
-                                   float eps, float* __restrict__ e_out) {
+                                   float eps, float* __restrict__ e_out, __half* __restrict__ x16,
+                                   float2* __restrict__ stats, int stats_slots) {
   constexpr int hidden = NV4 * 128;
   const int lane = threadIdx.x & 31;
   const long warps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -133,6 +134,24 @@ __global__ void embed_preln_kernel(float* __restrict__ x, const float* __restric
     ln_row<NV4>(v, g, b, hidden, eps, lane);
 #pragma unroll
     for (int i = 0; i < NV4; ++i) xr[lane + 32 * i] = v[i];
+    if (x16 != nullptr) {   // LayerNorm-folded tower: fp16 copy of the row (the first GEMM's A operand) and its moments
+      uint2* hr = reinterpret_cast<uint2*>(x16 + row * hidden);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
+        const __half2 lo = __floats2half2_rn(v[i].x, v[i].y), hi = __floats2half2_rn(v[i].z, v[i].w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        hr[lane + 32 * i] = pk;
+        const float2 a = __half22float2(lo), c = __half22float2(hi);
+        s1 += (a.x + a.y) + (c.x + c.y);
+        s2 += fmaf(a.x, a.x, a.y * a.y) + fmaf(c.x, c.x, c.y * c.y);
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane < stats_slots) stats[row * stats_slots + lane] = (lane == 0) ? make_float2(s1, s2) : make_float2(0.f, 0.f);
+    }
   }
 }
 
@@ -219,12 +238,17 @@ int layernorm_f16(const float* x, void* y, const float* gamma, const float* beta
 }
 
 int embed_preln(float* x, const float* cls, const float* pos, const float* gamma, const float* beta, long rows,
-                int tokens, int hidden, float eps, int num_sms, cudaStream_t stream, float* e_out) {
+                int tokens, int hidden, float eps, int num_sms, cudaStream_t stream, float* e_out, void* x16,
+                float* stats) {
   if (hidden % 128) { set_last_error("embed_preln: hidden %d not a multiple of 128", hidden); return 1; }
+  if ((x16 == nullptr) != (stats == nullptr) || hidden / 128 > 32) { set_last_error("embed_preln: x16 and stats go together (hidden <= 4096)"); return 1; }
   const int grid = grid_for(rows, 8, num_sms);
   ProfScope prof("embed_preln", stream);
   PG_DISPATCH_NV4(hidden, (embed_preln_kernel<NV4><<<grid, 256, 0, stream>>>(x, cls, pos, gamma, beta, rows,
-                                                                               tokens, eps, e_out)));
+                                                                               tokens, eps, e_out,
+                                                                               reinterpret_cast<__half*>(x16),
+                                                                               reinterpret_cast<float2*>(stats),
+                                                                               hidden / 128)));
   return check_launch("embed_preln");
 }
 

@@ -60,6 +60,11 @@ def attention_f16(qkv: torch.Tensor, n_views: int, seq: int, heads: int, variant
     return out
 
 
+def refiner_set_schedule(mode: int) -> None:
+    """A/B switch of the refiner scan: 0 automatic, 1 query-major, 2 cell-major (same results)."""
+    check(load().pg_refiner_set_schedule(int(mode)), "pg_refiner_set_schedule")
+
+
 def head_pack_weight(weight: torch.Tensor) -> torch.Tensor:
     """cell_layer.weight f32 [C, D] -> fp16 [C, 3*D] error-compensated split consumed by `head_forward`."""
     _need_cuda(weight)

@@ -199,10 +199,13 @@ def test_refiner_cell_major_equals_query_major(cuda, C, P, D, B, kc, topk, membe
     init = torch.from_numpy(synthetic.synthetic_geocells(B, seed=15)).to(cuda)
     dbank = ops.DeviceBank(cuda, **bank)
     args = (dbank, emb, init, torch.from_numpy(cand).to(cuda), torch.from_numpy(probs).to(cuda), topk, 1.6, 1e6)
-    monkeypatch.setenv("PG_REFINER_QUERY_MAJOR", "1")
-    ll_q, cell_q, dq = ops.refiner_forward(*args, debug=True)
-    monkeypatch.setenv("PG_REFINER_QUERY_MAJOR", "0")
-    ll_c, cell_c, dc = ops.refiner_forward(*args, debug=True)
+    try:
+        ops.refiner_set_schedule(1)
+        ll_q, cell_q, dq = ops.refiner_forward(*args, debug=True)
+        ops.refiner_set_schedule(2)
+        ll_c, cell_c, dc = ops.refiner_forward(*args, debug=True)
+    finally:
+        ops.refiner_set_schedule(0)
     torch.cuda.synchronize()
     # identical winners except where two prototypes tie to within fp32 summation-order noise
     same = (dq["best_proto"] == dc["best_proto"])

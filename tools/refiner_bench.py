@@ -57,7 +57,7 @@ def main():
         pairs_elems = float(sizes[cand].sum()) * D           # (prototype, query) element pairs
         row = dict(C=C, P=P, D=D, B=B, k=k, algorithmic_GB=alg_bytes / 1e9)
         for mode in ("cell_major", "query_major"):
-            os.environ["PG_REFINER_QUERY_MAJOR"] = "1" if mode == "query_major" else "0"
+            ops.refiner_set_schedule(1 if mode == "query_major" else 2)
             if mode == "query_major" and pairs_elems > 2e11:
                 continue
             ms = timeit(lambda: ops.refiner_forward(bank, emb, init, candt, probst, k, 1.6, 1000.0))
