@@ -11,9 +11,11 @@
 //   * persistent, ONE CTA per SM, 512 threads; a CTA works on "jobs" of TWO 128-row query tiles (slots 0 / 1) that ping-pong:
 //     while the softmax warps of one slot work, the tensor pipe serves the other.  Two tiles of the same (view, head) share one
 //     K/V stream; the odd last tiles (577 = 4 * 128 + 65) of two neighbouring heads are paired with separate streams.
-//   * KV blocks of 128: S_i = Q_i K_j^T is 4 MMAs of 128 x 128 x 16, P_i V_j 8 MMAs of 128 x 64 x 16; Q lives in TENSOR MEMORY
-//     (A operand), so every MMA reads only its B operand (K or V, 64 B/clk) from shared memory.
-//   * softmax threads (one per query row, 2 x 4 warps) process 128 logits per barrier round trip; the row maximum is computed
+//   * KV blocks of 64 with TWO S buffers per tile: S_i[b] = Q_i K_j^T is 4 MMAs of 128 x 64 x 16, P_i V_j 4 MMAs of
+//     128 x 64 x 16; the MMA warp runs two blocks ahead, so the softmax warps of a tile find their next S block complete and
+//     never wait for the tensor round trip.  Q lives in TENSOR MEMORY (A operand): every MMA reads only its B operand (K or
+//     V, 64 B/clk) from shared memory.
+//   * softmax threads (one per query row, 2 x 4 warps) process 64 logits per barrier round trip; the row maximum is computed
 //     for the first block only: later blocks reuse it and check the block sum instead (P = 2^(x - m) stays below 2^15, exact
 //     in fp16 range; a larger sum triggers the exact path: true maximum, O and l rescaled in TMEM, block redone).
 //   * a tunable share of the exponentials runs on the FMA pipe (Cody-Waite + degree-3 minimax, 7.5e-5 relative — below the
@@ -21,8 +23,8 @@
 //   * Q tiles arrive by TMA into a staging buffer one job ahead and are copied to TMEM while the previous job finishes; the
 //     epilogue (O / l -> fp16 -> global) runs on its own 4 warps, so consecutive jobs overlap.
 //
-// TMEM columns: S0 [0,128) S1 [128,256) (P_i aliases the first 64 columns of S_i as packed fp16) O0 [256,320) O1 [320,384)
-// Q0 [384,416) Q1 [416,448).
+// TMEM columns: tile 0 S buffers [0,64) [64,128), tile 1 [128,192) [192,256) (P aliases the first 32 columns of its S buffer
+// as packed fp16), O0 [256,320) O1 [320,384), Q0 [384,416) Q1 [416,448).
 // Warps: 0-3 softmax slot 0, 4-7 softmax slot 1, 8-11 epilogue, 12 TMA producer, 13 TMEM allocator + MMA issuer, 14-15 idle.
 #include "attention.h"
 #include "prof.h"
@@ -37,28 +39,32 @@ namespace pg {
 namespace {
 
 constexpr int kHeadDim = 64;
-constexpr int kBlock = 128;                            // query rows per tile and kv rows per block
-constexpr int kTileBytes = kBlock * kHeadDim * 2;      // 16 KB: one Q, K or V tile
-constexpr int kSlots = 8;                              // K/V ring
-constexpr int kThreads = 512;                        // 16 warps: setmaxnreg is a per-warpgroup (4 warps) operation
+constexpr int kBlock = 128;                            // query rows per tile
+constexpr int kSub = 64;                               // kv rows per block
+constexpr int kSubBytes = kSub * kHeadDim * 2;         // 8 KB: one K or V block (a Q tile is two of them)
+constexpr int kQBytes = 2 * kSubBytes;
+constexpr int kSlots = 16;                             // K/V ring
+constexpr int kThreads = 512;                          // 16 warps: setmaxnreg is a per-warpgroup (4 warps) operation
 constexpr int kWarpEpi = 8, kWarpTma = 12, kWarpMma = 13;
 constexpr uint32_t kColS = 0, kColO = 256, kColQ = 384;
 constexpr int kTmemCols = 512;
+constexpr float kRescaleThreshold = 8.0f;              // log2 domain, ragged last block (exact maximum, lazy rescale)
 constexpr float kSumLimit = 32768.f;                   // block sum that triggers the exact-maximum path (P < 2^15)
 
 struct Bars {
   uint64_t kv_full[kSlots], kv_empty[kSlots];
   uint64_t qs_full[2], qs_empty[2];   // TMA -> softmax (Q staging tile landed), softmax -> TMA (copied to TMEM)
   uint64_t q_ready[2];                // softmax -> MMA : Q_i is in TMEM
-  uint64_t s_full[2];                 // MMA -> softmax : S_i block complete
-  uint64_t p_ready[2];                // softmax -> MMA : P_i block written
+  uint64_t s_full[2][2];              // MMA -> softmax : S block complete in buffer [tile][b]
+  uint64_t p_ready[2][2];             // softmax -> MMA : P written over buffer [tile][b]
   uint64_t pv_done[2];                // MMA -> softmax : P_i V retired (O_i quiescent), one phase per block
   uint64_t o_full[2];                 // MMA -> epilogue: O_i complete
   uint64_t o_free[2];                 // epilogue -> MMA / softmax : O_i and the row statistics were read
   uint64_t l_ready[2];                // softmax -> epilogue : row statistics published
   uint32_t tmem_ptr;
 };
-constexpr int kSmemBytes = 1024 + (kSlots + 2) * kTileBytes + 1024 /* Bars */ + 2 * 2 * kBlock * 4;
+constexpr int kRingBytes = kSlots * kSubBytes;
+constexpr int kSmemBytes = 1024 + kRingBytes + 2 * kQBytes + 1024 /* Bars */ + 2 * 2 * kBlock * 4;
 
 struct PairArgs {
   const __half* qkv;
@@ -227,16 +233,16 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_kv = smem;
-  uint8_t* smem_q = smem + kSlots * kTileBytes;
-  Bars* bars = reinterpret_cast<Bars*>(smem + (kSlots + 2) * kTileBytes);
-  float* lm = reinterpret_cast<float*>(smem + (kSlots + 2) * kTileBytes + 1024);   // [slot][l | m][row]
+  uint8_t* smem_q = smem + kRingBytes;
+  Bars* bars = reinterpret_cast<Bars*>(smem + kRingBytes + 2 * kQBytes);
+  float* lm = reinterpret_cast<float*>(smem + kRingBytes + 2 * kQBytes + 1024);   // [slot][l | m][row]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int S = args.seq;
-  const int nb = (S + kBlock - 1) / kBlock;                    // KV blocks (5 for S = 577)
-  const int last_valid = S - (nb - 1) * kBlock;                // valid kv columns in the last block (65)
-  const int last_n = (last_valid + 15) & ~15;                  // MMA N / K extent of the last block (80)
+  const int nb = (S + kSub - 1) / kSub;                        // KV blocks (10 for S = 577)
+  const int last_valid = S - (nb - 1) * kSub;                  // valid kv columns in the last block (1)
+  const int last_n = (last_valid + 15) & ~15;                  // MMA N / K extent of the last block (16)
   const int n_jobs = args.n_jobs;
   const int stride = gridDim.x;
 
@@ -250,8 +256,10 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
       mbar_init(&bars->qs_full[i], 1);
       mbar_init(&bars->qs_empty[i], 4);
       mbar_init(&bars->q_ready[i], 4);
-      mbar_init(&bars->s_full[i], 1);
-      mbar_init(&bars->p_ready[i], 4);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&bars->s_full[i][b], 1);
+        mbar_init(&bars->p_ready[i][b], 4);
+      }
       mbar_init(&bars->pv_done[i], 1);
       mbar_init(&bars->o_full[i], 1);
       mbar_init(&bars->o_free[i], 4);
@@ -268,10 +276,9 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_ptr;
 
-  // register budget: 512 threads start with 128 each; the softmax warps hold a whole row of P (64 packed registers) plus
-  // the logits in flight and take the share the other roles do not need (8*168 + 4*96 + 4*80 = 16*128 per lane).
-  // setmaxnreg must be executed with the SAME value by all four warps of a warpgroup: warps 12-15 (TMA, MMA, two idle)
-  // form one.
+  // register budget: 512 threads start with 128 each; the softmax warps take the share the other roles do not need
+  // (8*168 + 4*96 + 4*80 = 16*128 per lane).  setmaxnreg must be executed with the SAME value by all four warps of a
+  // warpgroup: warps 12-15 (TMA, MMA, two idle) form one.
   if (warp >= kWarpTma) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
   if (warp > kWarpMma) {
     // idle warps of the last warpgroup
@@ -284,8 +291,8 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
       auto load_kv = [&](int col, int row) {
         mbar_wait(&bars->kv_empty[slot], phase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&bars->kv_full[slot], kTileBytes);
-          tma_load_2d(smem_kv + slot * kTileBytes, &tmap_qkv, &bars->kv_full[slot], col, row);
+          mbar_arrive_expect_tx(&bars->kv_full[slot], kSubBytes);
+          tma_load_2d(smem_kv + slot * kSubBytes, &tmap_qkv, &bars->kv_full[slot], col, row);
         }
         __syncwarp();
         if (++slot == kSlots) { slot = 0; phase ^= 1; }
@@ -295,9 +302,10 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
         uint32_t& nq = I ? nq1 : nq0;
         mbar_wait(&bars->qs_empty[I], (nq & 1) ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&bars->qs_full[I], kTileBytes);
-          tma_load_2d(smem_q + I * kTileBytes, &tmap_qkv, &bars->qs_full[I], (I ? jb.h1 : jb.h0) * kHeadDim,
-                      jb.view * S + (I ? jb.t1 : jb.t0) * kBlock);
+          const int col = (I ? jb.h1 : jb.h0) * kHeadDim, row = jb.view * S + (I ? jb.t1 : jb.t0) * kBlock;
+          mbar_arrive_expect_tx(&bars->qs_full[I], kQBytes);
+          tma_load_2d(smem_q + I * kQBytes, &tmap_qkv, &bars->qs_full[I], col, row);
+          tma_load_2d(smem_q + I * kQBytes + kSubBytes, &tmap_qkv, &bars->qs_full[I], col, row + kSub);
         }
         __syncwarp();
         ++nq;
@@ -322,20 +330,25 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
         // order = the MMA warp's acquisition order
         if (jb.shared) {
           load_kv(ka, row0);
+          if (nb > 1) load_kv(ka, row0 + kSub);
           for (int j = 0; j < nb; ++j) {
-            load_kv(va, row0 + j * kBlock);
-            if (j + 1 < nb) load_kv(ka, row0 + (j + 1) * kBlock);
+            load_kv(va, row0 + j * kSub);
+            if (j + 2 < nb) load_kv(ka, row0 + (j + 2) * kSub);
             if (j == 0) next_q();
           }
         } else {
           load_kv(ka, row0);
           if (jb.a1) load_kv(kb, row0);
+          if (nb > 1) {
+            load_kv(ka, row0 + kSub);
+            if (jb.a1) load_kv(kb, row0 + kSub);
+          }
           for (int j = 0; j < nb; ++j) {
-            load_kv(va, row0 + j * kBlock);
-            if (j + 1 < nb) load_kv(ka, row0 + (j + 1) * kBlock);
+            load_kv(va, row0 + j * kSub);
+            if (j + 2 < nb) load_kv(ka, row0 + (j + 2) * kSub);
             if (jb.a1) {
-              load_kv(vb, row0 + j * kBlock);
-              if (j + 1 < nb) load_kv(kb, row0 + (j + 1) * kBlock);
+              load_kv(vb, row0 + j * kSub);
+              if (j + 2 < nb) load_kv(kb, row0 + (j + 2) * kSub);
             }
             if (j == 0) next_q();
           }
@@ -347,13 +360,13 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
     {
       int slot = 0;
       uint32_t phase = 0;
-      uint32_t n_p0 = 0, n_p1 = 0;     // p_ready phases consumed
-      uint32_t n_j0 = 0, n_j1 = 0;     // jobs started per slot
-      // descriptor of ring slot s, k-step k: base + s * (16 KB >> 4) + k * (32 B >> 4) for K (K-major rows of 128 B),
-      // base + s * 1024 + k * (16 rows * 128 B >> 4) for V (MN-major: row = kv index)
+      uint32_t n_p00 = 0, n_p01 = 0, n_p10 = 0, n_p11 = 0;   // p_ready phases consumed, [tile][buffer]
+      uint32_t n_j0 = 0, n_j1 = 0;                             // jobs started per tile
+      // descriptor of ring slot s, k-step k: base + s * (8 KB >> 4) + k * (32 B >> 4) for K (K-major rows of 128 B),
+      // base + s * 512 + k * (16 rows * 128 B >> 4) for V (MN-major: row = kv index)
       const uint64_t k_desc0 = make_smem_desc(smem_u32(smem_kv), 16, 1024, kLayoutSw128);
       const uint64_t v_desc0 = make_smem_desc(smem_u32(smem_kv), 1024, 1024, kLayoutSw128);
-      const uint32_t idesc_s = make_idesc_f16(kBlock, kBlock, 0, 0);
+      const uint32_t idesc_s = make_idesc_f16(kBlock, kSub, 0, 0);
       const uint32_t idesc_s_last = make_idesc_f16(kBlock, last_n, 0, 0);
       const uint32_t idesc_pv = make_idesc_f16(kBlock, kHeadDim, 0, 1);    // B (= V) is MN-major
       auto acquire = [&]() -> int {
@@ -367,29 +380,30 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
         if (elect_one()) tc_commit(&bars->kv_empty[sl]);
         __syncwarp();
       };
-      auto issue_s = [&](auto I_, int sl, int j) {
+      auto issue_s = [&](auto I_, int sl, int j) {   // S_I[j & 1] = Q_I K_j^T
         constexpr int I = decltype(I_)::value;
         if (elect_one()) {
           const uint32_t idesc = (j == nb - 1) ? idesc_s_last : idesc_s;
-          const uint64_t kd = k_desc0 + (uint64_t)(sl * (kTileBytes >> 4));
+          const uint64_t kd = k_desc0 + (uint64_t)(sl * (kSubBytes >> 4));
+          const uint32_t d = tmem_base + kColS + 128 * I + kSub * (j & 1);
 #pragma unroll
           for (int k = 0; k < kHeadDim / 16; ++k)
-            umma_ts(tmem_base + kColS + 128 * I, tmem_base + kColQ + 32 * I + 8 * k, kd + 2 * k, idesc, k != 0);
-          tc_commit(&bars->s_full[I]);
+            umma_ts(d, tmem_base + kColQ + 32 * I + 8 * k, kd + 2 * k, idesc, k != 0);
+          tc_commit(&bars->s_full[I][j & 1]);
         }
         __syncwarp();
       };
-      auto issue_pv = [&](auto I_, int sl, int j) {
+      auto issue_pv = [&](auto I_, int sl, int j) {   // O_I += P_I[j & 1] V_j
         constexpr int I = decltype(I_)::value;
         if (elect_one()) {
-          const uint64_t vd = v_desc0 + (uint64_t)(sl * (kTileBytes >> 4));
-          const uint32_t d = tmem_base + kColO + 64 * I, a = tmem_base + kColS + 128 * I;
+          const uint64_t vd = v_desc0 + (uint64_t)(sl * (kSubBytes >> 4));
+          const uint32_t d = tmem_base + kColO + 64 * I, a = tmem_base + kColS + 128 * I + kSub * (j & 1);
           umma_ts(d, a, vd, idesc_pv, j != 0);
           if (j == nb - 1) {
             for (int k = 1; k < last_n / 16; ++k) umma_ts(d, a + 8 * k, vd + 128 * k, idesc_pv, 1);
           } else {
 #pragma unroll
-            for (int k = 1; k < kBlock / 16; ++k) umma_ts(d, a + 8 * k, vd + 128 * k, idesc_pv, 1);
+            for (int k = 1; k < kSub / 16; ++k) umma_ts(d, a + 8 * k, vd + 128 * k, idesc_pv, 1);
           }
           tc_commit(&bars->pv_done[I]);
           if (j == nb - 1) tc_commit(&bars->o_full[I]);
@@ -398,9 +412,10 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
       };
       auto wait_p = [&](auto I_, int j) {
         constexpr int I = decltype(I_)::value;
-        uint32_t& n_p = I ? n_p1 : n_p0;
+        const int b = j & 1;
+        uint32_t& n_p = I ? (b ? n_p11 : n_p10) : (b ? n_p01 : n_p00);
         const uint32_t n_j = I ? n_j1 : n_j0;
-        mbar_wait(&bars->p_ready[I], n_p & 1);
+        mbar_wait(&bars->p_ready[I][b], n_p & 1);
         ++n_p;
         if (j == 0) mbar_wait(&bars->o_free[I], (n_j & 1) ^ 1);   // the previous job's O_i was read out
         tc_fence_after();
@@ -412,24 +427,30 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
         if (jb.a1) mbar_wait(&bars->q_ready[1], n_j1 & 1);
         tc_fence_after();
         if (jb.shared) {
-          const int ks = acquire();
-          issue_s(Slot<0>{}, ks, 0);
-          issue_s(Slot<1>{}, ks, 0);
-          release(ks);
+          int sl = acquire();
+          issue_s(Slot<0>{}, sl, 0);
+          issue_s(Slot<1>{}, sl, 0);
+          release(sl);
+          if (nb > 1) {
+            sl = acquire();
+            issue_s(Slot<0>{}, sl, 1);
+            issue_s(Slot<1>{}, sl, 1);
+            release(sl);
+          }
           for (int j = 0; j < nb; ++j) {
             wait_p(Slot<0>{}, j);
             const int vs = acquire();
             issue_pv(Slot<0>{}, vs, j);
             int kn = 0;
-            if (j + 1 < nb) {
+            if (j + 2 < nb) {
               kn = acquire();
-              issue_s(Slot<0>{}, kn, j + 1);
+              issue_s(Slot<0>{}, kn, j + 2);
             }
             wait_p(Slot<1>{}, j);
             issue_pv(Slot<1>{}, vs, j);
             release(vs);
-            if (j + 1 < nb) {
-              issue_s(Slot<1>{}, kn, j + 1);
+            if (j + 2 < nb) {
+              issue_s(Slot<1>{}, kn, j + 2);
               release(kn);
             }
           }
@@ -442,14 +463,24 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
             issue_s(Slot<1>{}, sl, 0);
             release(sl);
           }
+          if (nb > 1) {
+            sl = acquire();
+            issue_s(Slot<0>{}, sl, 1);
+            release(sl);
+            if (jb.a1) {
+              sl = acquire();
+              issue_s(Slot<1>{}, sl, 1);
+              release(sl);
+            }
+          }
           for (int j = 0; j < nb; ++j) {
             wait_p(Slot<0>{}, j);
             sl = acquire();
             issue_pv(Slot<0>{}, sl, j);
             release(sl);
-            if (j + 1 < nb) {
+            if (j + 2 < nb) {
               sl = acquire();
-              issue_s(Slot<0>{}, sl, j + 1);
+              issue_s(Slot<0>{}, sl, j + 2);
               release(sl);
             }
             if (jb.a1) {
@@ -457,9 +488,9 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
               sl = acquire();
               issue_pv(Slot<1>{}, sl, j);
               release(sl);
-              if (j + 1 < nb) {
+              if (j + 2 < nb) {
                 sl = acquire();
-                issue_s(Slot<1>{}, sl, j + 1);
+                issue_s(Slot<1>{}, sl, j + 2);
                 release(sl);
               }
             }
@@ -472,16 +503,16 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
   } else if (warp < kWarpEpi) {
     // ---------------------------------------------------------------- softmax warps: thread = query row = TMEM lane
     asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
-    const int i = warp >> 2;        // slot
+    const int i = warp >> 2;        // tile slot
     const int wq = warp & 3;        // lane quarter
     const int row = wq * 32 + lane;
     const uint32_t lane_base = uint32_t(wq * 32) << 16;
-    const uint32_t s_tmem = tmem_base + lane_base + kColS + 128 * i;
+    const uint32_t s_tmem0 = tmem_base + lane_base + kColS + 128 * i;
     const uint32_t o_tmem = tmem_base + lane_base + kColO + 64 * i;
     const uint32_t q_tmem = tmem_base + lane_base + kColQ + 32 * i;
-    const uint32_t q_smem = smem_u32(smem_q + i * kTileBytes) + row * 128;
+    const uint32_t q_smem = smem_u32(smem_q + i * kQBytes) + row * 128;
     const float c = args.scale_log2;
-    uint32_t n_q = 0, n_s = 0, n_blk = 0, n_job = 0;
+    uint32_t n_q = 0, n_s0 = 0, n_s1 = 0, n_blk = 0, n_job = 0;
     bool q_done = false;
 
     // staged Q tile (128-byte swizzle: 16-byte chunk ch of row r sits at chunk ch ^ (r & 7)) -> TMEM A operand
@@ -537,8 +568,13 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
       };
 
       for (int j = 0; j < nb; ++j) {
-        mbar_wait(&bars->s_full[i], n_s & 1);
-        ++n_s;
+        const int b = j & 1;
+        const uint32_t s_tmem = s_tmem0 + kSub * b;
+        {
+          uint32_t& n_s = b ? n_s1 : n_s0;
+          mbar_wait(&bars->s_full[i][b], n_s & 1);
+          ++n_s;
+        }
         tc_fence_after();
         if (j == nb - 1 && next_active) {   // every S_i MMA of this job has retired: Q_i may be replaced
           copy_q();
@@ -546,89 +582,116 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
         }
         if (!warp_active) {
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->p_ready[i]);
+          if (lane == 0) mbar_arrive(&bars->p_ready[i][b]);
           ++n_blk;
           continue;
         }
-        // valid key columns of this block: nfull whole 16-column chunks + `rem` columns of one ragged chunk (last block only)
-        const int ncols = (j == nb - 1) ? last_valid : kBlock;
-        const int nfull = ncols >> 4, rem = ncols & 15;
-        uint32_t pk[64], pkm[8];
-        float bs;
-        bool do_max = (j == 0);
-        for (;;) {
-          if (do_max) {   // exact row maximum of the block (first block of a job, or a block whose sum overflowed)
-            float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
+        if (j < nb - 1 || last_valid == kSub) {
+          // ---- a block of 64 valid key columns: one branch-free basic block, P held in registers until the sum is checked
+          uint32_t pk[32];
+          float bs;
+          bool do_max = (j == 0);
+          for (;;) {
+            if (do_max) {   // exact row maximum of the block (first block of a job, or a block whose sum overflowed)
+              float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-              if (ch < nfull) {
-                uint32_t r[16];
-                tmem_ld16p(s_tmem + 16 * ch, r);
-                tmem_ld_wait16(r);
-                b0 = fmax3(b0, __uint_as_float(r[0]), __uint_as_float(r[1]));
-                b1 = fmax3(b1, __uint_as_float(r[2]), __uint_as_float(r[3]));
-                b2 = fmax3(b2, __uint_as_float(r[4]), __uint_as_float(r[5]));
-                b3 = fmax3(b3, __uint_as_float(r[6]), __uint_as_float(r[7]));
-                b0 = fmax3(b0, __uint_as_float(r[8]), __uint_as_float(r[9]));
-                b1 = fmax3(b1, __uint_as_float(r[10]), __uint_as_float(r[11]));
-                b2 = fmax3(b2, __uint_as_float(r[12]), __uint_as_float(r[13]));
-                b3 = fmax3(b3, __uint_as_float(r[14]), __uint_as_float(r[15]));
+              for (int h = 0; h < 2; ++h) {
+                uint32_t r[32];
+                tmem_ld32(s_tmem + 32 * h, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int x = 0; x < 32; x += 8) {
+                  b0 = fmax3(b0, __uint_as_float(r[x]), __uint_as_float(r[x + 1]));
+                  b1 = fmax3(b1, __uint_as_float(r[x + 2]), __uint_as_float(r[x + 3]));
+                  b2 = fmax3(b2, __uint_as_float(r[x + 4]), __uint_as_float(r[x + 5]));
+                  b3 = fmax3(b3, __uint_as_float(r[x + 6]), __uint_as_float(r[x + 7]));
+                }
               }
+              const float m_new = fmaxf(fmaxf(m, fmaxf(b0, b1)), fmaxf(b2, b3));
+              if (j > 0) rescale(m_new);
+              m = m_new;
             }
-            if (rem) {
-              uint32_t r[16];
-              tmem_ld16p(s_tmem + 16 * nfull, r);
-              tmem_ld_wait16(r);
+            const float mc = m * c;
+            const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
+            float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+            uint32_t ra[16], rb[16];
+            tmem_ld16p(s_tmem, ra);
 #pragma unroll
-              for (int x = 0; x < 16; ++x)
-                if (x < rem) b0 = fmaxf(b0, __uint_as_float(r[x]));
+            for (int ch = 0; ch < 4; ch += 2) {   // software-pipelined: the next chunk's load is in flight during the arithmetic
+              tmem_ld_wait16(ra);
+              tmem_ld16p(s_tmem + 16 * (ch + 1), rb);
+              exp_chunk<POLY>(ra, pk + 8 * ch, c2, nmc2, acc0, acc1);
+              tmem_ld_wait16(rb);
+              if (ch + 2 < 4) tmem_ld16p(s_tmem + 16 * (ch + 2), ra);
+              exp_chunk<POLY>(rb, pk + 8 * (ch + 1), c2, nmc2, acc0, acc1);
             }
-            const float m_new = fmaxf(fmaxf(m, fmaxf(b0, b1)), fmaxf(b2, b3));
-            if (j > 0) rescale(m_new);
+            bs = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+            if (!do_max && __any_sync(0xffffffffu, !(bs < kSumLimit))) {   // some P may not fit fp16: exact path
+              do_max = true;
+              continue;
+            }
+            break;
+          }
+          l += bs;
+          // P (packed fp16) over the first 32 columns of the S buffer: every logit of the block is already in registers
+          tmem_st32p(s_tmem, pk);
+        } else {
+          // ---- ragged last block: nfull whole 16-column chunks + `rem` valid columns of one more.  Exact maximum first
+          // (lazy rescale: P <= 2^8), then P chunk by chunk (P of chunk ch lands on S columns of chunks <= ch, already read).
+          const int nfull = last_valid >> 4, rem = last_valid & 15;
+          float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
+          for (int ch = 0; ch < nfull; ++ch) {
+            uint32_t r[16];
+            tmem_ld16p(s_tmem + 16 * ch, r);
+            tmem_ld_wait16(r);
+            b0 = fmax3(b0, __uint_as_float(r[0]), __uint_as_float(r[1]));
+            b1 = fmax3(b1, __uint_as_float(r[2]), __uint_as_float(r[3]));
+            b2 = fmax3(b2, __uint_as_float(r[4]), __uint_as_float(r[5]));
+            b3 = fmax3(b3, __uint_as_float(r[6]), __uint_as_float(r[7]));
+            b0 = fmax3(b0, __uint_as_float(r[8]), __uint_as_float(r[9]));
+            b1 = fmax3(b1, __uint_as_float(r[10]), __uint_as_float(r[11]));
+            b2 = fmax3(b2, __uint_as_float(r[12]), __uint_as_float(r[13]));
+            b3 = fmax3(b3, __uint_as_float(r[14]), __uint_as_float(r[15]));
+          }
+          if (rem) {
+            uint32_t r[16];
+            tmem_ld16p(s_tmem + 16 * nfull, r);
+            tmem_ld_wait16(r);
+#pragma unroll
+            for (int x = 0; x < 16; ++x)
+              if (x < rem) b0 = fmaxf(b0, __uint_as_float(r[x]));
+          }
+          const float m_new = fmaxf(fmaxf(m, fmaxf(b0, b1)), fmaxf(b2, b3));
+          if (j == 0) {
+            m = m_new;
+          } else if (__any_sync(0xffffffffu, (m_new - m) * c > kRescaleThreshold)) {
+            rescale(m_new);
             m = m_new;
           }
           const float mc = m * c;
           const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
           float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-          uint32_t ra[16], rb[16];
-          if (nfull > 0) tmem_ld16p(s_tmem, ra);
-#pragma unroll
-          for (int ch = 0; ch < 8; ch += 2) {   // software-pipelined: the next chunk's load is in flight during the arithmetic
-            if (ch < nfull) {
-              tmem_ld_wait16(ra);
-              if (ch + 1 < nfull) tmem_ld16p(s_tmem + 16 * (ch + 1), rb);
-              exp_chunk<POLY>(ra, pk + 8 * ch, c2, nmc2, acc0, acc1);
-            }
-            if (ch + 1 < nfull) {
-              tmem_ld_wait16(rb);
-              if (ch + 2 < nfull) tmem_ld16p(s_tmem + 16 * (ch + 2), ra);
-              exp_chunk<POLY>(rb, pk + 8 * (ch + 1), c2, nmc2, acc0, acc1);
-            }
+          for (int ch = 0; ch < nfull; ++ch) {
+            uint32_t r[16], pk8[8];
+            tmem_ld16p(s_tmem + 16 * ch, r);
+            tmem_ld_wait16(r);
+            exp_chunk<0>(r, pk8, c2, nmc2, acc0, acc1);
+            tmem_st8p(s_tmem + 8 * ch, pk8);
           }
-          bs = (acc0.x + acc0.y) + (acc1.x + acc1.y);
+          float bs = (acc0.x + acc0.y) + (acc1.x + acc1.y);
           if (rem) {
-            tmem_ld16p(s_tmem + 16 * nfull, ra);
-            tmem_ld_wait16(ra);
-            exp_chunk_masked(ra, pkm, rem, c, -mc, bs);
+            uint32_t r[16], pk8[8];
+            tmem_ld16p(s_tmem + 16 * nfull, r);
+            tmem_ld_wait16(r);
+            exp_chunk_masked(r, pk8, rem, c, -mc, bs);
+            tmem_st8p(s_tmem + 8 * nfull, pk8);
           }
-          if (!do_max && __any_sync(0xffffffffu, !(bs < kSumLimit))) {   // some P may not fit fp16: exact path
-            do_max = true;
-            continue;
-          }
-          break;
+          l += bs;
         }
-        l += bs;
-        // P (packed fp16) over the first columns of S_i: every logit of the block is already in registers
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          if (2 * h + 2 <= nfull) tmem_st16p(s_tmem + 16 * h, pk + 16 * h);
-          else if (2 * h + 1 <= nfull) tmem_st8p(s_tmem + 16 * h, pk + 16 * h);
-        }
-        if (rem) tmem_st8p(s_tmem + 8 * nfull, pkm);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->p_ready[i]);
+        if (lane == 0) mbar_arrive(&bars->p_ready[i][b]);
         ++n_blk;
       }
 
@@ -703,7 +766,7 @@ int launch_pair(int variant, const void* qkv, void* out, int n_views, int seq, i
                 float* lse2) {
   const int hidden = heads * kHeadDim;
   CUtensorMap tm;
-  if (make_tmap_f16_2d(&tm, qkv, (uint64_t)n_views * seq, 3 * hidden, 3 * hidden, kBlock, kHeadDim)) return 1;
+  if (make_tmap_f16_2d(&tm, qkv, (uint64_t)n_views * seq, 3 * hidden, 3 * hidden, kSub, kHeadDim)) return 1;
   auto kern = attention_pair_kernel<POLY>;
   int dev = 0;
   cudaGetDevice(&dev);
