@@ -25,7 +25,8 @@
 //
 // TMEM columns: tile 0 S buffers [0,64) [64,128), tile 1 [128,192) [192,256) (P aliases the first 32 columns of its S buffer
 // as packed fp16), O0 [256,320) O1 [320,384), Q0 [384,416) Q1 [416,448).
-// Warps: 0-3 softmax slot 0, 4-7 softmax slot 1, 8-11 epilogue, 12 TMA producer, 13 TMEM allocator + MMA issuer, 14-15 idle.
+// Warps: 0-3 softmax tile 0, 4-7 softmax tile 1, 8-11 epilogue, 12 TMA producer, 13 / 14 MMA issuers of tile 0 / 1 (13 also
+// allocates TMEM), 15 idle.
 #include "attention.h"
 #include "prof.h"
 #include "ptx.cuh"
@@ -43,9 +44,10 @@ constexpr int kBlock = 128;                            // query rows per tile
 constexpr int kSub = 64;                               // kv rows per block
 constexpr int kSubBytes = kSub * kHeadDim * 2;         // 8 KB: one K or V block (a Q tile is two of them)
 constexpr int kQBytes = 2 * kSubBytes;
-constexpr int kSlots = 16;                             // K/V ring
+constexpr int kSlots = 8;                              // K/V ring of 16 KB slots: {K_0, K_1} or {V_j, K_(j+2)} of one tile stream
+constexpr int kSlotBytes = 2 * kSubBytes;
 constexpr int kThreads = 512;                          // 16 warps: setmaxnreg is a per-warpgroup (4 warps) operation
-constexpr int kWarpEpi = 8, kWarpTma = 12, kWarpMma = 13;
+constexpr int kWarpEpi = 8, kWarpTma = 12, kWarpMma = 13;   // MMA issuers: warp 13 (tile 0), warp 14 (tile 1)
 constexpr uint32_t kColS = 0, kColO = 256, kColQ = 384;
 constexpr int kTmemCols = 512;
 constexpr float kRescaleThreshold = 8.0f;              // log2 domain, ragged last block (exact maximum, lazy rescale)
@@ -63,7 +65,7 @@ struct Bars {
   uint64_t l_ready[2];                // softmax -> epilogue : row statistics published
   uint32_t tmem_ptr;
 };
-constexpr int kRingBytes = kSlots * kSubBytes;
+constexpr int kRingBytes = kSlots * kSlotBytes;
 constexpr int kSmemBytes = 1024 + kRingBytes + 2 * kQBytes + 1024 /* Bars */ + 2 * 2 * kBlock * 4;
 
 struct PairArgs {
@@ -250,7 +252,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
     tma_prefetch_desc(&tmap_qkv);
     for (int s = 0; s < kSlots; ++s) {
       mbar_init(&bars->kv_full[s], 1);
-      mbar_init(&bars->kv_empty[s], 1);
+      mbar_init(&bars->kv_empty[s], 2);   // two tcgen05.commit arrivals: one per MMA warp (shared stream) or both from the owner
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->qs_full[i], 1);
@@ -280,22 +282,28 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
   // (8*168 + 4*96 + 4*80 = 16*128 per lane).  setmaxnreg must be executed with the SAME value by all four warps of a
   // warpgroup: warps 12-15 (TMA, MMA, two idle) form one.
   if (warp >= kWarpTma) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-  if (warp > kWarpMma) {
-    // idle warps of the last warpgroup
+  // K/V ring protocol.  A job's stream of a tile is 1 + nb slots: {K_0, K_1}, then {V_j, K_(j+2)} for j = 0 .. nb-1.  Two tiles
+  // of one (view, head) share ONE stream (both MMA warps read every slot and commit once each); otherwise the two streams are
+  // interleaved slot by slot (the owner commits twice), or there is a single stream (tile 1 absent).  Every role derives the
+  // same ring positions from the job list.
+  if (warp > kWarpMma + 1) {
+    // idle warp of the last warpgroup
   } else if (warp == kWarpTma) {
     // ---------------------------------------------------------------- TMA producer (warp-uniform, one elected lane issues)
     if (blockIdx.x < n_jobs) {
-      int slot = 0;
-      uint32_t phase = 0;
+      uint32_t pos = 0;              // ring position
       uint32_t nq0 = 0, nq1 = 0;
-      auto load_kv = [&](int col, int row) {
-        mbar_wait(&bars->kv_empty[slot], phase ^ 1);
+      // slot contents: rows [r_a, +64) at column col_a, and (if col_b >= 0) rows [r_b, +64) at column col_b
+      auto load_slot = [&](int col_a, int r_a, int col_b, int r_b) {
+        const int slot = pos % kSlots;
+        mbar_wait(&bars->kv_empty[slot], ((pos / kSlots) & 1) ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&bars->kv_full[slot], kSubBytes);
-          tma_load_2d(smem_kv + slot * kSubBytes, &tmap_qkv, &bars->kv_full[slot], col, row);
+          mbar_arrive_expect_tx(&bars->kv_full[slot], col_b >= 0 ? kSlotBytes : kSubBytes);
+          tma_load_2d(smem_kv + slot * kSlotBytes, &tmap_qkv, &bars->kv_full[slot], col_a, r_a);
+          if (col_b >= 0) tma_load_2d(smem_kv + slot * kSlotBytes + kSubBytes, &tmap_qkv, &bars->kv_full[slot], col_b, r_b);
         }
         __syncwarp();
-        if (++slot == kSlots) { slot = 0; phase ^= 1; }
+        ++pos;
       };
       auto load_q = [&](auto I_, const Job& jb) {
         constexpr int I = decltype(I_)::value;
@@ -318,187 +326,90 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
       for (int job = blockIdx.x; job < n_jobs; job += stride) {
         const Job jb = decode_job(job, args);
         const int row0 = jb.view * S;
-        const bool has_next = job + stride < n_jobs;
-        const int ka = args.hidden + jb.h0 * kHeadDim, va = 2 * args.hidden + jb.h0 * kHeadDim;
-        const int kb = args.hidden + jb.h1 * kHeadDim, vb = 2 * args.hidden + jb.h1 * kHeadDim;
-        auto next_q = [&]() {   // the next job's Q tiles, once this job's first blocks are on their way
-          if (!has_next) return;
-          const Job jn = decode_job(job + stride, args);
-          load_q(Slot<0>{}, jn);
-          if (jn.a1) load_q(Slot<1>{}, jn);
-        };
-        // order = the MMA warp's acquisition order
-        if (jb.shared) {
-          load_kv(ka, row0);
-          if (nb > 1) load_kv(ka, row0 + kSub);
-          for (int j = 0; j < nb; ++j) {
-            load_kv(va, row0 + j * kSub);
-            if (j + 2 < nb) load_kv(ka, row0 + (j + 2) * kSub);
-            if (j == 0) next_q();
+        const int nstream = (jb.shared || !jb.a1) ? 1 : 2;
+        for (int step = 0; step <= nb; ++step) {          // step 0 = {K_0, K_1}; step j + 1 = {V_j, K_(j+2)}
+          for (int t = 0; t < nstream; ++t) {
+            const int h = t ? jb.h1 : jb.h0;
+            const int kc = args.hidden + h * kHeadDim, vc = 2 * args.hidden + h * kHeadDim;
+            if (step == 0) load_slot(kc, row0, nb > 1 ? kc : -1, row0 + kSub);
+            else load_slot(vc, row0 + (step - 1) * kSub, step + 1 < nb ? kc : -1, row0 + (step + 1) * kSub);
           }
-        } else {
-          load_kv(ka, row0);
-          if (jb.a1) load_kv(kb, row0);
-          if (nb > 1) {
-            load_kv(ka, row0 + kSub);
-            if (jb.a1) load_kv(kb, row0 + kSub);
-          }
-          for (int j = 0; j < nb; ++j) {
-            load_kv(va, row0 + j * kSub);
-            if (j + 2 < nb) load_kv(ka, row0 + (j + 2) * kSub);
-            if (jb.a1) {
-              load_kv(vb, row0 + j * kSub);
-              if (j + 2 < nb) load_kv(kb, row0 + (j + 2) * kSub);
-            }
-            if (j == 0) next_q();
+          if (step == 1 && job + stride < n_jobs) {       // the next job's Q tiles, once this job's first blocks are on their way
+            const Job jn = decode_job(job + stride, args);
+            load_q(Slot<0>{}, jn);
+            if (jn.a1) load_q(Slot<1>{}, jn);
           }
         }
       }
     }
-  } else if (warp == kWarpMma) {
-    // ---------------------------------------------------------------- MMA issuer (warp-uniform, one elected lane issues)
-    {
-      int slot = 0;
-      uint32_t phase = 0;
-      uint32_t n_p00 = 0, n_p01 = 0, n_p10 = 0, n_p11 = 0;   // p_ready phases consumed, [tile][buffer]
-      uint32_t n_j0 = 0, n_j1 = 0;                             // jobs started per tile
-      // descriptor of ring slot s, k-step k: base + s * (8 KB >> 4) + k * (32 B >> 4) for K (K-major rows of 128 B),
-      // base + s * 512 + k * (16 rows * 128 B >> 4) for V (MN-major: row = kv index)
-      const uint64_t k_desc0 = make_smem_desc(smem_u32(smem_kv), 16, 1024, kLayoutSw128);
-      const uint64_t v_desc0 = make_smem_desc(smem_u32(smem_kv), 1024, 1024, kLayoutSw128);
-      const uint32_t idesc_s = make_idesc_f16(kBlock, kSub, 0, 0);
-      const uint32_t idesc_s_last = make_idesc_f16(kBlock, last_n, 0, 0);
-      const uint32_t idesc_pv = make_idesc_f16(kBlock, kHeadDim, 0, 1);    // B (= V) is MN-major
-      auto acquire = [&]() -> int {
-        mbar_wait(&bars->kv_full[slot], phase);
-        tc_fence_after();
-        const int sl = slot;
-        if (++slot == kSlots) { slot = 0; phase ^= 1; }
-        return sl;
-      };
-      auto release = [&](int sl) {
-        if (elect_one()) tc_commit(&bars->kv_empty[sl]);
-        __syncwarp();
-      };
-      auto issue_s = [&](auto I_, int sl, int j) {   // S_I[j & 1] = Q_I K_j^T
-        constexpr int I = decltype(I_)::value;
-        if (elect_one()) {
-          const uint32_t idesc = (j == nb - 1) ? idesc_s_last : idesc_s;
-          const uint64_t kd = k_desc0 + (uint64_t)(sl * (kSubBytes >> 4));
-          const uint32_t d = tmem_base + kColS + 128 * I + kSub * (j & 1);
+  } else if (warp >= kWarpMma) {
+    // ---------------------------------------------------------------- MMA issuers: warp 13 -> tile 0, warp 14 -> tile 1
+    // (warp-uniform; one elected lane issues)
+    const int I = warp - kWarpMma;
+    uint32_t pos = 0;                                    // ring position at the start of the current job
+    uint32_t n_p0 = 0, n_p1 = 0;                         // p_ready phases consumed, per S buffer
+    uint32_t n_j = 0;                                    // jobs this tile took part in
+    // smem descriptors of a slot's first (offset 0) / second (offset 8 KB) block: K is K-major (rows of 128 B, k-step = 32 B),
+    // V is MN-major (row = kv index, k-step = 16 rows)
+    const uint64_t k_desc0 = make_smem_desc(smem_u32(smem_kv), 16, 1024, kLayoutSw128);
+    const uint64_t v_desc0 = make_smem_desc(smem_u32(smem_kv), 1024, 1024, kLayoutSw128);
+    const uint32_t idesc_s = make_idesc_f16(kBlock, kSub, 0, 0);
+    const uint32_t idesc_s_last = make_idesc_f16(kBlock, last_n, 0, 0);
+    const uint32_t idesc_pv = make_idesc_f16(kBlock, kHeadDim, 0, 1);    // B (= V) is MN-major
+    const uint32_t s_base = tmem_base + kColS + 128 * I, o_base = tmem_base + kColO + 64 * I, q_base = tmem_base + kColQ + 32 * I;
+    auto issue_s = [&](uint64_t kd, int j) {   // S_I[j & 1] = Q_I K_j^T   (inside an elected region)
+      const uint32_t idesc = (j == nb - 1) ? idesc_s_last : idesc_s;
+      const uint32_t d = s_base + kSub * (j & 1);
 #pragma unroll
-          for (int k = 0; k < kHeadDim / 16; ++k)
-            umma_ts(d, tmem_base + kColQ + 32 * I + 8 * k, kd + 2 * k, idesc, k != 0);
-          tc_commit(&bars->s_full[I][j & 1]);
+      for (int k = 0; k < kHeadDim / 16; ++k) umma_ts(d, q_base + 8 * k, kd + 2 * k, idesc, k != 0);
+      tc_commit(&bars->s_full[I][j & 1]);
+    };
+    for (int job = blockIdx.x; job < n_jobs; job += stride) {
+      const Job jb = decode_job(job, args);
+      const int nstream = (jb.shared || !jb.a1) ? 1 : 2;
+      const uint32_t pos_job = pos;
+      pos += (uint32_t)(nb + 1) * nstream;
+      if (I == 1 && !jb.a1) continue;
+      const uint32_t first = (nstream == 2) ? I : 0;
+      const int ncommit = jb.shared ? 1 : 2;
+      mbar_wait(&bars->q_ready[I], n_j & 1);
+      for (int step = 0; step <= nb; ++step) {
+        const uint32_t p = pos_job + first + (uint32_t)step * nstream;
+        const int slot = p % kSlots;
+        const int j = step - 1;
+        if (step > 0) {
+          uint32_t& n_p = (j & 1) ? n_p1 : n_p0;
+          mbar_wait(&bars->p_ready[I][j & 1], n_p & 1);
+          ++n_p;
+          if (j == 0) mbar_wait(&bars->o_free[I], (n_j & 1) ^ 1);   // the previous job's O_I was read out
         }
-        __syncwarp();
-      };
-      auto issue_pv = [&](auto I_, int sl, int j) {   // O_I += P_I[j & 1] V_j
-        constexpr int I = decltype(I_)::value;
+        mbar_wait(&bars->kv_full[slot], (p / kSlots) & 1);
+        tc_fence_after();
         if (elect_one()) {
-          const uint64_t vd = v_desc0 + (uint64_t)(sl * (kSubBytes >> 4));
-          const uint32_t d = tmem_base + kColO + 64 * I, a = tmem_base + kColS + 128 * I + kSub * (j & 1);
-          umma_ts(d, a, vd, idesc_pv, j != 0);
-          if (j == nb - 1) {
-            for (int k = 1; k < last_n / 16; ++k) umma_ts(d, a + 8 * k, vd + 128 * k, idesc_pv, 1);
+          const uint64_t d0 = (uint64_t)(slot * (kSlotBytes >> 4)), d1 = d0 + (kSubBytes >> 4);
+          if (step == 0) {
+            issue_s(k_desc0 + d0, 0);
+            if (nb > 1) issue_s(k_desc0 + d1, 1);
           } else {
+            const uint64_t vd = v_desc0 + d0;
+            const uint32_t a = s_base + kSub * (j & 1);       // P_I[j & 1] (packed fp16 over the S buffer)
+            umma_ts(o_base, a, vd, idesc_pv, j != 0);
+            if (j == nb - 1) {
+              for (int k = 1; k < last_n / 16; ++k) umma_ts(o_base, a + 8 * k, vd + 128 * k, idesc_pv, 1);
+            } else {
 #pragma unroll
-            for (int k = 1; k < kSub / 16; ++k) umma_ts(d, a + 8 * k, vd + 128 * k, idesc_pv, 1);
+              for (int k = 1; k < kSub / 16; ++k) umma_ts(o_base, a + 8 * k, vd + 128 * k, idesc_pv, 1);
+            }
+            tc_commit(&bars->pv_done[I]);
+            if (j == nb - 1) tc_commit(&bars->o_full[I]);
+            if (j + 2 < nb) issue_s(k_desc0 + d1, j + 2);
           }
-          tc_commit(&bars->pv_done[I]);
-          if (j == nb - 1) tc_commit(&bars->o_full[I]);
+          tc_commit(&bars->kv_empty[slot]);
+          if (ncommit == 2) tc_commit(&bars->kv_empty[slot]);
         }
         __syncwarp();
-      };
-      auto wait_p = [&](auto I_, int j) {
-        constexpr int I = decltype(I_)::value;
-        const int b = j & 1;
-        uint32_t& n_p = I ? (b ? n_p11 : n_p10) : (b ? n_p01 : n_p00);
-        const uint32_t n_j = I ? n_j1 : n_j0;
-        mbar_wait(&bars->p_ready[I][b], n_p & 1);
-        ++n_p;
-        if (j == 0) mbar_wait(&bars->o_free[I], (n_j & 1) ^ 1);   // the previous job's O_i was read out
-        tc_fence_after();
-      };
-
-      for (int job = blockIdx.x; job < n_jobs; job += stride) {
-        const Job jb = decode_job(job, args);
-        mbar_wait(&bars->q_ready[0], n_j0 & 1);
-        if (jb.a1) mbar_wait(&bars->q_ready[1], n_j1 & 1);
-        tc_fence_after();
-        if (jb.shared) {
-          int sl = acquire();
-          issue_s(Slot<0>{}, sl, 0);
-          issue_s(Slot<1>{}, sl, 0);
-          release(sl);
-          if (nb > 1) {
-            sl = acquire();
-            issue_s(Slot<0>{}, sl, 1);
-            issue_s(Slot<1>{}, sl, 1);
-            release(sl);
-          }
-          for (int j = 0; j < nb; ++j) {
-            wait_p(Slot<0>{}, j);
-            const int vs = acquire();
-            issue_pv(Slot<0>{}, vs, j);
-            int kn = 0;
-            if (j + 2 < nb) {
-              kn = acquire();
-              issue_s(Slot<0>{}, kn, j + 2);
-            }
-            wait_p(Slot<1>{}, j);
-            issue_pv(Slot<1>{}, vs, j);
-            release(vs);
-            if (j + 2 < nb) {
-              issue_s(Slot<1>{}, kn, j + 2);
-              release(kn);
-            }
-          }
-        } else {
-          int sl = acquire();
-          issue_s(Slot<0>{}, sl, 0);
-          release(sl);
-          if (jb.a1) {
-            sl = acquire();
-            issue_s(Slot<1>{}, sl, 0);
-            release(sl);
-          }
-          if (nb > 1) {
-            sl = acquire();
-            issue_s(Slot<0>{}, sl, 1);
-            release(sl);
-            if (jb.a1) {
-              sl = acquire();
-              issue_s(Slot<1>{}, sl, 1);
-              release(sl);
-            }
-          }
-          for (int j = 0; j < nb; ++j) {
-            wait_p(Slot<0>{}, j);
-            sl = acquire();
-            issue_pv(Slot<0>{}, sl, j);
-            release(sl);
-            if (j + 2 < nb) {
-              sl = acquire();
-              issue_s(Slot<0>{}, sl, j + 2);
-              release(sl);
-            }
-            if (jb.a1) {
-              wait_p(Slot<1>{}, j);
-              sl = acquire();
-              issue_pv(Slot<1>{}, sl, j);
-              release(sl);
-              if (j + 2 < nb) {
-                sl = acquire();
-                issue_s(Slot<1>{}, sl, j + 2);
-                release(sl);
-              }
-            }
-          }
-        }
-        ++n_j0;
-        if (jb.a1) ++n_j1;
       }
+      ++n_j;
     }
   } else if (warp < kWarpEpi) {
     // ---------------------------------------------------------------- softmax warps: thread = query row = TMEM lane

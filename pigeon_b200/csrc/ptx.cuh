@@ -64,14 +64,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// Out of line: the report costs ~50 instructions per call site otherwise, and the attention kernels have dozens of waits
+// whose code competes for the instruction cache.
+static __device__ __noinline__ void mbar_deadlock(uint32_t bar, uint32_t parity) {
+  printf("pigeon_b200: mbarrier dead-lock block=(%d,%d,%d) thread=%d bar=%u parity=%u\n",
+         blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
+  __trap();
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > PG_SPIN_LIMIT) {
-      printf("pigeon_b200: mbarrier dead-lock block=(%d,%d,%d) thread=%d bar=%u parity=%u\n",
-             blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
+    if (++spins > PG_SPIN_LIMIT) mbar_deadlock(smem_u32(bar), parity);
   }
 }
 
