@@ -52,9 +52,14 @@ def _nvcc() -> str:
     return exe
 
 
+def _flags() -> list:
+    """NVCC_FLAGS plus the debugging extras of PG_NVCC_EXTRA (e.g. -DPG_DEADLOCK_REPORT)."""
+    return NVCC_FLAGS + os.environ.get("PG_NVCC_EXTRA", "").split()
+
+
 def _digest() -> str:
     h = hashlib.sha256()
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(_flags()).encode())
     files = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted(INCLUDE.glob("*.h"))
     for f in files:
         h.update(f.name.encode())
@@ -79,7 +84,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(src: str) -> Path:
         obj = OBJ_DIR / (Path(src).stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *_flags(), "-I", str(INCLUDE), "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         r = subprocess.run(cmd, capture_output=True, text=True)

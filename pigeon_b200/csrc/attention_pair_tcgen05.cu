@@ -281,137 +281,11 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
   // register budget: 512 threads start with 128 each; the softmax warps take the share the other roles do not need
   // (8*168 + 4*96 + 4*80 = 16*128 per lane).  setmaxnreg must be executed with the SAME value by all four warps of a
   // warpgroup: warps 12-15 (TMA, MMA, two idle) form one.
-  if (warp >= kWarpTma) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
   // K/V ring protocol.  A job's stream of a tile is 1 + nb slots: {K_0, K_1}, then {V_j, K_(j+2)} for j = 0 .. nb-1.  Two tiles
   // of one (view, head) share ONE stream (both MMA warps read every slot and commit once each); otherwise the two streams are
   // interleaved slot by slot (the owner commits twice), or there is a single stream (tile 1 absent).  Every role derives the
   // same ring positions from the job list.
-  if (warp > kWarpMma + 1) {
-    // idle warp of the last warpgroup
-  } else if (warp == kWarpTma) {
-    // ---------------------------------------------------------------- TMA producer (warp-uniform, one elected lane issues)
-    if (blockIdx.x < n_jobs) {
-      uint32_t pos = 0;              // ring position
-      uint32_t nq0 = 0, nq1 = 0;
-      // slot contents: rows [r_a, +64) at column col_a, and (if col_b >= 0) rows [r_b, +64) at column col_b
-      auto load_slot = [&](int col_a, int r_a, int col_b, int r_b) {
-        const int slot = pos % kSlots;
-        mbar_wait(&bars->kv_empty[slot], ((pos / kSlots) & 1) ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&bars->kv_full[slot], col_b >= 0 ? kSlotBytes : kSubBytes);
-          tma_load_2d(smem_kv + slot * kSlotBytes, &tmap_qkv, &bars->kv_full[slot], col_a, r_a);
-          if (col_b >= 0) tma_load_2d(smem_kv + slot * kSlotBytes + kSubBytes, &tmap_qkv, &bars->kv_full[slot], col_b, r_b);
-        }
-        __syncwarp();
-        ++pos;
-      };
-      auto load_q = [&](auto I_, const Job& jb) {
-        constexpr int I = decltype(I_)::value;
-        uint32_t& nq = I ? nq1 : nq0;
-        mbar_wait(&bars->qs_empty[I], (nq & 1) ^ 1);
-        if (elect_one()) {
-          const int col = (I ? jb.h1 : jb.h0) * kHeadDim, row = jb.view * S + (I ? jb.t1 : jb.t0) * kBlock;
-          mbar_arrive_expect_tx(&bars->qs_full[I], kQBytes);
-          tma_load_2d(smem_q + I * kQBytes, &tmap_qkv, &bars->qs_full[I], col, row);
-          tma_load_2d(smem_q + I * kQBytes + kSubBytes, &tmap_qkv, &bars->qs_full[I], col, row + kSub);
-        }
-        __syncwarp();
-        ++nq;
-      };
-      {
-        const Job j0 = decode_job(blockIdx.x, args);
-        load_q(Slot<0>{}, j0);
-        if (j0.a1) load_q(Slot<1>{}, j0);
-      }
-      for (int job = blockIdx.x; job < n_jobs; job += stride) {
-        const Job jb = decode_job(job, args);
-        const int row0 = jb.view * S;
-        const int nstream = (jb.shared || !jb.a1) ? 1 : 2;
-        for (int step = 0; step <= nb; ++step) {          // step 0 = {K_0, K_1}; step j + 1 = {V_j, K_(j+2)}
-          for (int t = 0; t < nstream; ++t) {
-            const int h = t ? jb.h1 : jb.h0;
-            const int kc = args.hidden + h * kHeadDim, vc = 2 * args.hidden + h * kHeadDim;
-            if (step == 0) load_slot(kc, row0, nb > 1 ? kc : -1, row0 + kSub);
-            else load_slot(vc, row0 + (step - 1) * kSub, step + 1 < nb ? kc : -1, row0 + (step + 1) * kSub);
-          }
-          if (step == 1 && job + stride < n_jobs) {       // the next job's Q tiles, once this job's first blocks are on their way
-            const Job jn = decode_job(job + stride, args);
-            load_q(Slot<0>{}, jn);
-            if (jn.a1) load_q(Slot<1>{}, jn);
-          }
-        }
-      }
-    }
-  } else if (warp >= kWarpMma) {
-    // ---------------------------------------------------------------- MMA issuers: warp 13 -> tile 0, warp 14 -> tile 1
-    // (warp-uniform; one elected lane issues)
-    const int I = warp - kWarpMma;
-    uint32_t pos = 0;                                    // ring position at the start of the current job
-    uint32_t n_p0 = 0, n_p1 = 0;                         // p_ready phases consumed, per S buffer
-    uint32_t n_j = 0;                                    // jobs this tile took part in
-    // smem descriptors of a slot's first (offset 0) / second (offset 8 KB) block: K is K-major (rows of 128 B, k-step = 32 B),
-    // V is MN-major (row = kv index, k-step = 16 rows)
-    const uint64_t k_desc0 = make_smem_desc(smem_u32(smem_kv), 16, 1024, kLayoutSw128);
-    const uint64_t v_desc0 = make_smem_desc(smem_u32(smem_kv), 1024, 1024, kLayoutSw128);
-    const uint32_t idesc_s = make_idesc_f16(kBlock, kSub, 0, 0);
-    const uint32_t idesc_s_last = make_idesc_f16(kBlock, last_n, 0, 0);
-    const uint32_t idesc_pv = make_idesc_f16(kBlock, kHeadDim, 0, 1);    // B (= V) is MN-major
-    const uint32_t s_base = tmem_base + kColS + 128 * I, o_base = tmem_base + kColO + 64 * I, q_base = tmem_base + kColQ + 32 * I;
-    auto issue_s = [&](uint64_t kd, int j) {   // S_I[j & 1] = Q_I K_j^T   (inside an elected region)
-      const uint32_t idesc = (j == nb - 1) ? idesc_s_last : idesc_s;
-      const uint32_t d = s_base + kSub * (j & 1);
-#pragma unroll
-      for (int k = 0; k < kHeadDim / 16; ++k) umma_ts(d, q_base + 8 * k, kd + 2 * k, idesc, k != 0);
-      tc_commit(&bars->s_full[I][j & 1]);
-    };
-    for (int job = blockIdx.x; job < n_jobs; job += stride) {
-      const Job jb = decode_job(job, args);
-      const int nstream = (jb.shared || !jb.a1) ? 1 : 2;
-      const uint32_t pos_job = pos;
-      pos += (uint32_t)(nb + 1) * nstream;
-      if (I == 1 && !jb.a1) continue;
-      const uint32_t first = (nstream == 2) ? I : 0;
-      const int ncommit = jb.shared ? 1 : 2;
-      mbar_wait(&bars->q_ready[I], n_j & 1);
-      for (int step = 0; step <= nb; ++step) {
-        const uint32_t p = pos_job + first + (uint32_t)step * nstream;
-        const int slot = p % kSlots;
-        const int j = step - 1;
-        if (step > 0) {
-          uint32_t& n_p = (j & 1) ? n_p1 : n_p0;
-          mbar_wait(&bars->p_ready[I][j & 1], n_p & 1);
-          ++n_p;
-          if (j == 0) mbar_wait(&bars->o_free[I], (n_j & 1) ^ 1);   // the previous job's O_I was read out
-        }
-        mbar_wait(&bars->kv_full[slot], (p / kSlots) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t d0 = (uint64_t)(slot * (kSlotBytes >> 4)), d1 = d0 + (kSubBytes >> 4);
-          if (step == 0) {
-            issue_s(k_desc0 + d0, 0);
-            if (nb > 1) issue_s(k_desc0 + d1, 1);
-          } else {
-            const uint64_t vd = v_desc0 + d0;
-            const uint32_t a = s_base + kSub * (j & 1);       // P_I[j & 1] (packed fp16 over the S buffer)
-            umma_ts(o_base, a, vd, idesc_pv, j != 0);
-            if (j == nb - 1) {
-              for (int k = 1; k < last_n / 16; ++k) umma_ts(o_base, a + 8 * k, vd + 128 * k, idesc_pv, 1);
-            } else {
-#pragma unroll
-              for (int k = 1; k < kSub / 16; ++k) umma_ts(o_base, a + 8 * k, vd + 128 * k, idesc_pv, 1);
-            }
-            tc_commit(&bars->pv_done[I]);
-            if (j == nb - 1) tc_commit(&bars->o_full[I]);
-            if (j + 2 < nb) issue_s(k_desc0 + d1, j + 2);
-          }
-          tc_commit(&bars->kv_empty[slot]);
-          if (ncommit == 2) tc_commit(&bars->kv_empty[slot]);
-        }
-        __syncwarp();
-      }
-      ++n_j;
-    }
-  } else if (warp < kWarpEpi) {
+  if (warp < kWarpEpi) {
     // ---------------------------------------------------------------- softmax warps: thread = query row = TMEM lane
     asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     const int i = warp >> 2;        // tile slot
@@ -614,7 +488,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
       if (lane == 0) mbar_arrive(&bars->l_ready[i]);
       ++n_job;
     }
-  } else {
+  } else if (warp < kWarpTma) {
     // ---------------------------------------------------------------- epilogue warps: O / l -> fp16 -> global
     asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     const int wq = warp & 3;
@@ -660,6 +534,136 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
         }
       }
     }
+  // (every warpgroup's setmaxnreg sits inside its own role branch, and no role calls a non-inlined function: ptxas compiles a
+  // shared callee for the smallest budget and then holds every caller to it)
+  } else {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+   if (warp > kWarpMma + 1) {
+    // idle warp of the last warpgroup
+   } else if (warp == kWarpTma) {
+    // ---------------------------------------------------------------- TMA producer (warp-uniform, one elected lane issues)
+    if (blockIdx.x < n_jobs) {
+      uint32_t pos = 0;              // ring position
+      uint32_t nq0 = 0, nq1 = 0;
+      // slot contents: rows [r_a, +64) at column col_a, and (if col_b >= 0) rows [r_b, +64) at column col_b
+      auto load_slot = [&](int col_a, int r_a, int col_b, int r_b) {
+        const int slot = pos % kSlots;
+        mbar_wait(&bars->kv_empty[slot], ((pos / kSlots) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bars->kv_full[slot], col_b >= 0 ? kSlotBytes : kSubBytes);
+          tma_load_2d(smem_kv + slot * kSlotBytes, &tmap_qkv, &bars->kv_full[slot], col_a, r_a);
+          if (col_b >= 0) tma_load_2d(smem_kv + slot * kSlotBytes + kSubBytes, &tmap_qkv, &bars->kv_full[slot], col_b, r_b);
+        }
+        __syncwarp();
+        ++pos;
+      };
+      auto load_q = [&](auto I_, const Job& jb) {
+        constexpr int I = decltype(I_)::value;
+        uint32_t& nq = I ? nq1 : nq0;
+        mbar_wait(&bars->qs_empty[I], (nq & 1) ^ 1);
+        if (elect_one()) {
+          const int col = (I ? jb.h1 : jb.h0) * kHeadDim, row = jb.view * S + (I ? jb.t1 : jb.t0) * kBlock;
+          mbar_arrive_expect_tx(&bars->qs_full[I], kQBytes);
+          tma_load_2d(smem_q + I * kQBytes, &tmap_qkv, &bars->qs_full[I], col, row);
+          tma_load_2d(smem_q + I * kQBytes + kSubBytes, &tmap_qkv, &bars->qs_full[I], col, row + kSub);
+        }
+        __syncwarp();
+        ++nq;
+      };
+      {
+        const Job j0 = decode_job(blockIdx.x, args);
+        load_q(Slot<0>{}, j0);
+        if (j0.a1) load_q(Slot<1>{}, j0);
+      }
+      for (int job = blockIdx.x; job < n_jobs; job += stride) {
+        const Job jb = decode_job(job, args);
+        const int row0 = jb.view * S;
+        const int nstream = (jb.shared || !jb.a1) ? 1 : 2;
+        for (int step = 0; step <= nb; ++step) {          // step 0 = {K_0, K_1}; step j + 1 = {V_j, K_(j+2)}
+          for (int t = 0; t < nstream; ++t) {
+            const int h = t ? jb.h1 : jb.h0;
+            const int kc = args.hidden + h * kHeadDim, vc = 2 * args.hidden + h * kHeadDim;
+            if (step == 0) load_slot(kc, row0, nb > 1 ? kc : -1, row0 + kSub);
+            else load_slot(vc, row0 + (step - 1) * kSub, step + 1 < nb ? kc : -1, row0 + (step + 1) * kSub);
+          }
+          if (step == 1 && job + stride < n_jobs) {       // the next job's Q tiles, once this job's first blocks are on their way
+            const Job jn = decode_job(job + stride, args);
+            load_q(Slot<0>{}, jn);
+            if (jn.a1) load_q(Slot<1>{}, jn);
+          }
+        }
+      }
+    }
+   } else {
+    // ---------------------------------------------------------------- MMA issuers: warp 13 -> tile 0, warp 14 -> tile 1
+    // (warp-uniform; one elected lane issues)
+    const int I = warp - kWarpMma;
+    uint32_t pos = 0;                                    // ring position at the start of the current job
+    uint32_t n_p0 = 0, n_p1 = 0;                         // p_ready phases consumed, per S buffer
+    uint32_t n_j = 0;                                    // jobs this tile took part in
+    // smem descriptors of a slot's first (offset 0) / second (offset 8 KB) block: K is K-major (rows of 128 B, k-step = 32 B),
+    // V is MN-major (row = kv index, k-step = 16 rows)
+    const uint64_t k_desc0 = make_smem_desc(smem_u32(smem_kv), 16, 1024, kLayoutSw128);
+    const uint64_t v_desc0 = make_smem_desc(smem_u32(smem_kv), 1024, 1024, kLayoutSw128);
+    const uint32_t idesc_s = make_idesc_f16(kBlock, kSub, 0, 0);
+    const uint32_t idesc_s_last = make_idesc_f16(kBlock, last_n, 0, 0);
+    const uint32_t idesc_pv = make_idesc_f16(kBlock, kHeadDim, 0, 1);    // B (= V) is MN-major
+    const uint32_t s_base = tmem_base + kColS + 128 * I, o_base = tmem_base + kColO + 64 * I, q_base = tmem_base + kColQ + 32 * I;
+    auto issue_s = [&](uint64_t kd, int j) {   // S_I[j & 1] = Q_I K_j^T   (inside an elected region)
+      const uint32_t idesc = (j == nb - 1) ? idesc_s_last : idesc_s;
+      const uint32_t d = s_base + kSub * (j & 1);
+#pragma unroll
+      for (int k = 0; k < kHeadDim / 16; ++k) umma_ts(d, q_base + 8 * k, kd + 2 * k, idesc, k != 0);
+      tc_commit(&bars->s_full[I][j & 1]);
+    };
+    for (int job = blockIdx.x; job < n_jobs; job += stride) {
+      const Job jb = decode_job(job, args);
+      const int nstream = (jb.shared || !jb.a1) ? 1 : 2;
+      const uint32_t pos_job = pos;
+      pos += (uint32_t)(nb + 1) * nstream;
+      if (I == 1 && !jb.a1) continue;
+      const uint32_t first = (nstream == 2) ? I : 0;
+      const int ncommit = jb.shared ? 1 : 2;
+      mbar_wait(&bars->q_ready[I], n_j & 1);
+      for (int step = 0; step <= nb; ++step) {
+        const uint32_t p = pos_job + first + (uint32_t)step * nstream;
+        const int slot = p % kSlots;
+        const int j = step - 1;
+        if (step > 0) {
+          uint32_t& n_p = (j & 1) ? n_p1 : n_p0;
+          mbar_wait(&bars->p_ready[I][j & 1], n_p & 1);
+          ++n_p;
+          if (j == 0) mbar_wait(&bars->o_free[I], (n_j & 1) ^ 1);   // the previous job's O_I was read out
+        }
+        mbar_wait(&bars->kv_full[slot], (p / kSlots) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t d0 = (uint64_t)(slot * (kSlotBytes >> 4)), d1 = d0 + (kSubBytes >> 4);
+          if (step == 0) {
+            issue_s(k_desc0 + d0, 0);
+            if (nb > 1) issue_s(k_desc0 + d1, 1);
+          } else {
+            const uint64_t vd = v_desc0 + d0;
+            const uint32_t a = s_base + kSub * (j & 1);       // P_I[j & 1] (packed fp16 over the S buffer)
+            umma_ts(o_base, a, vd, idesc_pv, j != 0);
+            if (j == nb - 1) {
+              for (int k = 1; k < last_n / 16; ++k) umma_ts(o_base, a + 8 * k, vd + 128 * k, idesc_pv, 1);
+            } else {
+#pragma unroll
+              for (int k = 1; k < kSub / 16; ++k) umma_ts(o_base, a + 8 * k, vd + 128 * k, idesc_pv, 1);
+            }
+            tc_commit(&bars->pv_done[I]);
+            if (j == nb - 1) tc_commit(&bars->o_full[I]);
+            if (j + 2 < nb) issue_s(k_desc0 + d1, j + 2);
+          }
+          tc_commit(&bars->kv_empty[slot]);
+          if (ncommit == 2) tc_commit(&bars->kv_empty[slot]);
+        }
+        __syncwarp();
+      }
+      ++n_j;
+    }
+   }
   }
 
   tc_fence_before();

@@ -64,18 +64,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-// Out of line: the report costs ~50 instructions per call site otherwise, and the attention kernels have dozens of waits
-// whose code competes for the instruction cache.
-static __device__ __noinline__ void mbar_deadlock(uint32_t bar, uint32_t parity) {
-  printf("pigeon_b200: mbarrier dead-lock block=(%d,%d,%d) thread=%d bar=%u parity=%u\n",
-         blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
-  __trap();
-}
-
+// A dead-locked wait traps (see PG_SPIN_LIMIT).  The report (block, thread, barrier address, parity) is compiled in only
+// with -DPG_DEADLOCK_REPORT (PG_NVCC_EXTRA="-DPG_DEADLOCK_REPORT" python -m pigeon_b200._build --force): inlined at every
+// wait it costs ~50 instructions per site and instruction-cache misses in the attention kernels (dozens of waits), and as
+// a __noinline__ function it made ptxas hold EVERY warp role to the smallest setmaxnreg budget of the kernel (measured:
+// the softmax warps of attention_pair_kernel spilled their loop state at 77 registers instead of using 132).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > PG_SPIN_LIMIT) mbar_deadlock(smem_u32(bar), parity);
+    if (++spins > PG_SPIN_LIMIT) {
+#ifdef PG_DEADLOCK_REPORT
+      printf("pigeon_b200: mbarrier dead-lock block=(%d,%d,%d) thread=%d bar=%u parity=%u\n",
+             blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+#endif
+      __trap();
+    }
   }
 }
 
