@@ -297,7 +297,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
     const uint32_t q_tmem = tmem_base + lane_base + kColQ + 32 * i;
     const uint32_t q_smem = smem_u32(smem_q + i * kQBytes) + row * 128;
     const float c = args.scale_log2;
-    uint32_t n_q = 0, n_s0 = 0, n_s1 = 0, n_blk = 0, n_job = 0;
+    uint32_t n_q = 0, n_blk = 0, n_job = 0;   // n_blk: running block count of this tile (block g lives in S buffer g & 1)
     bool q_done = false;
 
     // staged Q tile (128-byte swizzle: 16-byte chunk ch of row r sits at chunk ch ^ (r & 7)) -> TMEM A operand
@@ -353,13 +353,9 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
       };
 
       for (int j = 0; j < nb; ++j) {
-        const int b = j & 1;
+        const int b = n_blk & 1;
         const uint32_t s_tmem = s_tmem0 + kSub * b;
-        {
-          uint32_t& n_s = b ? n_s1 : n_s0;
-          mbar_wait(&bars->s_full[i][b], n_s & 1);
-          ++n_s;
-        }
+        mbar_wait(&bars->s_full[i][b], (n_blk >> 1) & 1);
         tc_fence_after();
         if (j == nb - 1 && next_active) {   // every S_i MMA of this job has retired: Q_i may be replaced
           copy_q();
@@ -375,27 +371,22 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
           // ---- a block of 64 valid key columns: one branch-free basic block, P held in registers until the sum is checked
           uint32_t pk[32];
           float bs;
-          bool do_max = (j == 0);
+          bool exact = false;   // m is known to be >= every logit of this block
+          if (j == 0) {
+            // reference maximum of a job: of the first 16 logits only (any reference works as long as the block sums stay
+            // below kSumLimit; the class token's key is column 0)
+            uint32_t r[16];
+            tmem_ld16p(s_tmem, r);
+            tmem_ld_wait16(r);
+            const float b0 = fmax3(fmax3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2])),
+                                   __uint_as_float(r[3]), __uint_as_float(r[4]));
+            const float b1 = fmax3(fmax3(__uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7])),
+                                   __uint_as_float(r[8]), __uint_as_float(r[9]));
+            const float b2 = fmax3(fmax3(__uint_as_float(r[10]), __uint_as_float(r[11]), __uint_as_float(r[12])),
+                                   __uint_as_float(r[13]), __uint_as_float(r[14]));
+            m = fmax3(b0, b1, fmaxf(b2, __uint_as_float(r[15])));
+          }
           for (;;) {
-            if (do_max) {   // exact row maximum of the block (first block of a job, or a block whose sum overflowed)
-              float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                uint32_t r[32];
-                tmem_ld32(s_tmem + 32 * h, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int x = 0; x < 32; x += 8) {
-                  b0 = fmax3(b0, __uint_as_float(r[x]), __uint_as_float(r[x + 1]));
-                  b1 = fmax3(b1, __uint_as_float(r[x + 2]), __uint_as_float(r[x + 3]));
-                  b2 = fmax3(b2, __uint_as_float(r[x + 4]), __uint_as_float(r[x + 5]));
-                  b3 = fmax3(b3, __uint_as_float(r[x + 6]), __uint_as_float(r[x + 7]));
-                }
-              }
-              const float m_new = fmaxf(fmaxf(m, fmaxf(b0, b1)), fmaxf(b2, b3));
-              if (j > 0) rescale(m_new);
-              m = m_new;
-            }
             const float mc = m * c;
             const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
             float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
@@ -411,8 +402,23 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
               exp_chunk<POLY>(rb, pk + 8 * (ch + 1), c2, nmc2, acc0, acc1);
             }
             bs = (acc0.x + acc0.y) + (acc1.x + acc1.y);
-            if (!do_max && __any_sync(0xffffffffu, !(bs < kSumLimit))) {   // some P may not fit fp16: exact path
-              do_max = true;
+            if (!exact && __any_sync(0xffffffffu, !(bs < kSumLimit))) {
+              // rare: some P may not fit fp16.  Take the exact maximum of the block, rescale O and l, redo the block.
+              float b0 = -INFINITY, b1 = -INFINITY;
+              for (int h = 0; h < 4; ++h) {
+                uint32_t r[16];
+                tmem_ld16p(s_tmem + 16 * h, r);
+                tmem_ld_wait16(r);
+#pragma unroll
+                for (int x = 0; x < 16; x += 4) {
+                  b0 = fmax3(b0, __uint_as_float(r[x]), __uint_as_float(r[x + 1]));
+                  b1 = fmax3(b1, __uint_as_float(r[x + 2]), __uint_as_float(r[x + 3]));
+                }
+              }
+              const float m_new = fmax3(m, b0, b1);
+              if (j > 0) rescale(m_new);
+              m = m_new;
+              exact = true;
               continue;
             }
             break;
@@ -599,8 +605,9 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
     // (warp-uniform; one elected lane issues)
     const int I = warp - kWarpMma;
     uint32_t pos = 0;                                    // ring position at the start of the current job
-    uint32_t n_p0 = 0, n_p1 = 0;                         // p_ready phases consumed, per S buffer
+    uint32_t g = 0;                                      // running block count of this tile: block g lives in S buffer g & 1
     uint32_t n_j = 0;                                    // jobs this tile took part in
+    bool pre = false;                                    // S of this job's first two blocks was issued during the previous job
     // smem descriptors of a slot's first (offset 0) / second (offset 8 KB) block: K is K-major (rows of 128 B, k-step = 32 B),
     // V is MN-major (row = kv index, k-step = 16 rows)
     const uint64_t k_desc0 = make_smem_desc(smem_u32(smem_kv), 16, 1024, kLayoutSw128);
@@ -609,12 +616,13 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
     const uint32_t idesc_s_last = make_idesc_f16(kBlock, last_n, 0, 0);
     const uint32_t idesc_pv = make_idesc_f16(kBlock, kHeadDim, 0, 1);    // B (= V) is MN-major
     const uint32_t s_base = tmem_base + kColS + 128 * I, o_base = tmem_base + kColO + 64 * I, q_base = tmem_base + kColQ + 32 * I;
-    auto issue_s = [&](uint64_t kd, int j) {   // S_I[j & 1] = Q_I K_j^T   (inside an elected region)
+    // S[buf] = Q_I K_j^T, j = block index inside its job   (inside an elected region)
+    auto issue_s = [&](uint64_t kd, int j, uint32_t buf) {
       const uint32_t idesc = (j == nb - 1) ? idesc_s_last : idesc_s;
-      const uint32_t d = s_base + kSub * (j & 1);
+      const uint32_t d = s_base + kSub * buf;
 #pragma unroll
       for (int k = 0; k < kHeadDim / 16; ++k) umma_ts(d, q_base + 8 * k, kd + 2 * k, idesc, k != 0);
-      tc_commit(&bars->s_full[I][j & 1]);
+      tc_commit(&bars->s_full[I][buf]);
     };
     for (int job = blockIdx.x; job < n_jobs; job += stride) {
       const Job jb = decode_job(job, args);
@@ -624,15 +632,26 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
       if (I == 1 && !jb.a1) continue;
       const uint32_t first = (nstream == 2) ? I : 0;
       const int ncommit = jb.shared ? 1 : 2;
-      mbar_wait(&bars->q_ready[I], n_j & 1);
-      for (int step = 0; step <= nb; ++step) {
+      // the next job of this tile: its first S blocks are issued while this job's last two blocks are in the softmax warps
+      bool has_next = (job + stride < n_jobs) && nb >= 2;
+      uint32_t next_p = 0;
+      int next_commit = 0;
+      if (has_next) {
+        const Job jn = decode_job(job + stride, args);
+        if (I == 1 && !jn.a1) has_next = false;
+        const int ns = (jn.shared || !jn.a1) ? 1 : 2;
+        next_p = pos + ((ns == 2) ? I : 0);
+        next_commit = jn.shared ? 1 : 2;
+      }
+      for (int step = pre ? 1 : 0; step <= nb; ++step) {
         const uint32_t p = pos_job + first + (uint32_t)step * nstream;
         const int slot = p % kSlots;
         const int j = step - 1;
-        if (step > 0) {
-          uint32_t& n_p = (j & 1) ? n_p1 : n_p0;
-          mbar_wait(&bars->p_ready[I][j & 1], n_p & 1);
-          ++n_p;
+        if (step == 0) {
+          mbar_wait(&bars->q_ready[I], n_j & 1);
+        } else {
+          const uint32_t gb = g + j;
+          mbar_wait(&bars->p_ready[I][gb & 1], (gb >> 1) & 1);
           if (j == 0) mbar_wait(&bars->o_free[I], (n_j & 1) ^ 1);   // the previous job's O_I was read out
         }
         mbar_wait(&bars->kv_full[slot], (p / kSlots) & 1);
@@ -640,11 +659,11 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
         if (elect_one()) {
           const uint64_t d0 = (uint64_t)(slot * (kSlotBytes >> 4)), d1 = d0 + (kSubBytes >> 4);
           if (step == 0) {
-            issue_s(k_desc0 + d0, 0);
-            if (nb > 1) issue_s(k_desc0 + d1, 1);
+            issue_s(k_desc0 + d0, 0, g & 1);
+            if (nb > 1) issue_s(k_desc0 + d1, 1, (g + 1) & 1);
           } else {
             const uint64_t vd = v_desc0 + d0;
-            const uint32_t a = s_base + kSub * (j & 1);       // P_I[j & 1] (packed fp16 over the S buffer)
+            const uint32_t a = s_base + kSub * ((g + j) & 1);       // P (packed fp16 over the S buffer)
             umma_ts(o_base, a, vd, idesc_pv, j != 0);
             if (j == nb - 1) {
               for (int k = 1; k < last_n / 16; ++k) umma_ts(o_base, a + 8 * k, vd + 128 * k, idesc_pv, 1);
@@ -654,13 +673,36 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const PairAr
             }
             tc_commit(&bars->pv_done[I]);
             if (j == nb - 1) tc_commit(&bars->o_full[I]);
-            if (j + 2 < nb) issue_s(k_desc0 + d1, j + 2);
+            if (j + 2 < nb) issue_s(k_desc0 + d1, j + 2, (g + j) & 1);
           }
           tc_commit(&bars->kv_empty[slot]);
           if (ncommit == 2) tc_commit(&bars->kv_empty[slot]);
         }
         __syncwarp();
+        if (has_next && j >= nb - 2) {
+          // block j's buffer is free again (its P V is issued): the next job's block j - (nb - 2) goes there.  Q of the next job
+          // reaches TMEM when the softmax warps start this job's last block.
+          const int slot_n = next_p % kSlots;
+          if (j == nb - 2) {
+            mbar_wait(&bars->q_ready[I], (n_j + 1) & 1);
+            mbar_wait(&bars->kv_full[slot_n], (next_p / kSlots) & 1);
+            tc_fence_after();
+          }
+          if (elect_one()) {
+            const uint64_t d0 = (uint64_t)(slot_n * (kSlotBytes >> 4));
+            if (j == nb - 2) {
+              issue_s(k_desc0 + d0, 0, (g + nb) & 1);
+            } else {
+              issue_s(k_desc0 + d0 + (kSubBytes >> 4), 1, (g + nb + 1) & 1);
+              tc_commit(&bars->kv_empty[slot_n]);
+              if (next_commit == 2) tc_commit(&bars->kv_empty[slot_n]);
+            }
+          }
+          __syncwarp();
+        }
       }
+      pre = has_next;
+      g += nb;
       ++n_j;
     }
    }
