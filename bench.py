@@ -85,12 +85,13 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_models(device, seed=0):
+def build_models(device, seed=0, fold_layernorm=True):
     from pigeon_b200 import CLIPVisionTower, ProtoRefiner, SuperGuessr, VitDims, synthetic
     dims = VitDims()
     tower = CLIPVisionTower(dims)
     tower.load_state_dict(synthetic.random_vit_state_dict(dims, seed=seed))
     tower.max_views_per_pass = 1024
+    tower.fold_layernorm = fold_layernorm
     cells = synthetic.synthetic_geocells(NUM_CELLS, 0)
     model = SuperGuessr(tower, panorama=True, freeze_base=True, num_candidates=NUM_CAND, geocells=cells).to(device).eval()
     bank = synthetic.synthetic_bank(NUM_CELLS, NUM_PROTOS, dims.hidden, seed=2, members_mean=0.0, empty_cells=5)
@@ -113,7 +114,7 @@ def run_ours(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     peaks = load_peaks()
     B = args.batch
-    model, refiner, dims, cells, bank = build_models(dev)
+    model, refiner, dims, cells, bank = build_models(dev, fold_layernorm=not args.no_ln_fold)
     g = torch.Generator().manual_seed(1 + rank)
     # synthetic panoramas, fp16, (B, 12, 336, 336): view index fastest inside a sample (dataset_preprocessing.py:199-200)
     px_host = torch.randn(B, 12, dims.image_size, dims.image_size, generator=g, dtype=torch.float32).half().pin_memory()
@@ -354,6 +355,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="four-view samples per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=4, help="four-view images in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ln-fold", action="store_true", help="A/B: run the LayerNorm kernels instead of the folded epilogues")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -96,6 +96,7 @@ class CLIPVisionTower(nn.Module):
         self._engine: Optional[VitEngine] = None
         self._packed_version = None
         self.max_views_per_pass = 256
+        self.fold_layernorm = True   # LayerNorm applied in the GEMM epilogues (False = LayerNorm kernels; A/B switch)
 
     # HF: `CLIPVisionModel.base_model` is the model itself
     @property
@@ -128,8 +129,10 @@ class CLIPVisionTower(nn.Module):
         v = self._weights_version()
         if self._engine is None or self._packed_version != v:
             sd = {k: t.detach() for k, t in self.state_dict().items()}
-            if self._engine is None or self._engine.device != p0.device:
-                self._engine = VitEngine(sd, self.dims, device=p0.device, max_views_per_pass=self.max_views_per_pass)
+            if (self._engine is None or self._engine.device != p0.device
+                    or self._engine.fold_layernorm != bool(self.fold_layernorm)):
+                self._engine = VitEngine(sd, self.dims, device=p0.device, max_views_per_pass=self.max_views_per_pass,
+                                         fold_layernorm=self.fold_layernorm)
             else:
                 self._engine.load_state_dict(sd)
             self._packed_version = v

@@ -60,8 +60,11 @@ class VitEngine:
     """B200 execution engine of HF CLIPVisionTransformer.forward(...).last_hidden_state (+ token mean)."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], dims: VitDims, device: torch.device | str = "cuda",
-                 max_views_per_pass: int = 256):
+                 max_views_per_pass: int = 256, fold_layernorm: bool = True):
+        """fold_layernorm: feed the GEMMs the raw fp16 residual row and apply LayerNorm in their epilogues (no LayerNorm
+        kernel, no normalised copy in HBM; see csrc/gemm.h EPI_F16_LN_*).  False keeps the LayerNorm kernels (A/B switch)."""
         self.dims = dims
+        self.fold_layernorm = bool(fold_layernorm)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise PigeonB200Error("VitEngine runs on a CUDA device only (no CPU path)")
@@ -113,6 +116,20 @@ class VitEngine:
             L.ln2_g, L.ln2_b = ptr(f32(p + "layer_norm2.weight")), ptr(f32(p + "layer_norm2.bias"))
             L.w_fc1, L.b_fc1 = ptr(f16(sd[p + "mlp.fc1.weight"])), ptr(f32(p + "mlp.fc1.bias"))
             L.w_fc2, L.b_fc2 = ptr(f16(sd[p + "mlp.fc2.weight"])), ptr(f32(p + "mlp.fc2.bias"))
+            if self.fold_layernorm:
+                # LN(x) W^T + b = rstd * (x (gamma*W)^T - mu * rowsum(gamma*W)) + (b + W beta): the tensor cores see the raw
+                # row x and W' = gamma * W; rowsum is taken over the fp16 values of W' so that acc - mu * rowsum is exact.
+                def fold(w, b, g, beta):
+                    w32 = w.detach().to(dev, torch.float32)
+                    wf = f16(w32 * g[None, :])
+                    cs = wf.float().sum(dim=1).contiguous()
+                    bf = (b.detach().to(dev, torch.float32) + w32 @ beta).contiguous()
+                    self._keep += [cs, bf]
+                    return ptr(wf), ptr(bf), ptr(cs)
+                g1, be1 = sd[p + "layer_norm1.weight"].detach().to(dev, torch.float32), sd[p + "layer_norm1.bias"].detach().to(dev, torch.float32)
+                g2, be2 = sd[p + "layer_norm2.weight"].detach().to(dev, torch.float32), sd[p + "layer_norm2.bias"].detach().to(dev, torch.float32)
+                L.w_qkv_ln, L.b_qkv_ln, L.cs_qkv = fold(torch.cat([wq, wk, wv], dim=0), torch.cat([bq, bk, bv], dim=0), g1, be1)
+                L.w_fc1_ln, L.b_fc1_ln, L.cs_fc1 = fold(sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"], g2, be2)
 
         cfg = _lib.VitConfig(d.image_size, d.patch_size, d.hidden, d.heads, d.intermediate, d.layers, d.ln_eps,
                              d.patch_k_pad)
