@@ -282,7 +282,8 @@ int pg_layernorm_f16(const float* x, void* y, const float* gamma, const float* b
 int pg_attention_f16(const void* qkv, void* out, int32_t n_views, int32_t seq, int32_t heads, void* stream);
 /* Measurement aid: the same op with the kernel chosen explicitly.  variant 0 = "pair" kernel (persistent, two query tiles per
  * CTA, KV blocks of 128, Q in tensor memory; poly = eighths of the exponentials evaluated on the FMA pipe, < 0 = default),
- * variant 1 = first-generation kernel (one tile per CTA, KV blocks of 32).  lse2 may be NULL. */
+ * variant 1 = first-generation kernel (one tile per CTA, KV blocks of 32), variant 2 = "split" kernel (the pair kernel with
+ * sixteen softmax warps: two independent column halves per S block, merged in the epilogue).  lse2 may be NULL. */
 int pg_attention_f16_variant(const void* qkv, void* out, float* lse2, int32_t n_views, int32_t seq, int32_t heads,
                              int32_t variant, int32_t poly, void* stream);
 /* Same, also writing lse2 f32 [n_views*heads, seq] (log2-sum-exp of the scaled logits) for the backward pass. */

@@ -26,6 +26,7 @@ SOURCES = [
     "gemm2_tcgen05.cu",
     "attention_tcgen05.cu",
     "attention_pair_tcgen05.cu",
+    "attention_split_tcgen05.cu",
     "vit_misc.cu",
     "head.cu",
     "refiner.cu",

@@ -14,7 +14,12 @@ int attention_f16(const void* qkv, void* out, int n_views, int seq, int heads, c
 int attention_pair_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream, float* lse2,
                        int poly);
 
-// Explicit kernel choice for A/B measurements: variant 0 = pair kernel (poly in eighths, < 0 = default), 1 = first-generation
+// Third-generation forward kernel (attention_split_tcgen05.cu): the pair kernel's job structure with SIXTEEN softmax warps
+// (every S block split into two independent column halves with their own accumulators, merged in the epilogue; Q in smem).
+int attention_split_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream, float* lse2,
+                        int poly);
+
+// Explicit kernel choice for A/B measurements: variant 0 = pair kernel, 2 = split kernel (poly in eighths, < 0 = default), 1 = first-generation
 // kernel (poly 0 / 4 / 2 = none / every 4th / every 2nd group).
 int attention_f16_variant(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream, float* lse2,
                           int variant, int poly);

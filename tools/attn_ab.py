@@ -3,7 +3,8 @@
     python tools/attn_ab.py check            # every variant vs a torch fp32 softmax at several geometries (exit 1 on mismatch)
     python tools/attn_ab.py time [views]     # alternating timings of the variants on the same inputs (L2 flushed)
 
-Variants: (0, p) = pair kernel with p eighths of the exponentials on the FMA pipe, (1, 0) = first-generation kernel.
+Variants: (0, p) = pair kernel with p eighths of the exponentials on the FMA pipe, (2, p) = split kernel, (1, 0) = first-generation
+kernel.
 """
 import os
 import sys
@@ -14,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pigeon_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda:0")
-VARIANTS = [(1, 0), (0, 0), (0, 2), (0, 3), (0, 4)]
+VARIANTS = [(1, 0), (0, 2), (2, 0), (2, 2), (2, 3), (2, 4)]
 
 
 def reference(qkv, n_views, seq, heads):
@@ -27,14 +28,12 @@ def reference(qkv, n_views, seq, heads):
 def check():
     bad = 0
     geoms = [(1, 128, 1), (1, 64, 2), (2, 577, 2), (3, 200, 1), (1, 577, 16), (2, 65, 1), (1, 129, 1), (1, 17, 4),
-             (3, 577, 3), (2, 256, 5), (40, 577, 16)]
+             (3, 577, 3), (2, 256, 5), (40, 577, 16), (2, 32, 2), (1, 33, 3), (2, 96, 1), (1, 100, 2), (1, 48, 1)]
     for (n_views, seq, heads) in geoms:
         g = torch.Generator(device="cpu").manual_seed(seq * 3 + heads)
         qkv = (torch.randn(n_views * seq, 3 * heads * 64, generator=g) * 1.5).half().to(dev)
         ref = reference(qkv, n_views, seq, heads)
         for (var, poly) in VARIANTS:
-            if var == 1 and poly:
-                continue
             out = ops.attention_f16(qkv, n_views, seq, heads, variant=var, poly=poly)
             torch.cuda.synchronize()
             err = ((out.float() - ref).norm() / ref.norm()).item()
@@ -55,11 +54,12 @@ def check():
         bad += not ok
         print(f"growing logits variant {var} poly {poly}: rel err {err:.2e} {'ok' if ok else 'FAIL'}", flush=True)
     # run-to-run determinism of the default variant
-    a = ops.attention_f16(qkv, n_views, seq, heads, variant=0)
-    b = ops.attention_f16(qkv, n_views, seq, heads, variant=0)
-    if not torch.equal(a, b):
-        bad += 1
-        print("pair kernel is not run-to-run deterministic: FAIL")
+    for var in (0, 2):
+        a = ops.attention_f16(qkv, n_views, seq, heads, variant=var)
+        b = ops.attention_f16(qkv, n_views, seq, heads, variant=var)
+        if not torch.equal(a, b):
+            bad += 1
+            print(f"variant {var} is not run-to-run deterministic: FAIL")
     return bad
 
 
