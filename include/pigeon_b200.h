@@ -197,6 +197,11 @@ typedef struct pg_vit_grads {
   float *d_pos_emb;   /* [tokens, hidden] */
   float *d_pre_ln_g, *d_pre_ln_b;
   const pg_vit_layer_bwd* layers_host;  /* [layers] */
+  /* Optional (may be NULL): layers + 1 cudaEvent_t handles.  pg_vit_backward records entry l on its stream as soon as the
+   * weight gradients of encoder layer l are complete for this call, entry `layers` after the embedding gradients — so that
+   * the caller can start the NCCL all-reduce of a layer's gradient bucket on a side stream while the layers below are
+   * still in their backward (reference: DDP's bucketed overlap, training/train_eval_loop.py:192,216).  NULL entries skipped. */
+  void* const* layer_done_events;
 } pg_vit_grads;
 
 size_t pg_vit_backward_workspace_bytes(const pg_vit* h, int32_t n_views);
@@ -221,6 +226,18 @@ typedef struct pg_refiner_bank {
 } pg_refiner_bank;
 
 size_t pg_refiner_workspace_bytes(int64_t B, int32_t topk, int32_t D, int32_t num_cells);
+/* The two stages of pg_refiner_forward as separate calls, for a CELL-SHARDED bank across GPUs (rank r holds the geocells with
+ * cell % world == r, every other cell range empty): pg_refiner_scan on every rank over ALL queries -> per (query, candidate)
+ * partials best_logit f32 [B, topk] (-100000 where this rank does not hold the cell), best_lnglat f32 [B, topk, 2],
+ * best_proto i32 [B, topk]; the caller merges the ranks' partials by owner (one small all-gather), then pg_refiner_finalize
+ * (temperature softmax x candidate probabilities, haversine gate, arg-max: reference models/proto_refiner.py:187-231). */
+int pg_refiner_scan(const pg_refiner_bank* bank, const float* emb, int64_t B, int32_t V, const int64_t* cand_idx,
+                    int32_t cand_stride, int32_t topk, void* workspace, size_t workspace_bytes, float* best_logit,
+                    float* best_lnglat, int32_t* best_proto, void* stream);
+int pg_refiner_finalize(const float* best_logit, const float* best_lnglat, const double* init_lnglat,
+                        const int64_t* cand_idx, const float* cand_prob, int32_t cand_stride, int64_t B, int32_t topk,
+                        float temperature, double max_refinement_km, float* out_lnglat, int64_t* out_cell, int32_t* choice,
+                        void* stream);
 /* Measurement aid: scan schedule of pg_refiner_forward for this process: 0 = automatic (cell-major when geocells are shared
  * by >= 2 (query, candidate) pairs on average), 1 = query-major, 2 = cell-major.  Same results either way. */
 int pg_refiner_set_schedule(int32_t mode);

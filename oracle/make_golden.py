@@ -293,7 +293,8 @@ def refiner_fixture(tmp, name, C, P, D, B, kc, topk, members, T, maxref, seed):
     import models.proto_refiner as pr
     bank = synthetic.synthetic_bank(C, P, D, seed=seed, members_mean=members, empty_cells=3)
     n_train = bank["data_emb"].shape[0]
-    ds_path, csv_path = os.path.join(tmp, f"hf_{name}"), os.path.join(tmp, f"protos_{name}.csv")
+    tag = name or f"anon{seed}"
+    ds_path, csv_path = os.path.join(tmp, f"hf_{tag}"), os.path.join(tmp, f"protos_{tag}.csv")
     # training embeddings as the reference stores them: (4, D) per sample (4-view panoramas) -> the refiner
     # averages views itself (:370-371).  Views are the stored mean +- a perturbation that cancels exactly.
     rng = np.random.default_rng(seed + 1)
@@ -360,10 +361,136 @@ def refiner_fixture(tmp, name, C, P, D, B, kc, topk, members, T, maxref, seed):
         ref.max_refinement = maxref
         _, ll, cell = ref(qt, initial_preds=torch.from_numpy(init), candidate_cells=candt, candidate_probs=probst)
         _, ll_np, cell_np = ref(qt, initial_preds=torch.from_numpy(init), candidate_cells=candt, candidate_probs=None)
-    np.savez_compressed(os.path.join(OUT, f"{name}.npz"),
-                        meta=json.dumps(dict(C=C, P=P, D=D, B=B, kc=kc, topk=topk, members=members, T=T, maxref=maxref, seed=seed)),
-                        emb=q, init=init, cand=cand, probs=probs, preds_LLH=ll.numpy(), preds_geocell=cell.numpy(),
-                        preds_LLH_noprob=ll_np.numpy(), preds_geocell_noprob=cell_np.numpy(), **{f"bank_{k}": v for k, v in packed.items()})
+    if name is not None:
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"),
+                            meta=json.dumps(dict(C=C, P=P, D=D, B=B, kc=kc, topk=topk, members=members, T=T, maxref=maxref, seed=seed)),
+                            emb=q, init=init, cand=cand, probs=probs, preds_LLH=ll.numpy(), preds_geocell=cell.numpy(),
+                            preds_LLH_noprob=ll_np.numpy(), preds_geocell_noprob=cell_np.numpy(), **{f"bank_{k}": v for k, v in packed.items()})
+    return ref, packed
+
+
+def _reference_function(path, fn_name, namespace):
+    """The UNMODIFIED source of one function of a reference file whose module cannot be imported here (accelerate /
+    tensorboard are not installed), executed in `namespace` (stand-ins for the names the body uses from those imports)."""
+    import ast
+    src = open(os.path.join("/root/reference", path)).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == fn_name)
+    exec(compile(ast.Module(body=[node], type_ignores=[]), os.path.join("/root/reference", path), "exec"), namespace)
+    return namespace[fn_name]
+
+
+def loops_fixture(tmp):
+    """The callers of the hot path: the bodies of `evaluate_model` (training/train_eval_loop.py:35-161) and
+    `compute_embeddings` (preprocessing/embed.py:16-43) run as they are, over the unmodified SuperGuessr / ProtoRefiner /
+    CLIPEmbedding modules — pins batch order, ragged last batch, what is concatenated and what reaches `metrics` / disk."""
+    import logging
+    from typing import Any, Callable
+    from torch.utils.data import DataLoader, Dataset
+    from models.super_guessr import SuperGuessr
+    from models.clip_embedder import CLIPEmbedding
+    C, D, N, bs, topk = 1000, 128, 11, 4, 5
+    ref, packed = refiner_fixture(tmp, None, C=C, P=1500, D=D, B=8, kc=10, topk=topk, members=1.5, T=1.6, maxref=1e6, seed=90)
+    W, b = head_weights(C, D, seed=91)
+    g = torch.Generator().manual_seed(92)
+    cand, _ = synthetic.synthetic_candidates(N, topk, C, seed=93)
+    emb = torch.from_numpy(synthetic.synthetic_queries(packed, cand, views=4, seed=94))          # [N, 4, D]
+    # make the head prefer each sample's candidate cells, so that retrieval works on non-empty cells
+    labels = synthetic.synthetic_geocells(N, 95)
+    labels_clf = cand[:, 0].copy()
+
+    class DS(Dataset):
+        def __len__(self):
+            return N
+
+        def __getitem__(self, i):
+            if isinstance(i, str):
+                return {"labels": labels, "labels_clf": labels_clf}[i]
+            return dict(embedding=emb[i], labels=torch.tensor(labels[i]), labels_clf=torch.tensor(labels_clf[i]))
+
+    class Writer:
+        def __init__(self):
+            self.scalars = {}
+
+        def add_scalar(self, k, v, step):
+            self.scalars[k] = float(v)
+
+    captured = {}
+
+    def metrics(results):
+        captured["results"] = results
+        return {"Geocell_accuracy": float((results[1] == results[7]).mean())}
+
+    def loader(ds, batch_size, **kw):
+        return DataLoader(ds, batch_size, shuffle=kw.get("shuffle", False), num_workers=0)
+
+    ns = dict(nn=torch.nn, Dataset=Dataset, Callable=Callable, Any=Any, TrainingArguments=object, ProtoRefiner=object,
+              SummaryWriter=Writer, DataLoader=loader, tqdm=lambda x, **kw: x, torch=torch, np=np,
+              logger=logging.getLogger("reference"), BenchmarkDataset=type("BenchmarkDataset", (), {}))
+    evaluate_model = _reference_function("training/train_eval_loop.py", "evaluate_model", ns)
+    with rs.chdir(tmp):
+        sg = SuperGuessr(None, panorama=True, num_candidates=topk, embed_dim=D).eval()
+    with torch.no_grad():
+        sg.cell_layer.weight.copy_(W)
+        sg.cell_layer.bias.copy_(b)
+        for i in range(N):                       # the candidate cells of sample i score highest for its embedding
+            sg.cell_layer.weight[cand[i]] += emb[i].mean(0) * (1.0 + 0.01 * torch.arange(topk))[:, None]
+
+    class Args:
+        per_device_eval_batch_size = bs
+
+    out = {}
+    for tag, refiner in (("refined", ref), ("plain", None)):
+        w = Writer()
+        with rs.device_redirect():
+            ret = evaluate_model(sg, DS(), metrics, Args(), refiner=refiner, writer=w)
+        r = captured["results"]
+        out.update({f"eval_{tag}_preds": r[0], f"eval_{tag}_preds_geocell": r[1], f"eval_{tag}_top5": r[5],
+                    f"eval_{tag}_return": np.float64(ret), f"eval_{tag}_loss_logged": np.float64(w.scalars["Loss/val"])})
+        assert r[2] is None and r[3] is None and r[4] is None and np.array_equal(r[6], labels) and np.array_equal(r[7], labels_clf)
+
+    # ---- compute_embeddings over the unmodified CLIPEmbedding (tiny random-init HF tower)
+    dims = VitDims(image_size=56, patch_size=14, hidden=256, heads=4, intermediate=512, layers=2)
+    sd = synthetic.random_vit_state_dict(dims, seed=96, std=0.05)
+    ce = object.__new__(CLIPEmbedding)
+    torch.nn.Module.__init__(ce)
+    ce.clip_model = hf_model(dims, sd)
+    ce.device, ce.panorama = "cpu", False
+    n_img, ebs = 9, 3                            # equal batches: np.save of the reference's LIST of batches needs them
+    px = torch.randn(n_img, 3, 56, 56, generator=torch.Generator().manual_seed(97))
+    order = torch.tensor([4, 0, 7, 2, 8, 1, 6, 3, 5])    # dataset order != index order: the consumer sorts by the saved index
+
+    class EDS(Dataset):
+        def __len__(self):
+            return n_img
+
+        def __getitem__(self, i):
+            return px[order[i]], order[i]
+
+    class Acc:
+        is_local_main_process = True
+
+        def gather(self, x):
+            return x
+
+    ens = dict(np=np, tqdm=lambda x, **kw: x, logger=logging.getLogger("reference"), AutoModel=object, DataLoader=DataLoader,
+               Accelerator=object, enumerate=enumerate)
+    compute_embeddings = _reference_function("preprocessing/embed.py", "compute_embeddings", ens)
+    os.makedirs(os.path.join(tmp, "data", "landmark_embeddings"), exist_ok=True)
+    with rs.chdir(tmp), torch.no_grad():
+        compute_embeddings("golden", ce, DataLoader(EDS(), ebs, shuffle=False), Acc())
+    saved = np.load(os.path.join(tmp, "data", "landmark_embeddings", "golden.npy"))
+    saved_idx = np.load(os.path.join(tmp, "data", "landmark_embeddings", "golden_indices.npy"))
+    # what preprocessing/dataset_preprocessing.py:296-300 makes of the two files
+    arg = np.argsort(saved_idx.flatten()[:n_img])
+    consumer = saved.reshape((-1, dims.hidden))[arg]
+    out.update(embed_saved=saved, embed_saved_indices=saved_idx, embed_consumer_rows=consumer)
+    np.savez_compressed(os.path.join(OUT, "loops.npz"),
+                        meta=json.dumps(dict(C=C, D=D, N=N, bs=bs, topk=topk, head_seed=91, bank=dict(C=C, P=1500, D=D, members=1.5, seed=90),
+                                             embed=dict(n_img=n_img, bs=ebs, sd_seed=96, px_seed=97, std=0.05, order=order.tolist(),
+                                                        dims=dict(image_size=56, patch_size=14, hidden=256, heads=4, intermediate=512, layers=2)))),
+                        emb=emb.numpy(), labels=labels, labels_clf=labels_clf, cand=cand, head_w=sg.cell_layer.weight.detach().numpy(),
+                        head_b=sg.cell_layer.bias.detach().numpy(), centroids=sg.lla_geocells.detach().numpy(),
+                        **{f"bank_{k}": v for k, v in packed.items()}, **out)
 
 
 def tower_train_fixtures(tmp):
@@ -389,6 +516,8 @@ def main():
             preprocess_fixture()
         if "tower" in only:
             tower_train_fixtures(tmp)
+        if "loops" in only:
+            loops_fixture(tmp)
         return
     geo_fixture()
     head_fixture(tmp)
@@ -401,6 +530,7 @@ def main():
     vit_fixture(tmp, "vit_large_pano", VitDims(), sd_seed=0, n_samples=2, panorama=True, px_seed=2, std=0.02)
     refiner_fixture(tmp, "refiner_count1", C=40, P=400, D=128, B=48, kc=10, topk=5, members=0.0, T=1.6, maxref=1000, seed=50)
     refiner_fixture(tmp, "refiner_members", C=30, P=200, D=128, B=40, kc=12, topk=12, members=5.0, T=0.6, maxref=100000, seed=60)
+    loops_fixture(tmp)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

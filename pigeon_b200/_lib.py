@@ -49,7 +49,8 @@ class VitLayerBwd(C.Structure):
 
 class VitGrads(C.Structure):
     _fields_ = [("d_patch_w", c_void_p), ("d_class_emb", c_void_p), ("d_pos_emb", c_void_p), ("d_pre_ln_g", c_void_p),
-                ("d_pre_ln_b", c_void_p), ("layers_host", C.POINTER(VitLayerBwd))]
+                ("d_pre_ln_b", c_void_p), ("layers_host", C.POINTER(VitLayerBwd)),
+                ("layer_done_events", C.POINTER(c_void_p))]
 
 
 class VitWeights(C.Structure):
@@ -109,6 +110,10 @@ SIGNATURES = {
                                      c_int32, c_int32, c_float, c_double, c_void_p, c_size_t, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pg_refiner_set_schedule": (c_int32, [c_int32]),
+    "pg_refiner_scan": (c_int32, [C.POINTER(RefinerBank), c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_void_p,
+                                  c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pg_refiner_finalize": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32,
+                                      c_float, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pg_bank_build": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "pg_profile_begin": (None, []),
     "pg_profile_end": (c_int32, []),

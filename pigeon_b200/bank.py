@@ -113,3 +113,36 @@ def bank_from_proto_rows(cells: Sequence[Optional[Sequence[dict]]], data_emb, da
                 proto_lnglat=np.asarray(pll, np.float32).reshape(-1, 2), proto_count=np.asarray(cnt, np.int32),
                 member_off=np.asarray(moff, np.int64), member_idx=np.asarray(midx, np.int64),
                 data_emb=emb.numpy(), data_lnglat=np.asarray(data_lnglat, np.float32))
+
+
+def shard_bank(arrays: Dict[str, np.ndarray], rank: int, world: int) -> Dict[str, np.ndarray]:
+    """Cell-sharded copy of a CSR bank for `rank` of `world`: geocell c stays iff c % world == rank, every
+    other cell becomes an empty range (the reference's `protos[cell] is None`), so a scan over the shard answers "empty cell"
+    (-100000) for the pairs it does not own.  Prototype rows, member lists and the member embeddings they point at are
+    compacted to the owned cells: the HBM bytes per rank are 1/world of the bank."""
+    cell_off = np.asarray(arrays["cell_off"], np.int64)
+    C = cell_off.shape[0] - 1
+    own = (np.arange(C) % world) == rank
+    sizes = np.where(own, cell_off[1:] - cell_off[:-1], 0)
+    new_off = np.zeros(C + 1, np.int64)
+    np.cumsum(sizes, out=new_off[1:])
+    keep = np.concatenate([np.arange(cell_off[c], cell_off[c + 1]) for c in range(C) if own[c]] or
+                          [np.zeros(0, np.int64)]).astype(np.int64)
+    member_off = np.asarray(arrays["member_off"], np.int64)
+    member_idx = np.asarray(arrays["member_idx"], np.int64)
+    m_sizes = member_off[keep + 1] - member_off[keep] if keep.size else np.zeros(0, np.int64)
+    new_moff = np.zeros(keep.size + 1, np.int64)
+    np.cumsum(m_sizes, out=new_moff[1:])
+    m_keep = np.concatenate([np.arange(member_off[p], member_off[p + 1]) for p in keep] or
+                            [np.zeros(0, np.int64)]).astype(np.int64)
+    old_rows = member_idx[m_keep] if m_keep.size else np.zeros(0, np.int64)
+    rows, inv = np.unique(old_rows, return_inverse=True) if old_rows.size else (np.zeros(0, np.int64), np.zeros(0, np.int64))
+    data_emb = np.asarray(arrays["data_emb"])
+    data_ll = np.asarray(arrays["data_lnglat"])
+    return dict(cell_off=new_off,
+                proto_emb=np.ascontiguousarray(np.asarray(arrays["proto_emb"])[keep]),
+                proto_lnglat=np.ascontiguousarray(np.asarray(arrays["proto_lnglat"])[keep]),
+                proto_count=np.ascontiguousarray(np.asarray(arrays["proto_count"])[keep]),
+                member_off=new_moff, member_idx=inv.astype(np.int64),
+                data_emb=np.ascontiguousarray(data_emb[rows]) if rows.size else data_emb[:0],
+                data_lnglat=np.ascontiguousarray(data_ll[rows]) if rows.size else data_ll[:0])

@@ -362,6 +362,59 @@ int pg_refiner_forward(const pg_refiner_bank* bank, const float* emb, int64_t B,
                           choice, stream);
 }
 
+// Cell-sharded retrieval: a rank whose bank holds only some geocells (the others empty) scans all queries
+// against ITS cells; pairs whose geocell it does not hold come back as "empty cell" (-100000).  After the per-pair partials
+// of all ranks are merged by owner, pg_refiner_finalize runs the temperature softmax / gate / arg-max on the merged values.
+int pg_refiner_scan(const pg_refiner_bank* bank, const float* emb, int64_t B, int32_t V, const int64_t* cand_idx,
+                    int32_t cand_stride, int32_t topk, void* workspace, size_t workspace_bytes, float* best_logit,
+                    float* best_lnglat, int32_t* best_proto, void* stream_) {
+  if (!bank || !emb || !cand_idx || !workspace || !best_logit || !best_lnglat || !best_proto) {
+    set_last_error("pg_refiner_scan: null argument"); return 1;
+  }
+  if (B <= 0) return 0;
+  if (topk <= 0 || topk > cand_stride) { set_last_error("pg_refiner_scan: \"topk\" (%d) must be <= number of candidates (%d)", topk, cand_stride); return 1; }
+  if (V <= 0 || bank->dim % 128 || bank->dim > 1024) { set_last_error("pg_refiner_scan: bad V=%d / dim=%d", V, bank->dim); return 1; }
+  if (workspace_bytes < pg_refiner_workspace_bytes(B, topk, bank->dim, bank->num_cells)) { set_last_error("pg_refiner_scan: workspace too small"); return 1; }
+  const int sms = sm_count();
+  if (sms < 0) return 1;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  Carver c(workspace);
+  float* q = reinterpret_cast<float*>(c.take((size_t)B * bank->dim * 4));
+  c.take((size_t)B * topk * 4);
+  c.take((size_t)B * topk * 2 * 4);
+  c.take((size_t)B * topk * 4);
+  void* sort_ws = c.take(refiner_sort_workspace_bytes(bank->num_cells, (long)B * topk));
+  RefinerBank rb;
+  rb.num_cells = bank->num_cells; rb.dim = bank->dim;
+  rb.cell_off = reinterpret_cast<const long long*>(bank->cell_off);
+  rb.proto_emb = bank->proto_emb; rb.proto_lnglat = bank->proto_lnglat; rb.proto_count = bank->proto_count;
+  rb.member_off = reinterpret_cast<const long long*>(bank->member_off);
+  rb.member_idx = reinterpret_cast<const long long*>(bank->member_idx);
+  rb.data_emb = bank->data_emb; rb.data_lnglat = bank->data_lnglat;
+  if (refiner_pool(emb, q, B, V, bank->dim, stream)) return 1;
+  const int sched = refiner_schedule();
+  const bool cell_major = sched == 2 || (sched == 0 && (long)B * topk >= 2L * bank->num_cells);
+  if (cell_major)
+    return refiner_scan_cell_major(rb, q, reinterpret_cast<const long long*>(cand_idx), cand_stride, B, topk, sort_ws,
+                                   best_logit, best_lnglat, best_proto, sms, stream);
+  return refiner_scan(rb, q, reinterpret_cast<const long long*>(cand_idx), cand_stride, B, topk, best_logit, best_lnglat,
+                      best_proto, sms, stream);
+}
+
+int pg_refiner_finalize(const float* best_logit, const float* best_lnglat, const double* init_lnglat,
+                        const int64_t* cand_idx, const float* cand_prob, int32_t cand_stride, int64_t B, int32_t topk,
+                        float temperature, double max_refinement_km, float* out_lnglat, int64_t* out_cell, int32_t* choice,
+                        void* stream) {
+  if (!best_logit || !best_lnglat || !init_lnglat || !cand_idx || !cand_prob || !out_lnglat || !out_cell) {
+    set_last_error("pg_refiner_finalize: null argument"); return 1;
+  }
+  if (B <= 0) return 0;
+  if (topk <= 0 || topk > cand_stride) { set_last_error("pg_refiner_finalize: bad topk %d / stride %d", topk, cand_stride); return 1; }
+  return refiner_finalize(best_logit, best_lnglat, reinterpret_cast<const long long*>(cand_idx), cand_prob, cand_stride,
+                          init_lnglat, B, topk, temperature, max_refinement_km, out_lnglat,
+                          reinterpret_cast<long long*>(out_cell), choice, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int pg_bank_build(const float* data_views, int64_t N, int32_t V, int32_t D, const int64_t* member_off,
                   const int64_t* member_idx, int64_t P, float* data_mean_out, float* proto_emb_out, void* stream) {
   if (!data_views || !member_off || !member_idx || !data_mean_out || !proto_emb_out || N <= 0 || V <= 0 || D <= 0 || P < 0) {

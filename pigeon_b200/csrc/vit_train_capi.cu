@@ -240,6 +240,10 @@ int pg_vit_backward(pg_vit* h, const pg_vit_saved* sv, const float* d_emb, int32
     if (layernorm_backward(w.t32, s.x0, L.ln1_g, w.g, 1, train ? B.d_ln1_g : nullptr, train ? B.d_ln1_b : nullptr, w.g16,
                            rows, H, c.ln_eps, sms, st))
       return 1;                                                                                // g = dX0 (+ bf16 copy)
+    if (train && gr->layer_done_events && gr->layer_done_events[l]) {   // layer l's gradient bucket is final for this call
+      cudaError_t e = cudaEventRecord(reinterpret_cast<cudaEvent_t>(gr->layer_done_events[l]), st);
+      if (e != cudaSuccess) { set_last_error("pg_vit_backward: cudaEventRecord(layer %d): %s", l, cudaGetErrorString(e)); return 1; }
+    }
   }
 
   if (emb_train) {
@@ -252,6 +256,10 @@ int pg_vit_backward(pg_vit* h, const pg_vit_saved* sv, const float* d_emb, int32
     if (wgrad(w.t32, SRC_F32, H, H, sv->im2col, SRC_F16, c.patch_k_pad, c.patch_k_pad, (long)n_views * np, gr->d_patch_w, w,
               sms, st, np, h->tokens, 1))
       return 1;
+    if (gr->layer_done_events && gr->layer_done_events[c.layers]) {
+      cudaError_t e = cudaEventRecord(reinterpret_cast<cudaEvent_t>(gr->layer_done_events[c.layers]), st);
+      if (e != cudaSuccess) { set_last_error("pg_vit_backward: cudaEventRecord(embeddings): %s", cudaGetErrorString(e)); return 1; }
+    }
   }
   return 0;
 }

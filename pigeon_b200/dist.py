@@ -66,3 +66,17 @@ def all_gather_rows(tensors: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]
         res[n] = piece
         off += nbytes
     return res
+
+
+def merge_partials_by_owner(gathered: Dict[str, torch.Tensor], cand_cells: torch.Tensor, world: int) -> Dict[str, torch.Tensor]:
+    """Cell-sharded retrieval: `gathered[name]` is the rank-ordered concatenation [world * B, topk, ...] of every rank's
+    per-(query, candidate) partials; the partial of pair (b, j) that counts is the one of the rank holding geocell
+    cand_cells[b, j], i.e. rank cand_cells[b, j] % world (bank.shard_bank).  Returns [B, topk, ...] tensors."""
+    B, k = cand_cells.shape
+    owner = torch.remainder(cand_cells, world).to(torch.int64)            # [B, k]
+    out = {}
+    for name, t in gathered.items():
+        t = t.reshape((world, B) + tuple(t.shape[1:]))
+        idx = owner.reshape((1, B, k) + (1,) * (t.dim() - 3)).expand((1,) + tuple(t.shape[1:]))
+        out[name] = torch.gather(t, 0, idx)[0]
+    return out

@@ -60,6 +60,51 @@ def attention_f16(qkv: torch.Tensor, n_views: int, seq: int, heads: int, variant
     return out
 
 
+def refiner_scan(bank: "DeviceBank", emb: torch.Tensor, cand_idx: torch.Tensor, topk: int):
+    """Scan stage only (cell-sharded banks): per (query, candidate) partials (best_logit [B, topk], best_lnglat
+    [B, topk, 2], best_proto [B, topk]); pairs whose geocell this bank does not hold come back as -100000 / (0, 0) / -1."""
+    import ctypes as C
+    if emb.dim() == 2:
+        emb = emb.unsqueeze(1)
+    emb = emb.to(torch.float32).contiguous()
+    cand_idx = cand_idx.to(torch.int64).contiguous()
+    _need_cuda(emb, cand_idx)
+    B, V, D = emb.shape
+    if D != bank.dim:
+        raise PigeonB200Error(f"embedding dim {D} != bank dim {bank.dim}")
+    dev = emb.device
+    lib = load()
+    ws = torch.empty(lib.pg_refiner_workspace_bytes(B, topk, D, bank.num_cells), dtype=torch.uint8, device=dev)
+    bl = torch.empty((B, topk), dtype=torch.float32, device=dev)
+    bll = torch.empty((B, topk, 2), dtype=torch.float32, device=dev)
+    bp = torch.empty((B, topk), dtype=torch.int32, device=dev)
+    check(lib.pg_refiner_scan(C.byref(bank.c_struct), ptr(emb), B, V, ptr(cand_idx), cand_idx.shape[1], topk, ptr(ws),
+                              ws.numel(), ptr(bl), ptr(bll), ptr(bp), current_stream_ptr()), "pg_refiner_scan")
+    return bl, bll, bp
+
+
+def refiner_finalize(best_logit: torch.Tensor, best_lnglat: torch.Tensor, init_lnglat: torch.Tensor,
+                     cand_idx: torch.Tensor, cand_prob: torch.Tensor, topk: int, temperature: float,
+                     max_refinement_km: float):
+    """Final stage on merged partials -> (preds_LLH f32 [B, 2], preds_geocell i64 [B], choice i32 [B])."""
+    best_logit = best_logit.to(torch.float32).contiguous()
+    best_lnglat = best_lnglat.to(torch.float32).contiguous()
+    init_lnglat = init_lnglat.to(torch.float64).contiguous()
+    cand_idx = cand_idx.to(torch.int64).contiguous()
+    cand_prob = cand_prob.to(torch.float32).contiguous()
+    _need_cuda(best_logit, best_lnglat, init_lnglat, cand_idx, cand_prob)
+    B = best_logit.shape[0]
+    dev = best_logit.device
+    out_ll = torch.empty((B, 2), dtype=torch.float32, device=dev)
+    out_cell = torch.empty((B,), dtype=torch.int64, device=dev)
+    choice = torch.empty((B,), dtype=torch.int32, device=dev)
+    check(load().pg_refiner_finalize(ptr(best_logit), ptr(best_lnglat), ptr(init_lnglat), ptr(cand_idx), ptr(cand_prob),
+                                     cand_idx.shape[1], B, topk, float(temperature), float(max_refinement_km),
+                                     ptr(out_ll), ptr(out_cell), ptr(choice), current_stream_ptr()),
+          "pg_refiner_finalize")
+    return out_ll, out_cell, choice
+
+
 def refiner_set_schedule(mode: int) -> None:
     """A/B switch of the refiner scan: 0 automatic, 1 query-major, 2 cell-major (same results)."""
     check(load().pg_refiner_set_schedule(int(mode)), "pg_refiner_set_schedule")

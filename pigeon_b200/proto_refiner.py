@@ -14,6 +14,7 @@ from torch import Tensor, nn
 from torch.nn.parameter import Parameter
 
 from . import bank as bank_mod
+from . import dist as dist_mod
 from . import ops
 from ._lib import PigeonB200Error
 from .config import DATASET_PATH, PROTO_PATH
@@ -24,7 +25,7 @@ class ProtoRefiner(nn.Module):
 
     def __init__(self, topk: int = 5, hedge: bool = False, max_refinement: int = 1000, temperature: float = 1.6,
                  proto_path: str = PROTO_PATH, dataset_path: str = DATASET_PATH, protos: Optional[object] = None,
-                 verbose: bool = False, device: str | torch.device = 'cuda'):
+                 verbose: bool = False, device: str | torch.device = 'cuda', shard_cells: bool = False):
         """Arguments as in the reference (:20-44).  `protos` may be
 
           * a dict of CSR arrays (layout of `pg_refiner_bank`; what `self.protos` of this class holds, so the
@@ -32,6 +33,10 @@ class ProtoRefiner(nn.Module):
           * the reference's own list (one entry per geocell: None or a per-cell dataset with lng / lat / count /
             indices / embedding rows) — then `dataset_path` must still point at the training embeddings;
           * None: the bank is built from `proto_path` + `dataset_path` like the reference constructor does.
+
+        `shard_cells` (extension, multi-GPU): under torch.distributed with world size W each rank keeps only the geocells
+        with cell % W == rank in HBM, scans every query against its own cells, and the per-candidate partials are
+        merged by owner through one small all-gather before the final stage — same outputs as the replicated bank.
         """
         super().__init__()
         if hedge:
@@ -41,6 +46,7 @@ class ProtoRefiner(nn.Module):
         self.hedge = hedge
         self.max_refinement = max_refinement
         self.verbose = verbose
+        self.shard_cells = bool(shard_cells)
         self._device = torch.device(device)
 
         if isinstance(protos, dict):
@@ -66,6 +72,7 @@ class ProtoRefiner(nn.Module):
     def __getstate__(self):  # device handles are rebuilt after unpickling (torch.save(refiner), evaluate.py:71)
         d = self.__dict__.copy()
         d['_bank'] = None
+        d.pop('_bank_world', None)
         return d
 
     def __str__(self):
@@ -82,7 +89,13 @@ class ProtoRefiner(nn.Module):
         if self._bank is None:
             if self._device.type != 'cuda':
                 raise PigeonB200Error("ProtoRefiner needs a CUDA device (no CPU path)")
-            self._bank = ops.DeviceBank(self._device, **self.protos)
+            arrays = self.protos
+            self._bank_world = 1
+            if self.shard_cells and dist_mod.is_distributed():
+                import torch.distributed as dist
+                self._bank_world = dist.get_world_size()
+                arrays = bank_mod.shard_bank(arrays, dist.get_rank(), self._bank_world)
+            self._bank = ops.DeviceBank(self._device, **arrays)
         return self._bank
 
     @torch.no_grad()
@@ -101,6 +114,9 @@ class ProtoRefiner(nn.Module):
             candidate_probs = torch.zeros(candidate_cells.shape, dtype=torch.float32, device=dev)
             candidate_probs[:, 0] = 1
         loss = 0 if self.training else None                                       # :151
+        if getattr(self, "_bank_world", 1) > 1:
+            return self._forward_sharded(bank, embedding, initial_preds.to(dev), candidate_cells, candidate_probs.to(dev),
+                                         loss, return_debug)
         res = ops.refiner_forward(bank, embedding, initial_preds.to(dev), candidate_cells, candidate_probs.to(dev),
                                   self.topk, float(self.temperature.item()), float(self.max_refinement),
                                   debug=return_debug or self.verbose)
@@ -110,3 +126,21 @@ class ProtoRefiner(nn.Module):
         if return_debug:
             return loss, res[0], res[1], res[2]
         return loss, res[0], res[1]
+
+    def _forward_sharded(self, bank, embedding, initial_preds, candidate_cells, candidate_probs, loss, return_debug):
+        """Cell-sharded bank: every rank holds the SAME queries (the gathered batch), scans them against its own geocells,
+        then one packed all-gather of the (B, topk, 3) partials, merge by owner, final stage on every rank."""
+        world = self._bank_world
+        cand = candidate_cells[:, : self.topk].to(torch.int64)
+        bl, bll, bp = ops.refiner_scan(bank, embedding, candidate_cells, self.topk)
+        gathered = dist_mod.all_gather_rows(dict(best_logit=bl, best_lnglat=bll))
+        merged = dist_mod.merge_partials_by_owner(gathered, cand, world)
+        ll, cell, choice = ops.refiner_finalize(merged["best_logit"], merged["best_lnglat"], initial_preds,
+                                                candidate_cells, candidate_probs, self.topk,
+                                                float(self.temperature.item()), float(self.max_refinement))
+        if self.verbose:
+            perc_changed = (choice != 0).sum() / choice.size(0)
+            print(f'Changed geocell predictions of {perc_changed * 100:.1f} % of guesses.')
+        if return_debug:
+            return loss, ll, cell, dict(best_logit=merged["best_logit"], best_lnglat=merged["best_lnglat"], choice=choice)
+        return loss, ll, cell

@@ -338,6 +338,8 @@ class SuperGuessr(nn.Module):
         head_trains = w.requires_grad
         flat = torch.zeros(Cc * D + Cc, dtype=torch.float32, device=dev)
         lib = load()
+        from . import dist as pdist
+        pdist_world = pdist.world_size()
         outs, loss_total = [], None
         mt_out, mt_loss, mt_grads = [], [0, 0, 0], None
         with torch.no_grad():
@@ -364,7 +366,8 @@ class SuperGuessr(nn.Module):
                     dpooled += mt[6]
                     mt_grads = mt[7] if mt_grads is None else [a + b_ for a, b_ in zip(mt_grads, mt[7])]
                 d_emb = (dpooled / V).repeat_interleave(V, dim=0) if V > 1 else dpooled      # backward of the view mean
-                tr.backward(d_emb)
+                # last chunk under torch.distributed: the gradient all-reduce rides behind this backward, bucket by bucket
+                tr.backward(d_emb, overlap_world=pdist_world if hi == B else 1)
                 part = loss.double() * (n / B)
                 loss_total = part if loss_total is None else loss_total + part
                 outs.append((h, emb))

@@ -161,9 +161,28 @@ class TowerTrainer:
                                              C.byref(self._saved), ptr(emb), current_stream_ptr()), "pg_vit_forward_train")
         return emb
 
+    def _buckets(self):
+        """Gradient buckets of the flat pending buffer in the order the backward completes them: encoder layers from the
+        top down, then the embeddings.  (event slot, first element, one past the last element)"""
+        g, d = self._pending_grads(), self.dims
+        base = self._pending_flat.data_ptr()
+        off = lambda t: (t.data_ptr() - base) // 4
+        out = []
+        emb_train, layers = self.layout()
+        for l in reversed(range(d.layers)):
+            if layers[l]:
+                out.append((l, off(g[f"{l}.ln1_g"]), off(g[f"{l}.b_fc2"]) + g[f"{l}.b_fc2"].numel()))
+        if emb_train:
+            out.append((d.layers, off(g["patch_w"]), off(g["pre_ln_b"]) + g["pre_ln_b"].numel()))
+        return out
+
     @torch.no_grad()
-    def backward(self, d_emb: torch.Tensor) -> None:
-        """d_emb f32 [n, hidden] for the views of the last forward; gradients accumulate in the pending buffers."""
+    def backward(self, d_emb: torch.Tensor, overlap_world: int = 1) -> None:
+        """d_emb f32 [n, hidden] for the views of the last forward; gradients accumulate in the pending buffers.
+
+        overlap_world > 1 (the LAST chunk of a micro-batch under torch.distributed): each layer's gradient bucket is summed
+        over the ranks by an NCCL all-reduce on a side stream as soon as pg_vit_backward reports the layer done, while the
+        layers below are still in their backward; `finalize` then only waits for the outstanding buckets."""
         d = self.dims
         n = self._saved_views
         if self._saved is None or d_emb.shape != (n, d.hidden):
@@ -185,12 +204,28 @@ class TowerTrainer:
             grads.d_patch_w, grads.d_class_emb, grads.d_pos_emb = g["patch_w"].data_ptr(), g["class_emb"].data_ptr(), g["pos_emb"].data_ptr()
             grads.d_pre_ln_g, grads.d_pre_ln_b = g["pre_ln_g"].data_ptr(), g["pre_ln_b"].data_ptr()
         grads.layers_host = lb
+        events, ev_arr = None, None
+        if overlap_world > 1:
+            if getattr(self, "_bucket_events", None) is None:
+                self._bucket_events = [torch.cuda.Event() for _ in range(d.layers + 1)]
+                for e in self._bucket_events:
+                    e.record()                                    # materialises the cudaEvent_t handle
+                self._side = torch.cuda.Stream(device=d_emb.device)
+            events = self._bucket_events
+            ev_arr = (C.c_void_p * (d.layers + 1))(*[e.cuda_event for e in events])
+            grads.layer_done_events = ev_arr
         need = int(self._lib.pg_vit_backward_workspace_bytes(eng._handle, n))
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = _aligned_empty(need, d_emb.device)
         check(self._lib.pg_vit_backward(eng._handle, C.byref(self._saved), ptr(d_emb), n, C.byref(grads), ptr(self._ws),
                                         self._ws.numel(), current_stream_ptr()), "pg_vit_backward")
+        if overlap_world > 1:
+            self._works = []
+            with torch.cuda.stream(self._side):
+                for slot, lo, hi in self._buckets():
+                    self._side.wait_event(events[slot])
+                    self._works.append(torch.distributed.all_reduce(self._pending_flat[lo:hi], async_op=True))
 
     @torch.no_grad()
     def finalize(self, world: int = 1) -> None:
@@ -199,7 +234,12 @@ class TowerTrainer:
             return
         g, d = self._pending, self.dims
         if world > 1:                                  # DDP: average of the per-rank gradients (train_eval_loop.py:192)
-            torch.distributed.all_reduce(self._pending_flat)
+            works, self._works = getattr(self, "_works", None), None
+            if works:                                  # buckets already in flight behind the last chunk's backward
+                for wk in works:
+                    wk.wait()                          # the current stream waits for the NCCL stream
+            else:
+                torch.distributed.all_reduce(self._pending_flat)
             self._pending_flat.mul_(1.0 / world)
         vm = self.tower.vision_model
 

@@ -152,6 +152,75 @@ def test_packed_all_gather_gloo_world2(tmp_path):
         assert p.returncode == 0, o
 
 
+def test_shard_bank_partitions_cells_and_members():
+    """bank.shard_bank: every geocell lives in exactly one shard (cell % world), prototype rows / member lists / member
+    embeddings are compacted consistently, the union of the shards is the bank."""
+    from pigeon_b200 import bank as bank_mod, synthetic
+    full = synthetic.synthetic_bank(37, 400, 128, seed=5, members_mean=3.0, empty_cells=3)
+    W = 4
+    C = full["cell_off"].shape[0] - 1
+    seen = np.zeros(C, np.int64)
+    total_p = 0
+    for r in range(W):
+        sh = bank_mod.shard_bank(full, r, W)
+        assert sh["cell_off"].shape == full["cell_off"].shape and sh["cell_off"][0] == 0
+        total_p += sh["proto_emb"].shape[0]
+        for c in range(C):
+            lo, hi = sh["cell_off"][c], sh["cell_off"][c + 1]
+            flo, fhi = full["cell_off"][c], full["cell_off"][c + 1]
+            if c % W != r:
+                assert hi == lo
+                continue
+            seen[c] += 1
+            assert hi - lo == fhi - flo
+            assert np.array_equal(sh["proto_emb"][lo:hi], full["proto_emb"][flo:fhi])
+            assert np.array_equal(sh["proto_lnglat"][lo:hi], full["proto_lnglat"][flo:fhi])
+            assert np.array_equal(sh["proto_count"][lo:hi], full["proto_count"][flo:fhi])
+            for k in range(hi - lo):       # member lists point at the same embeddings / labels after compaction
+                m_new = sh["member_idx"][sh["member_off"][lo + k]: sh["member_off"][lo + k + 1]]
+                m_old = full["member_idx"][full["member_off"][flo + k]: full["member_off"][flo + k + 1]]
+                assert np.array_equal(sh["data_emb"][m_new], full["data_emb"][m_old])
+                assert np.array_equal(sh["data_lnglat"][m_new], full["data_lnglat"][m_old])
+    assert (seen == 1).all() and total_p == full["proto_emb"].shape[0]
+
+
+GLOO_MERGE_WORKER = textwrap.dedent("""
+    import os, sys, torch, torch.distributed as dist
+    sys.path.insert(0, %r)
+    from pigeon_b200 import dist as pdist
+    rank, world = int(sys.argv[1]), 2
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=sys.argv[2], RANK=str(rank), WORLD_SIZE="2")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    B, k = 5, 3
+    g = torch.Generator().manual_seed(3)
+    cand = torch.randint(0, 11, (B, k), generator=g)
+    truth_logit = -torch.rand(B, k, generator=g)
+    truth_ll = torch.rand(B, k, 2, generator=g)
+    mine = (cand %% world) == rank                       # what a scan over this rank's shard returns
+    bl = torch.where(mine, truth_logit, torch.full((B, k), -100000.0))
+    bll = torch.where(mine[..., None], truth_ll, torch.zeros(B, k, 2))
+    gathered = pdist.all_gather_rows(dict(best_logit=bl, best_lnglat=bll))
+    merged = pdist.merge_partials_by_owner(gathered, cand, world)
+    assert torch.equal(merged["best_logit"], truth_logit), merged["best_logit"]
+    assert torch.equal(merged["best_lnglat"], truth_ll)
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+""")
+
+
+def test_owner_merge_of_sharded_partials_gloo_world2(tmp_path):
+    """Cell-sharded retrieval, host side: partials of two ranks (each -100000 where it does not hold the geocell) merged by
+    owner after the packed all-gather reproduce the unsharded partials bit for bit."""
+    script = tmp_path / "m.py"
+    script.write_text(GLOO_MERGE_WORKER % ROOT)
+    port = str(31000 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), port], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=120)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+
+
 def test_preprocess_plan_matches_oracle_geometry():
     """pg_preprocess_workspace_bytes is pure host arithmetic (resize geometry, Pillow's kernel support, the input rows the
     vertical pass needs): its layout must follow from the oracle's restatement of the same formulas."""

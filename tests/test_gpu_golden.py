@@ -78,8 +78,15 @@ def test_superguessr_pixels_to_geocells(cuda, name):
     assert np.array_equal(out.preds_LLH.cpu().numpy(), z["preds_LLH"]) and out.preds_LLH.dtype == torch.float64
     np.testing.assert_allclose(out.top5_geocells.values.cpu().numpy(), z["topk_val"], rtol=5 * REL_TOL)
     np.testing.assert_allclose(out.loss.item(), z["loss"], rtol=REL_TOL)
-    k_same = (out.top5_geocells.indices.cpu().numpy() == z["topk_idx"]).mean()
-    assert k_same > 0.8, k_same                                         # deep in the top-50 the margins vanish
+    # candidate ORDER: identical down to the first pair of neighbours whose probabilities the reference itself separates by
+    # less than the tolerance on the values (5 x 1e-3; deep in the top-50 the margins vanish); the top-5 the refiner
+    # consumes must be inside
+    idx, val = out.top5_geocells.indices.cpu().numpy(), z["topk_val"]
+    gaps = (val[:, :-1] - val[:, 1:]) / val[:, :-1]
+    safe = np.concatenate([np.ones_like(val[:, :1], dtype=bool), np.cumprod(gaps > 5 * REL_TOL, axis=1).astype(bool)], axis=1)
+    assert safe[:, :5].all(), "fixture: the top-5 candidates must be separated by more than the tolerance"
+    assert np.array_equal(idx[safe], z["topk_idx"][safe])
+    assert set(map(tuple, np.sort(idx, 1))) == set(map(tuple, np.sort(z["topk_idx"], 1))) or (idx == z["topk_idx"]).mean() > 0.9
 
 
 def test_clip_embedding_small_and_large(cuda):
@@ -189,6 +196,90 @@ def test_evaluate_model_loop_matches_direct_calls(cuda):
     np.testing.assert_allclose(res["loss"], out.loss.item(), rtol=1e-5)
 
 
+def test_evaluate_model_loop_matches_reference_loop_golden(cuda):
+    """loops.evaluate_model against tests/golden/loops.npz: the UNMODIFIED body of the reference's `evaluate_model`
+    (training/train_eval_loop.py:35-161) run over the unmodified SuperGuessr + ProtoRefiner on an 11-sample dataset in
+    batches of 4 (ragged last batch).  Pins batch order, what is concatenated, what `metrics` receives and the return."""
+    from pigeon_b200 import ProtoRefiner, SuperGuessr
+    from pigeon_b200.loops import evaluate_model
+    z, meta = load("loops")
+    N, bs, topk, D = meta["N"], meta["bs"], meta["topk"], meta["D"]
+    emb, labels, labels_clf = torch.tensor(z["emb"]), z["labels"], z["labels_clf"]
+    bank = {k[5:]: z[k] for k in z.files if k.startswith("bank_")}
+    sg = SuperGuessr(None, panorama=True, num_candidates=topk, embed_dim=D, geocells=z["centroids"])
+    with torch.no_grad():
+        sg.cell_layer.weight.copy_(torch.tensor(z["head_w"]))
+        sg.cell_layer.bias.copy_(torch.tensor(z["head_b"]))
+    sg.to(cuda).eval()
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return N
+
+        def __getitem__(self, i):
+            if isinstance(i, str):
+                return {"labels": labels, "labels_clf": labels_clf}[i]
+            return dict(embedding=emb[i], labels=torch.tensor(labels[i]), labels_clf=torch.tensor(labels_clf[i]))
+
+    class Args:
+        per_device_eval_batch_size = bs
+
+    captured = {}
+
+    def metrics(results):
+        captured["r"] = results
+        return {"Geocell_accuracy": float((results[1] == results[7]).mean())}
+
+    for tag, refiner in (("refined", ProtoRefiner(topk=topk, max_refinement=1e6, temperature=1.6, protos=bank).eval()), ("plain", None)):
+        ret = evaluate_model(sg, DS(), metrics, Args(), refiner)
+        r = captured["r"]
+        assert len(r) == 11 and r[2] is None and r[3] is None and r[4] is None and r[8] is None
+        assert np.array_equal(r[1], z[f"eval_{tag}_preds_geocell"])
+        assert np.array_equal(r[5], z[f"eval_{tag}_top5"])
+        assert np.array_equal(r[0], z[f"eval_{tag}_preds"]) and r[0].dtype == z[f"eval_{tag}_preds"].dtype
+        assert np.array_equal(r[6], labels) and np.array_equal(r[7], labels_clf)
+        assert ret == float(z[f"eval_{tag}_return"])
+    # the loss the reference logs is sum_batches(loss_b * len(data)) / len(dataset) with len(data) = the number of COLUMNS of
+    # the batch dict (3), train_eval_loop.py:81 — reproduce that figure from this path's per-batch losses
+    logged = 0.0
+    for lo in range(0, N, bs):
+        o = sg(embedding=emb[lo:lo + bs], labels=torch.tensor(labels[lo:lo + bs]), labels_clf=torch.tensor(labels_clf[lo:lo + bs]))
+        logged += float(o.loss) * 3
+    np.testing.assert_allclose(logged / N, float(z["eval_refined_loss_logged"]), rtol=2e-5)
+
+
+def test_compute_embeddings_matches_reference_loop_golden(cuda, tmp_path):
+    """loops.compute_embeddings against the UNMODIFIED body of the reference's (preprocessing/embed.py:16-43) over the
+    unmodified CLIPEmbedding: what lands on disk must give the reference's consumer (dataset_preprocessing.py:296-300:
+    flatten the indices, reshape the embeddings to rows, sort by index) the same rows."""
+    from pigeon_b200 import CLIPEmbedding, CLIPVisionTower, VitDims, synthetic
+    from pigeon_b200.loops import compute_embeddings
+    z, meta = load("loops")
+    e = meta["embed"]
+    dims = VitDims(**e["dims"])
+    tower = CLIPVisionTower(dims)
+    tower.load_state_dict(synthetic.random_vit_state_dict(dims, seed=e["sd_seed"], std=e["std"]))
+    ce = CLIPEmbedding("unused", device="cuda", clip_model=tower.to(cuda))
+    px = torch.randn(e["n_img"], 3, dims.image_size, dims.image_size, generator=torch.Generator().manual_seed(e["px_seed"]))
+    order = torch.tensor(e["order"])
+
+    class EDS(torch.utils.data.Dataset):
+        def __len__(self):
+            return e["n_img"]
+
+        def __getitem__(self, i):
+            return px[order[i]], order[i]
+
+    compute_embeddings("golden", ce, torch.utils.data.DataLoader(EDS(), e["bs"], shuffle=False), save_dir=str(tmp_path))
+    saved, idx = np.load(tmp_path / "golden.npy"), np.load(tmp_path / "golden_indices.npy")
+    assert np.array_equal(idx.flatten(), z["embed_saved_indices"].flatten())          # same batch / row order on disk
+    arg = np.argsort(idx.flatten()[: e["n_img"]])
+    rows = saved.reshape((-1, dims.hidden))[arg]
+    assert rows.shape == z["embed_consumer_rows"].shape
+    assert _rel(rows, z["embed_consumer_rows"]) < REL_TOL
+    assert _rel(saved.reshape(-1, dims.hidden), z["embed_saved"].reshape(-1, dims.hidden)) < REL_TOL
+
+
 def test_bank_builder_matches_reference_prototypes(cuda):
     """pg_bank_build (GPU segmented mean) == the prototype embeddings the reference constructor computed
     (`_compute_protos_for_cell`, proto_refiner.py:359-378; packed into the golden by oracle/make_golden.py)."""
@@ -238,3 +329,16 @@ def test_checkpoint_round_trip_through_load_state(cuda, tmp_path):
     ob = b(pixel_values=px, labels_clf=lab)
     assert torch.equal(oa.embedding, ob.embedding) and torch.equal(oa.preds_geocell, ob.preds_geocell)
     assert torch.equal(oa.top5_geocells.values, ob.top5_geocells.values) and float(oa.loss) == float(ob.loss)
+
+
+def test_multi_rank_outputs_equal_single_rank_bit_for_bit(cuda):
+    """SURVEY.md §4-iii on NCCL: world-size-2 gathered outputs (replicated and cell-sharded bank) == single-rank outputs."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29579", os.path.join(root, "tools", "ddp_infer_check.py")],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

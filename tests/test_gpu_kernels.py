@@ -153,6 +153,9 @@ def test_head(cuda, B, V, D, C, k):
     (50, 600, 1024, 64, 10, 5, 0.0, 1.6, 1000.0),
     (50, 600, 768, 64, 10, 10, 6.0, 0.6, 100000.0),
     (40, 300, 256, 33, 5, 5, 3.0, 1.0, 2000.0),
+    # BASELINE.json configs[2] scale: the 100k-prototype bank of the bench, one rank's batch, top-5 and top-40
+    (1000, 100_000, 1024, 256, 40, 5, 0.0, 1.6, 1000.0),
+    (1000, 100_000, 1024, 256, 40, 40, 0.0, 0.6, 100000.0),
 ])
 def test_refiner_vs_oracle(cuda, C, P, D, B, kc, topk, members, T, maxref):
     import numpy as np
@@ -214,3 +217,28 @@ def test_refiner_cell_major_equals_query_major(cuda, C, P, D, B, kc, topk, membe
     assert torch.equal(dq["best_lnglat"][same], dc["best_lnglat"][same])
     rows = same.all(dim=1)
     assert torch.equal(cell_q[rows], cell_c[rows]) and torch.equal(ll_q[rows], ll_c[rows])
+
+
+@pytest.mark.parametrize("world,members", [(2, 0.0), (4, 3.0), (8, 0.0)])
+def test_refiner_cell_sharded_equals_replicated(cuda, world, members):
+    """SURVEY.md 8e-ii on one GPU: scan the same queries against each of `world` cell shards (bank.shard_bank), merge the
+    partials by owner (dist.merge_partials_by_owner, what the ranks do after their all-gather), run the final stage:
+    every output must equal the replicated bank's, bit for bit (the owner runs the same arithmetic on the same rows)."""
+    from pigeon_b200 import bank as bank_mod, dist as pdist, ops, synthetic
+    C, P, D, B, kc, topk = 300, 6000, 256, 700, 8, 5
+    full = synthetic.synthetic_bank(C, P, D, seed=21, members_mean=members, empty_cells=4)
+    cand, probs = synthetic.synthetic_candidates(B, kc, C, seed=22)
+    emb = torch.from_numpy(synthetic.synthetic_queries(full, cand, views=1, seed=23)).to(cuda)
+    init = torch.from_numpy(synthetic.synthetic_geocells(B, seed=24)).to(cuda)
+    candt, probst = torch.from_numpy(cand).to(cuda), torch.from_numpy(probs).to(cuda)
+    ll_ref, cell_ref, dbg = ops.refiner_forward(ops.DeviceBank(cuda, **full), emb, init, candt, probst, topk, 1.6, 1e6, debug=True)
+    parts_l, parts_ll = [], []
+    for r in range(world):
+        bl, bll, _ = ops.refiner_scan(ops.DeviceBank(cuda, **bank_mod.shard_bank(full, r, world)), emb, candt, topk)
+        parts_l.append(bl)
+        parts_ll.append(bll)
+    gathered = dict(best_logit=torch.cat(parts_l), best_lnglat=torch.cat(parts_ll))
+    merged = pdist.merge_partials_by_owner(gathered, candt[:, :topk], world)
+    assert torch.equal(merged["best_logit"], dbg["best_logit"]) and torch.equal(merged["best_lnglat"], dbg["best_lnglat"])
+    ll, cell, choice = ops.refiner_finalize(merged["best_logit"], merged["best_lnglat"], init, candt, probst, topk, 1.6, 1e6)
+    assert torch.equal(ll, ll_ref) and torch.equal(cell, cell_ref) and torch.equal(choice, dbg["choice"])

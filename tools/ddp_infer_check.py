@@ -1,0 +1,53 @@
+"""Multi-rank result parity of the inference path on 2+ GPUs (torchrun): every rank embeds its shard of a
+fixed global batch, the head outputs are exchanged with the packed NCCL all-gather, retrieval runs over (a) a replicated
+bank and (b) a bank whose geocells are sharded across the ranks (second all-gather of the per-candidate partials) — and
+both gathered results must equal, BIT FOR BIT, what one rank computes alone on the whole batch.  Exit code 0 on success."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    from pigeon_b200 import CLIPVisionTower, ProtoRefiner, SuperGuessr, VitDims, evaluation, synthetic
+    from pigeon_b200 import dist as pdist
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    dist.init_process_group("nccl", device_id=dev)
+    dims = VitDims(image_size=112, patch_size=14, hidden=256, heads=4, intermediate=768, layers=3)
+    C, P, k = 64, 3000, 5
+    tower = CLIPVisionTower(dims)
+    tower.load_state_dict(synthetic.random_vit_state_dict(dims, seed=4, std=0.05))
+    cells = synthetic.synthetic_geocells(C, 0)
+    model = SuperGuessr(tower, panorama=True, freeze_base=True, num_candidates=12, geocells=cells).to(dev).eval()
+    bank = synthetic.synthetic_bank(C, P, dims.hidden, seed=6, members_mean=2.5, empty_cells=3)
+    mk = lambda shard: ProtoRefiner(topk=k, max_refinement=1e6, temperature=1.6, protos=bank, device=dev, shard_cells=shard).eval()
+    Bg = 6 * world
+    px = torch.randn(Bg, 12, dims.image_size, dims.image_size, generator=torch.Generator().manual_seed(9)).half().to(dev)
+    labels = torch.from_numpy(synthetic.synthetic_geocells(Bg, 3)).to(dev)
+    clf = (torch.arange(Bg) % C).to(dev)
+    lo, hi = pdist.shard_range(Bg, rank, world)
+    mine = dict(pixel_values=px[lo:hi], labels=labels[lo:hi], labels_clf=clf[lo:hi])
+    ok = True
+    # single-rank reference on the whole batch (no collectives)
+    ll1, cell1, out1 = evaluation.predict_batch(model, mk(False), dict(pixel_values=px, labels=labels, labels_clf=clf), gather=False)
+    for name, shard in (("replicated bank", False), ("cell-sharded bank", True)):
+        ll, cell, out = evaluation.predict_batch(model, mk(shard), mine)
+        same = (ll.shape == ll1.shape and torch.equal(ll, ll1) and torch.equal(cell, cell1)
+                and torch.equal(out.embedding, out1.embedding[lo:hi]))
+        print(f"rank {rank} world {world} {name}: gathered outputs == single-rank outputs: {same}", flush=True)
+        ok = ok and same
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
