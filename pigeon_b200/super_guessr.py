@@ -190,7 +190,9 @@ class SuperGuessr(nn.Module):
 
         self._set_hidden_size()
         if geocells is not None:
-            self.lla_geocells = Parameter(torch.as_tensor(geocells, dtype=torch.float64).clone(), requires_grad=False)
+            # (.clone() keeps the strides of e.g. a Fortran-ordered numpy array: the kernels index it row-major)
+            self.lla_geocells = Parameter(torch.as_tensor(geocells, dtype=torch.float64).contiguous().clone(),
+                                          requires_grad=False)
         else:
             self.lla_geocells = self.load_geocells(GEOCELL_PATH_YFCC if self.yfcc else GEOCELL_PATH)
         self.num_cells = self.lla_geocells.size(0)
@@ -234,7 +236,7 @@ class SuperGuessr(nn.Module):
 
     def load_geocells(self, path: str) -> Tensor:
         geo_df = pd.read_csv(path)
-        lla_coords = torch.tensor(geo_df[['lng', 'lat']].values)
+        lla_coords = torch.tensor(geo_df[['lng', 'lat']].values).contiguous()   # pandas hands out column-major blocks
         return Parameter(data=lla_coords, requires_grad=False)
 
     def load_state(self, path: str):
