@@ -43,7 +43,8 @@ def evaluate_model(model, dataset, metrics: Optional[Callable], train_args=None,
             cells.append(outputs.preds_geocell)
             top_cells.append(outputs.top5_geocells.indices)
             top_probs.append(outputs.top5_geocells.values)
-    preds_np = torch.cat(preds).float().cpu().numpy()                                # single D2H at the end
+    # dtype as the reference collects it: float32 from the refiner, float64 centroid coordinates without (:98-105)
+    preds_np = torch.cat(preds).cpu().numpy()                                        # single D2H at the end
     cells_np = torch.cat(cells).cpu().numpy()
     top_np = torch.cat(top_cells).cpu().numpy()
     labels_lla, labels_cell = dataset['labels'], dataset['labels_clf']               # :115-120

@@ -13,6 +13,16 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    import traceback
+    try:
+        _main()
+    except Exception:
+        traceback.print_exc()
+        sys.stdout.flush()
+        sys.exit(2)
+
+
+def _main():
     from pigeon_b200 import CLIPVisionTower, ProtoRefiner, SuperGuessr, VitDims, evaluation, synthetic
     from pigeon_b200 import dist as pdist
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -38,9 +48,14 @@ def main():
     ll1, cell1, out1 = evaluation.predict_batch(model, mk(False), dict(pixel_values=px, labels=labels, labels_clf=clf), gather=False)
     for name, shard in (("replicated bank", False), ("cell-sharded bank", True)):
         ll, cell, out = evaluation.predict_batch(model, mk(shard), mine)
-        same = (ll.shape == ll1.shape and torch.equal(ll, ll1) and torch.equal(cell, cell1)
-                and torch.equal(out.embedding, out1.embedding[lo:hi]))
-        print(f"rank {rank} world {world} {name}: gathered outputs == single-rank outputs: {same}", flush=True)
+        e_emb = torch.equal(out.embedding, out1.embedding[lo:hi])
+        e_top = torch.equal(out.top5_geocells.indices, out1.top5_geocells.indices[lo:hi])
+        e_ll = ll.shape == ll1.shape and torch.equal(ll, ll1)
+        e_cell = cell.shape == cell1.shape and torch.equal(cell, cell1)
+        same = e_emb and e_top and e_ll and e_cell
+        print(f"rank {rank} world {world} {name}: gathered outputs == single-rank outputs: {same} "
+              f"(embedding {e_emb}, candidates {e_top}, preds_LLH {e_ll} {tuple(ll.shape)} vs {tuple(ll1.shape)}, "
+              f"geocell {e_cell}; embedding max |diff| {(out.embedding - out1.embedding[lo:hi]).abs().max().item():.3e})", flush=True)
         ok = ok and same
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
