@@ -155,6 +155,7 @@ def read_profile():
 def build_models(device, seed=0, fold_layernorm=True, shard_cells=False):
     from pigeon_b200 import CLIPVisionTower, ProtoRefiner, SuperGuessr, VitDims, synthetic
     dims = VitDims()
+    torch.manual_seed(1000 + seed)   # same geocell head on every rank (nn.Linear's default init uses the global RNG)
     tower = CLIPVisionTower(dims)
     tower.load_state_dict(synthetic.random_vit_state_dict(dims, seed=seed))
     tower.max_views_per_pass = 1024

@@ -12,6 +12,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def _say(rank, msg):
+    print(msg, flush=True)
+    d = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, f"ddp_infer_check_rank{rank}.log"), "a") as f:
+            f.write(msg + "\n")
+
+
 def main():
     import traceback
     try:
@@ -31,6 +39,7 @@ def _main():
     dist.init_process_group("nccl", device_id=dev)
     dims = VitDims(image_size=112, patch_size=14, hidden=256, heads=4, intermediate=768, layers=3)
     C, P, k = 64, 3000, 5
+    torch.manual_seed(1234)          # every rank must hold the SAME geocell head (nn.Linear's default init draws from the global RNG)
     tower = CLIPVisionTower(dims)
     tower.load_state_dict(synthetic.random_vit_state_dict(dims, seed=4, std=0.05))
     cells = synthetic.synthetic_geocells(C, 0)
@@ -53,9 +62,11 @@ def _main():
         e_ll = ll.shape == ll1.shape and torch.equal(ll, ll1)
         e_cell = cell.shape == cell1.shape and torch.equal(cell, cell1)
         same = e_emb and e_top and e_ll and e_cell
-        print(f"rank {rank} world {world} {name}: gathered outputs == single-rank outputs: {same} "
+        _say(rank, f"rank {rank} world {world} {name}: gathered outputs == single-rank outputs: {same} "
               f"(embedding {e_emb}, candidates {e_top}, preds_LLH {e_ll} {tuple(ll.shape)} vs {tuple(ll1.shape)}, "
-              f"geocell {e_cell}; embedding max |diff| {(out.embedding - out1.embedding[lo:hi]).abs().max().item():.3e})", flush=True)
+              f"geocell {e_cell}; embedding max |diff| {(out.embedding - out1.embedding[lo:hi]).abs().max().item():.3e}; "
+              f"preds_LLH max |diff| {(ll - ll1).abs().max().item() if ll.shape == ll1.shape else -1:.3e}, "
+              f"geocell mismatches {(cell != cell1).sum().item() if cell.shape == cell1.shape else -1})")
         ok = ok and same
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
