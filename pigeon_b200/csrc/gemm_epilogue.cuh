@@ -138,18 +138,21 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
     float v[CHUNK];
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) v[i] = __uint_as_float(r[i]);
-    if (kLn) {   // LayerNorm folded: rstd * acc - rstd * mu * colsum   (N is a multiple of the chunk: checked at launch)
+    if (kLn) {   // LayerNorm folded: rstd * acc + (-rstd * mu) * colsum + bias, two FMAs per element
+      // (N is a multiple of the chunk and bias != nullptr: checked at launch)
       const float4* c4 = reinterpret_cast<const float4*>(args.colsum + col0);
+      const float4* b4 = reinterpret_cast<const float4*>(args.bias + col0);
 #pragma unroll
       for (int i = 0; i < CHUNK / 4; ++i) {
         const float4 cs = __ldg(c4 + i);
-        v[4 * i + 0] = fmaf(ln_a, v[4 * i + 0], ln_b * cs.x);
-        v[4 * i + 1] = fmaf(ln_a, v[4 * i + 1], ln_b * cs.y);
-        v[4 * i + 2] = fmaf(ln_a, v[4 * i + 2], ln_b * cs.z);
-        v[4 * i + 3] = fmaf(ln_a, v[4 * i + 3], ln_b * cs.w);
+        const float4 b = __ldg(b4 + i);
+        v[4 * i + 0] = fmaf(ln_a, v[4 * i + 0], fmaf(ln_b, cs.x, b.x));
+        v[4 * i + 1] = fmaf(ln_a, v[4 * i + 1], fmaf(ln_b, cs.y, b.y));
+        v[4 * i + 2] = fmaf(ln_a, v[4 * i + 2], fmaf(ln_b, cs.z, b.z));
+        v[4 * i + 3] = fmaf(ln_a, v[4 * i + 3], fmaf(ln_b, cs.w, b.w));
       }
     }
-    if (args.bias != nullptr) {
+    if (!kLn && args.bias != nullptr) {
       if (in_n) {
         const float4* b4 = reinterpret_cast<const float4*>(args.bias + col0);
 #pragma unroll

@@ -204,8 +204,8 @@ int launch(const GemmProblem& p, int num_sms, cudaStream_t stream) {
     a.stats_slots = p.N / 128;
   }
   if (EpiTraits<EPI>::kLn) {
-    if (!p.stats || !p.colsum || (p.K % 128) || (p.N % 64) || (reinterpret_cast<uintptr_t>(p.colsum) & 15)) {
-      set_last_error("gemm: LayerNorm-consumer epilogue needs stats, a 16-byte aligned colsum, K %% 128 == 0 and N %% 64 == 0"); return 1;
+    if (!p.stats || !p.colsum || !p.bias || (p.K % 128) || (p.N % 64) || (reinterpret_cast<uintptr_t>(p.colsum) & 15)) {
+      set_last_error("gemm: LayerNorm-consumer epilogue needs stats, a bias, a 16-byte aligned colsum, K %% 128 == 0 and N %% 64 == 0"); return 1;
     }
     a.stats_slots = p.K / 128;
   }
