@@ -108,7 +108,10 @@ int pg_head_forward(const float* emb, int32_t B, int32_t V, int32_t D, const voi
  *   mode 0: labels_idx i64 [B] class indices;  mode 1: soft f32 [B, C] target probabilities;
  *   mode 2: haversine-smoothed targets from labels_lnglat f64 [B, 2] and centroids f64 [C, 2]
  *           (preprocessing/geo_utils.py:58-74 + preprocessing/utils.py:7-19, smoothing_km = 65).
- * per_sample f64 [B] is scratch/out; loss_out f64 [1]. */
+ * per_sample f64 [B] is scratch/out; loss_out f64 [1].
+ * mode 0 labels outside [0, C) are never used as an index: that sample's loss and the batch mean become NaN (and, in
+ * pg_head_loss_grad, its gradient row zero).  torch's ignore_index = -100 is not implemented — the reference's labels on this
+ * path are geocell indices and never negative. */
 int pg_head_loss(const float* logits, int32_t B, int32_t C, int32_t mode, const int64_t* labels_idx,
                  const float* soft, const double* labels_lnglat, const double* centroids, double smoothing_km,
                  double* per_sample, double* loss_out, void* stream);

@@ -27,6 +27,7 @@ SOURCES = [
     "attention_tcgen05.cu",
     "attention_pair_tcgen05.cu",
     "attention_split_tcgen05.cu",
+    "attention_fold_tcgen05.cu",
     "vit_misc.cu",
     "head.cu",
     "refiner.cu",

@@ -23,8 +23,10 @@ def _load_indices(index_json) -> list:
 
 def bank_from_arrays(proto_cell: np.ndarray, proto_lnglat: np.ndarray, proto_indices: Sequence[Sequence[int]],
                      data_emb: torch.Tensor, data_lnglat: np.ndarray, num_cells: Optional[int] = None,
-                     device: str | torch.device = "cpu") -> Dict[str, np.ndarray]:
-    """Rows (one per prototype, any order) -> CSR bank.  `data_emb` is [N, D] or [N, 4, D] (views averaged first)."""
+                     device: str | torch.device = "cpu", proto_count: Optional[Sequence[int]] = None) -> Dict[str, np.ndarray]:
+    """Rows (one per prototype, any order) -> CSR bank.  `data_emb` is [N, D] or [N, 4, D] (views averaged first).
+    `proto_count` is the CSV `count` column: the reference's single-member shortcut tests it (:243-244, cluster['count'] == 1),
+    not the length of the index list, so it is carried as given; omitted, the list lengths are used."""
     proto_cell = np.asarray(proto_cell, np.int64)
     C = int(num_cells if num_cells is not None else proto_cell.max() + 1)
     keep = np.array([len(ix) > 0 for ix in proto_indices], bool)
@@ -63,7 +65,8 @@ def bank_from_arrays(proto_cell: np.ndarray, proto_lnglat: np.ndarray, proto_ind
         proto_emb = sums / torch.as_tensor(member_len, dtype=torch.float32)[:, None]   # mean over members (:373)
     return dict(cell_off=cell_off, proto_emb=proto_emb.cpu().numpy(),
                 proto_lnglat=np.asarray(proto_lnglat, np.float64)[rows].astype(np.float32),
-                proto_count=member_len.astype(np.int32), member_off=member_off, member_idx=member_idx,
+                proto_count=(member_len if proto_count is None else np.asarray(proto_count, np.int64)[rows]).astype(np.int32),
+                member_off=member_off, member_idx=member_idx,
                 data_emb=emb.cpu().numpy(), data_lnglat=np.asarray(data_lnglat, np.float32))
 
 
@@ -87,7 +90,7 @@ def bank_from_reference_files(proto_path: str, dataset_path, device: str | torch
     idx = [_load_indices(s) for s in df['indices']]
     cells = df['geocell_idx'].astype(int).to_numpy()
     return bank_from_arrays(cells, df[['lng', 'lat']].to_numpy(), idx, data_emb, data_ll,
-                            num_cells=int(cells.max()) + 1, device=device)
+                            num_cells=int(cells.max()) + 1, device=device, proto_count=df['count'].to_numpy())
 
 
 def bank_from_proto_rows(cells: Sequence[Optional[Sequence[dict]]], data_emb, data_lnglat) -> Dict[str, np.ndarray]:

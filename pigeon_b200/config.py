@@ -19,6 +19,7 @@ PRETRAINED_CLIP = 'saved_models/StreetviewCLIP.model'
 CLIP_PRETRAINED_HEAD = 'saved_models/New_Base_smooth_avg_MT_Geo_SV.model'
 PRETRAINED_CLIP_YFCC = 'saved_models/WorldCLIP.model'
 CLIP_PRETRAINED_HEAD_YFCC = 'saved_models/WorldCLIP_head.model'
+CLIP_PRETRAINED_HEAD_YFCC_LANDMARKS = 'saved_models/WorldCLIP_head_landmarks.model'
 
 # Embedding                                                            (config.py:70-71)
 EMBED_BATCH_SIZE_PER_GPU = 512
@@ -27,9 +28,12 @@ EMBED_BATCH_SIZE_PER_GPU = 512
 PROTO_PATH = 'data/data_prototypes_2203.csv'
 DATASET_PATH = 'data/hf_SVCLIP_2203'
 PROTO_MODEL_PATH = 'saved_models/refiner/proto.refiner'
-PROTO_PATH_YFCC = 'data/data_yfcc_prototypes.csv'
-DATASET_PATH_YFCC = 'data/hf_yfcc_embeddings'
-PROTO_MODEL_YFCC_PATH = 'saved_models/refiner/proto_yfcc.refiner'
+PROTO_PATH_YFCC = 'data/data_prototypes_YFCC.csv'
+DATASET_PATH_YFCC = 'data/hf_YFCC'
+PROTO_MODEL_YFCC_PATH = 'saved_models/refiner/proto_YFCC.refiner'
+PROTO_PATH_LANDMARKS = 'data/data_prototypes_landmarks.csv'
+DATASET_PATH_LANDMARKS = 'data/hf_landmarks'
+PROTO_MODEL_LANDMARKS_PATH = 'saved_models/refiner/proto_landmarks.refiner'
 
 # Evaluation batch size (TRAIN_ARGS.per_device_eval_batch_size)        (config.py:98)
 EVAL_BATCH_SIZE = 256

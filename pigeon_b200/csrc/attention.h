@@ -19,7 +19,12 @@ int attention_pair_f16(const void* qkv, void* out, int n_views, int seq, int hea
 int attention_split_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream, float* lse2,
                         int poly);
 
-// Explicit kernel choice for A/B measurements: variant 0 = pair kernel, 2 = split kernel (poly in eighths, < 0 = default), 1 = first-generation
+// Fourth-generation forward kernel (attention_fold_tcgen05.cu): the pair kernel with the softmax scale, reference subtraction
+// and row sum moved into the MMAs (extra k-step / ones-column accumulator); rows whose fp16 P overflows are repaired exactly.
+int attention_fold_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream, float* lse2,
+                       int poly);
+
+// Explicit kernel choice for A/B measurements: variant 0 = pair kernel, 2 = split kernel, 3 = fold kernel (poly in eighths, < 0 = default), 1 = first-generation
 // kernel (poly 0 / 4 / 2 = none / every 4th / every 2nd group).
 int attention_f16_variant(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream, float* lse2,
                           int variant, int poly);

@@ -476,13 +476,14 @@ int launch_attention(const void* qkv, void* out, int n_views, int seq, int heads
 // PG_ATTN_POLY: eighths of the exponentials on the FMA pipe for the pair kernel, or 4 / 2 = every 4th / 2nd group for
 // the legacy kernel).
 struct AttnSwitches {
-  int variant = 0;   // 0 pair, 1 legacy 32/2/4, 2 "64", 3 "64s", 4 "64h", 5 "32c", 6 split
+  int variant = 0;   // 0 pair, 1 legacy 32/2/4, 2 "64", 3 "64s", 4 "64h", 5 "32c", 6 split, 7 fold
   int poly = -1;
   AttnSwitches() {
     const char* v = getenv("PG_ATTN_VARIANT");
     if (v) {
       if (!strcmp(v, "legacy") || !strcmp(v, "32")) variant = 1;
       else if (!strcmp(v, "split")) variant = 6;
+      else if (!strcmp(v, "fold")) variant = 7;
       else if (!strcmp(v, "64")) variant = 2;
       else if (!strcmp(v, "64s")) variant = 3;
       else if (!strcmp(v, "64h")) variant = 4;
@@ -498,6 +499,7 @@ int attention_f16_variant(const void* qkv, void* out, int n_views, int seq, int 
   if (n_views <= 0) return 0;
   if (variant == 0) return attention_pair_f16(qkv, out, n_views, seq, heads, stream, lse2, poly < 0 ? 2 : poly);
   if (variant == 2) return attention_split_f16(qkv, out, n_views, seq, heads, stream, lse2, poly < 0 ? 2 : poly);
+  if (variant == 3) return attention_fold_f16(qkv, out, n_views, seq, heads, stream, lse2, poly < 0 ? 3 : poly);
   if (n_views > 65535) { set_last_error("attention (legacy kernel): n_views %d > 65535 (grid.z)", n_views); return 1; }
   if (poly == 4) return launch_attention<AttnCfg<32, 2, 4, 4>>(qkv, out, n_views, seq, heads, stream, lse2);
   if (poly == 2) return launch_attention<AttnCfg<32, 2, 4, 2>>(qkv, out, n_views, seq, heads, stream, lse2);
@@ -514,6 +516,7 @@ int attention_f16(const void* qkv, void* out, int n_views, int seq, int heads, c
   switch (sw.variant) {
     case 0: return attention_pair_f16(qkv, out, n_views, seq, heads, stream, lse2, sw.poly < 0 ? 2 : sw.poly);
     case 6: return attention_split_f16(qkv, out, n_views, seq, heads, stream, lse2, sw.poly < 0 ? 2 : sw.poly);
+    case 7: return attention_fold_f16(qkv, out, n_views, seq, heads, stream, lse2, sw.poly < 0 ? 3 : sw.poly);
     case 2: return launch_attention<AttnCfg<64, 3, 2>>(qkv, out, n_views, seq, heads, stream, lse2);
     case 3: return launch_attention<AttnCfg<64, 1, 4, 0, 4>>(qkv, out, n_views, seq, heads, stream, lse2);
     case 4: return launch_attention<AttnCfg<64, 1, 4, 0, 4, true>>(qkv, out, n_views, seq, heads, stream, lse2);

@@ -65,6 +65,15 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// same, with an L2 eviction policy for the lines the load touches
+__device__ __forceinline__ void tma_load_2d_2sm_hint(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                     int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
                "r"(ncols)
@@ -148,6 +157,9 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // A is read by the n_blocks CTA pairs that share its 256 rows (they run concurrently, consecutive tile indices): keep its
+      // lines in L2 over the streaming traffic of the epilogues
+      const uint64_t pol_a = l2_policy_evict_last();
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
         const int a_row = m_blk * 2 * BLOCK_M_CTA + rank * BLOCK_M_CTA;
@@ -158,7 +170,8 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
           else        mbar_arrive_cluster(full_leader);
           if (!args.mn_major) {
-            tma_load_2d_2sm(smem_a + stage * kABytes, &tmap_a, full_leader, kb * BLOCK_K, a_row);
+            if (n_blocks > 1) tma_load_2d_2sm_hint(smem_a + stage * kABytes, &tmap_a, full_leader, kb * BLOCK_K, a_row, pol_a);
+            else tma_load_2d_2sm(smem_a + stage * kABytes, &tmap_a, full_leader, kb * BLOCK_K, a_row);
             tma_load_2d_2sm(smem_b + stage * kBBytes, &tmap_b, full_leader, kb * BLOCK_K, b_row);
           } else {
             // operand tiles [64 contraction rows x 64 M/N columns] (128 B per row, swizzled): two per operand and CTA
@@ -220,6 +233,22 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+      if (EpiTraits<EPI>::kResid && args.vec_ok) {
+        // the residual rows this warp will read-modify-write one tile from now: pulled into L2 a whole epilogue ahead (one
+        // 512-byte bulk prefetch per lane = row), because the register prefetch inside epilogue_tile keeps only 4 KB per
+        // warp in flight — too little for HBM latency when the epilogue is the longer phase (out_proj: K = 1024)
+        const int nt = tile + num_pairs;
+        if (nt < num_tiles) {
+          const int nm = nt / n_blocks, nn = nt % n_blocks;
+          const long row = (long)nm * 2 * BLOCK_M_CTA + rank * BLOCK_M_CTA + q * 32 + lane;
+          const int col = nn * BLOCK_N + ((warp - kEpiWarp0) >= 4 ? BLOCK_N / 2 : 0);
+          if (row < args.M && col + BLOCK_N / 2 <= args.N)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const float*>(args.resid) +
+                                                                          row * args.ldo + col),
+                         "r"(BLOCK_N / 2 * 4)
+                         : "memory");
+        }
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N;

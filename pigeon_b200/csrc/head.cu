@@ -189,10 +189,15 @@ ce_loss_kernel(const float* __restrict__ logits, int C, int mode, const long lon
   // backward (dlogits != nullptr): d loss_b / d x_c = softmax_c * sum_c'(t_c') - t_c, times grad_scale
   float* g = dlogits ? dlogits + (long)b * C : nullptr;
   if (mode == 0) {
+    // A label outside [0, C) never indexes memory: the sample's loss (and so the batch mean) becomes NaN and its gradient row
+    // zero, which is loud instead of undefined.  torch's ignore_index (-100) is not implemented: the reference's labels on
+    // this path are geocell indices produced by its own dataset code and are never negative.
     const long long y = labels_idx[b];
-    if (tid == 0) loss = lse - (double)x[y];
+    const bool valid = y >= 0 && y < C;
+    if (tid == 0) loss = valid ? lse - (double)x[y] : (double)NAN;
     if (g)
-      for (int c = tid; c < C; c += 256) g[c] = (float)(grad_scale * (exp((double)x[c] - lse) - (c == y ? 1.0 : 0.0)));
+      for (int c = tid; c < C; c += 256)
+        g[c] = valid ? (float)(grad_scale * (exp((double)x[c] - lse) - (c == y ? 1.0 : 0.0))) : 0.f;
   } else if (mode == 1) {
     double tsum = 0;
     for (int c = tid; c < C; c += 256) {

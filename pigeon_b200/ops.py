@@ -45,19 +45,24 @@ def layernorm_f16(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
 
 
 def attention_f16(qkv: torch.Tensor, n_views: int, seq: int, heads: int, variant: int | None = None,
-                  poly: int = -1) -> torch.Tensor:
+                  poly: int = -1, return_lse2: bool = False):
     """qkv fp16 [n_views*seq, 3*heads*64] -> fp16 [n_views*seq, heads*64].
 
-    `variant` (A/B measurements only): 0 = pair kernel, 1 = first-generation kernel; None = the library default."""
+    `variant` (A/B measurements only): 0 = pair kernel, 1 = first-generation kernel, 2 = split kernel, 3 = fold kernel;
+    None = the library default.  `return_lse2` (with an explicit variant): also the log2-domain log-sum-exp of the scaled
+    logits, f32 [n_views*heads, seq], the side output the training forward keeps for the backward pass."""
     _need_cuda(qkv)
     assert qkv.dtype == torch.float16 and qkv.shape == (n_views * seq, 3 * heads * 64)
     out = torch.empty((n_views * seq, heads * 64), dtype=torch.float16, device=qkv.device)
+    lse2 = torch.empty((n_views * heads, seq), dtype=torch.float32, device=qkv.device) if return_lse2 else None
     if variant is None:
+        if return_lse2:
+            raise ValueError("return_lse2 needs an explicit variant (pg_attention_f16 has no lse2 argument)")
         check(load().pg_attention_f16(ptr(qkv), ptr(out), n_views, seq, heads, current_stream_ptr()), "pg_attention_f16")
     else:
-        check(load().pg_attention_f16_variant(ptr(qkv), ptr(out), None, n_views, seq, heads, variant, poly,
-                                              current_stream_ptr()), "pg_attention_f16_variant")
-    return out
+        check(load().pg_attention_f16_variant(ptr(qkv), ptr(out), ptr(lse2) if return_lse2 else None, n_views, seq, heads,
+                                              variant, poly, current_stream_ptr()), "pg_attention_f16_variant")
+    return (out, lse2) if return_lse2 else out
 
 
 def refiner_scan(bank: "DeviceBank", emb: torch.Tensor, cand_idx: torch.Tensor, topk: int):

@@ -223,16 +223,21 @@ class SuperGuessr(nn.Module):
             self.mode = 'transformer'
 
     def _freeze_params(self):
-        if self.base_model is not None:
-            if self.freeze_base:
-                for param in self.base_model.parameters():
-                    param.requires_grad = False
-            elif 'clip-vit' in self.base_model.config._name_or_path and not self.serving:
-                head = CLIP_PRETRAINED_HEAD_YFCC if self.yfcc else CLIP_PRETRAINED_HEAD
-                self.load_state(head)
-                print(f'Initialized model parameters from model: {head}')
-                for param in self.base_model.vision_model.encoder.layers[:-1].parameters():
-                    param.requires_grad = False
+        """reference :146-160: a frozen base model trains nothing in the tower; an unfrozen CLIP tower outside serving starts
+        from the pretrained head checkpoint and trains only its last encoder layer."""
+        tower = self.base_model
+        if tower is None:
+            return
+        if self.freeze_base:
+            tower.requires_grad_(False)
+            return
+        if self.serving or 'clip-vit' not in tower.config._name_or_path:
+            return
+        checkpoint = CLIP_PRETRAINED_HEAD_YFCC if self.yfcc else CLIP_PRETRAINED_HEAD
+        self.load_state(checkpoint)
+        print(f'Initialized model parameters from model: {checkpoint}')
+        for layer in tower.vision_model.encoder.layers[:-1]:
+            layer.requires_grad_(False)
 
     def load_geocells(self, path: str) -> Tensor:
         geo_df = pd.read_csv(path)
@@ -240,16 +245,15 @@ class SuperGuessr(nn.Module):
         return Parameter(data=lla_coords, requires_grad=False)
 
     def load_state(self, path: str):
-        """reference :222-238 — by-name copy, unknown keys printed and skipped."""
-        own_state = self.state_dict()
-        state_dict = torch.load(path, map_location=torch.device('cuda'))
-        for name, param in state_dict.items():
-            if name not in own_state:
-                print(f'Parameter {name} not in model\'s state.')
-                continue
-            if isinstance(param, Parameter):
-                param = param.data
-            own_state[name].copy_(param)
+        """reference :222-238 — checkpoint entries are copied into the same-named entries of this module; a name this module
+        does not have is reported on stdout and skipped (shape mismatches raise, as copy_ does)."""
+        mine = self.state_dict()
+        for key, value in torch.load(path, map_location=torch.device('cuda')).items():
+            target = mine.get(key)
+            if target is None:
+                print(f'Parameter {key} not in model\'s state.')
+            else:
+                target.copy_(value.data if isinstance(value, Parameter) else value)
         if self.base_model is not None:
             self.base_model._weights_changed()
 
@@ -567,18 +571,10 @@ class SuperGuessr(nn.Module):
                                preds_climate, preds_month, geocell_topk, embedding)
 
     def __str__(self):
-        rep = 'SuperGuessr(\n'
-        rep += f'\tbase_model\t= {self.base_model is not None}\n'
-        rep += f'\tpanorama\t= {self.panorama}\n'
-        rep += f'\thierarchical\t= {self.hierarchical}\n'
-        rep += f'\tmulti-task\t= {self.multi_task}\n'
-        rep += f'\tyfcc\t\t= {self.yfcc}\n'
-        rep += f'\tembedding_size\t= {self.hidden_size}\n'
-        rep += f'\tinput_dim\t= {self.input_dim}\n'
-        rep += f'\tnum_geocells\t= {self.num_cells}\n'
-        rep += f'\tlabel_smoothing\t= {self.should_smooth_labels}\n'
-        rep += f'\tuses_headings\t= {self.heading}\n'
-        rep += f'\tfreeze_base\t= {self.freeze_base}\n'
-        rep += f'\tserving\t\t= {self.serving}\n'
-        rep += ')'
-        return rep
+        """Same text as the reference prints at start-up (:486-501): one tab-aligned `name = value` line per switch."""
+        fields = (('base_model\t', self.base_model is not None), ('panorama\t', self.panorama),
+                  ('hierarchical\t', self.hierarchical), ('multi-task\t', self.multi_task), ('yfcc\t\t', self.yfcc),
+                  ('embedding_size\t', self.hidden_size), ('input_dim\t', self.input_dim),
+                  ('num_geocells\t', self.num_cells), ('label_smoothing\t', self.should_smooth_labels),
+                  ('uses_headings\t', self.heading), ('freeze_base\t', self.freeze_base), ('serving\t\t', self.serving))
+        return 'SuperGuessr(\n' + ''.join(f'\t{name}= {value}\n' for name, value in fields) + ')'

@@ -72,72 +72,79 @@ class VitEngine:
         self._lib = load()
         self._handle = C.c_void_p()
         self._ws: Optional[torch.Tensor] = None
-        self._keep = []  # tensors referenced by raw pointer from the C side
+        self._packs = None   # group ("embeddings" | layer index) -> tensors referenced by raw pointer from the C side
         self.load_state_dict(state_dict)
 
     # ------------------------------------------------------------------------------------------ weights
-    def load_state_dict(self, state_dict: Dict[str, torch.Tensor]) -> None:
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], changed=None) -> None:
+        """(Re)pack weights for the kernels.  `changed` limits the work to the groups whose parameters moved: a set holding
+        "embeddings" and / or encoder layer indices (None = everything).  Under the reference's fine-tune policy only the last
+        layer changes between optimizer steps, so one layer is repacked per step instead of 24."""
         d, dev = self.dims, self.device
         sd = _strip_prefix(state_dict)
+        if changed is None or self._packs is None:
+            changed = {"embeddings", *range(d.layers)}
+            self._packs = {}
+            self._layers = (_lib.VitLayer * d.layers)()
 
-        def f32(name):
-            t = sd[name].detach().to(device=dev, dtype=torch.float32).contiguous()
-            self._keep.append(t)
-            return t
+        def group(key):
+            keep = []
+            self._packs[key] = keep
 
-        def f16(t):
-            t = t.detach().to(device=dev, dtype=torch.float32).to(torch.float16).contiguous()
-            self._keep.append(t)
-            return t
+            def f32(t):
+                t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+                keep.append(t)
+                return t
 
-        self._keep = []
-        pw = sd["embeddings.patch_embedding.weight"].detach().to(dev, torch.float32).reshape(d.hidden, d.patch_k)
-        pw_pad = torch.zeros((d.hidden, d.patch_k_pad), dtype=torch.float32, device=dev)
-        pw_pad[:, : d.patch_k] = pw
-        patch_w = f16(pw_pad)
-        cls = f32("embeddings.class_embedding")
-        pos = f32("embeddings.position_embedding.weight")
-        if pos.shape != (d.tokens, d.hidden):
-            raise PigeonB200Error(f"position_embedding {tuple(pos.shape)} != ({d.tokens}, {d.hidden})")
-        pre_g, pre_b = f32("pre_layrnorm.weight"), f32("pre_layrnorm.bias")
+            def f16(t):
+                t = t.detach().to(device=dev, dtype=torch.float32).to(torch.float16).contiguous()
+                keep.append(t)
+                return t
+            return f32, f16
 
-        layers = (_lib.VitLayer * d.layers)()
-        for i in range(d.layers):
+        if "embeddings" in changed:
+            f32, f16 = group("embeddings")
+            pw = sd["embeddings.patch_embedding.weight"].detach().to(dev, torch.float32).reshape(d.hidden, d.patch_k)
+            pw_pad = torch.zeros((d.hidden, d.patch_k_pad), dtype=torch.float32, device=dev)
+            pw_pad[:, : d.patch_k] = pw
+            pos = f32(sd["embeddings.position_embedding.weight"])
+            if pos.shape != (d.tokens, d.hidden):
+                raise PigeonB200Error(f"position_embedding {tuple(pos.shape)} != ({d.tokens}, {d.hidden})")
+            self._top = (ptr(f16(pw_pad)), ptr(f32(sd["embeddings.class_embedding"])), ptr(pos),
+                         ptr(f32(sd["pre_layrnorm.weight"])), ptr(f32(sd["pre_layrnorm.bias"])))
+
+        for i in sorted(k for k in changed if k != "embeddings"):
+            f32, f16 = group(i)
             p = f"encoder.layers.{i}."
-            wq, wk, wv = (sd[p + f"self_attn.{n}_proj.weight"] for n in "qkv")
-            bq, bk, bv = (sd[p + f"self_attn.{n}_proj.bias"] for n in "qkv")
-            w_qkv = f16(torch.cat([wq, wk, wv], dim=0))
-            b_qkv = torch.cat([bq, bk, bv], dim=0).detach().to(dev, torch.float32).contiguous()
-            self._keep.append(b_qkv)
-            L = layers[i]
-            L.ln1_g, L.ln1_b = ptr(f32(p + "layer_norm1.weight")), ptr(f32(p + "layer_norm1.bias"))
-            L.w_qkv, L.b_qkv = ptr(w_qkv), ptr(b_qkv)
-            L.w_o, L.b_o = ptr(f16(sd[p + "self_attn.out_proj.weight"])), ptr(f32(p + "self_attn.out_proj.bias"))
-            L.ln2_g, L.ln2_b = ptr(f32(p + "layer_norm2.weight")), ptr(f32(p + "layer_norm2.bias"))
-            L.w_fc1, L.b_fc1 = ptr(f16(sd[p + "mlp.fc1.weight"])), ptr(f32(p + "mlp.fc1.bias"))
-            L.w_fc2, L.b_fc2 = ptr(f16(sd[p + "mlp.fc2.weight"])), ptr(f32(p + "mlp.fc2.bias"))
+            w_qkv = torch.cat([sd[p + f"self_attn.{n}_proj.weight"] for n in "qkv"], dim=0)
+            b_qkv = torch.cat([sd[p + f"self_attn.{n}_proj.bias"] for n in "qkv"], dim=0)
+            L = self._layers[i]
+            L.ln1_g, L.ln1_b = ptr(f32(sd[p + "layer_norm1.weight"])), ptr(f32(sd[p + "layer_norm1.bias"]))
+            L.w_qkv, L.b_qkv = ptr(f16(w_qkv)), ptr(f32(b_qkv))
+            L.w_o, L.b_o = ptr(f16(sd[p + "self_attn.out_proj.weight"])), ptr(f32(sd[p + "self_attn.out_proj.bias"]))
+            L.ln2_g, L.ln2_b = ptr(f32(sd[p + "layer_norm2.weight"])), ptr(f32(sd[p + "layer_norm2.bias"]))
+            L.w_fc1, L.b_fc1 = ptr(f16(sd[p + "mlp.fc1.weight"])), ptr(f32(sd[p + "mlp.fc1.bias"]))
+            L.w_fc2, L.b_fc2 = ptr(f16(sd[p + "mlp.fc2.weight"])), ptr(f32(sd[p + "mlp.fc2.bias"]))
             if self.fold_layernorm:
                 # LN(x) W^T + b = rstd * (x (gamma*W)^T - mu * rowsum(gamma*W)) + (b + W beta): the tensor cores see the raw
                 # row x and W' = gamma * W; rowsum is taken over the fp16 values of W' so that acc - mu * rowsum is exact.
                 def fold(w, b, g, beta):
                     w32 = w.detach().to(dev, torch.float32)
-                    wf = f16(w32 * g[None, :])
-                    cs = wf.float().sum(dim=1).contiguous()
-                    bf = (b.detach().to(dev, torch.float32) + w32 @ beta).contiguous()
-                    self._keep += [cs, bf]
+                    wf = f16(w32 * g.detach().to(dev, torch.float32)[None, :])
+                    cs = f32(wf.float().sum(dim=1))
+                    bf = f32(b.detach().to(dev, torch.float32) + w32 @ beta.detach().to(dev, torch.float32))
                     return ptr(wf), ptr(bf), ptr(cs)
-                g1, be1 = sd[p + "layer_norm1.weight"].detach().to(dev, torch.float32), sd[p + "layer_norm1.bias"].detach().to(dev, torch.float32)
-                g2, be2 = sd[p + "layer_norm2.weight"].detach().to(dev, torch.float32), sd[p + "layer_norm2.bias"].detach().to(dev, torch.float32)
-                L.w_qkv_ln, L.b_qkv_ln, L.cs_qkv = fold(torch.cat([wq, wk, wv], dim=0), torch.cat([bq, bk, bv], dim=0), g1, be1)
-                L.w_fc1_ln, L.b_fc1_ln, L.cs_fc1 = fold(sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"], g2, be2)
+                L.w_qkv_ln, L.b_qkv_ln, L.cs_qkv = fold(w_qkv, b_qkv, sd[p + "layer_norm1.weight"], sd[p + "layer_norm1.bias"])
+                L.w_fc1_ln, L.b_fc1_ln, L.cs_fc1 = fold(sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"],
+                                                         sd[p + "layer_norm2.weight"], sd[p + "layer_norm2.bias"])
 
         cfg = _lib.VitConfig(d.image_size, d.patch_size, d.hidden, d.heads, d.intermediate, d.layers, d.ln_eps,
                              d.patch_k_pad)
-        w = _lib.VitWeights(ptr(patch_w), ptr(cls), ptr(pos), ptr(pre_g), ptr(pre_b), layers)
+        w = _lib.VitWeights(*self._top, self._layers)
         if self._handle:
             self._lib.pg_vit_destroy(self._handle)
             self._handle = C.c_void_p()
-        check(self._lib.pg_vit_create(C.byref(cfg), C.byref(w), C.byref(self._handle)), "pg_vit_create")
+        check(self._lib.pg_vit_create(C.byref(cfg), C.byref(w), C.byref(self._handle)), "pg_vit_create")   # copies the structs
 
     def __del__(self):
         try:

@@ -35,12 +35,18 @@ def evaluate(model: str, dataset, yfcc: bool, landmarks: bool = False, base_mode
     full_model = SuperGuessr(embed_model, panorama=True, hierarchical=False, multi_task=False, heading=heading,
                              freeze_base=True, yfcc=yfcc, num_candidates=50)               # :42-44
     full_model.to('cuda')
-    full_model.load_state(model)                                                           # :45-46
+    # :45-46 — the PIGEOTTO head first, then `model` on top: entries `model` does not carry keep the base head's values
+    full_model.load_state(cfg.CLIP_PRETRAINED_HEAD_YFCC)
+    full_model.load_state(model)
     refiner = None
     if refine:                                                                             # :50-80
         proto_model_path = cfg.PROTO_MODEL_YFCC_PATH if yfcc else cfg.PROTO_MODEL_PATH
         proto_path = cfg.PROTO_PATH_YFCC if yfcc else cfg.PROTO_PATH
         dataset_path = cfg.DATASET_PATH_YFCC if yfcc else cfg.DATASET_PATH
+        if landmarks:                                                                      # :57-60: YFCC + landmarks bank
+            proto_path = cfg.PROTO_PATH_LANDMARKS
+            proto_model_path = cfg.PROTO_MODEL_LANDMARKS_PATH
+            dataset_path = [cfg.DATASET_PATH_YFCC, cfg.DATASET_PATH_LANDMARKS]
         protos = None
         try:
             protos = torch.load(proto_model_path, map_location='cpu', weights_only=False).protos

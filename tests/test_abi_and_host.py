@@ -73,6 +73,11 @@ def test_bank_from_arrays_matches_manual_means():
     m = torch.from_numpy(data).mean(1)
     np.testing.assert_allclose(b["proto_emb"][1], m[[1, 2, 3]].mean(0).numpy(), rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(b["data_emb"], m.numpy())
+    # the CSV `count` column, when given, is what the single-member shortcut tests (proto_refiner.py:243-244) — also where it
+    # disagrees with the length of the index list
+    b2 = bank_mod.bank_from_arrays(cells, rng.uniform(-90, 90, (5, 2)), idx, torch.from_numpy(data), ll, num_cells=6,
+                                   proto_count=[1, 7, 2, 9, 1])
+    assert b2["proto_count"].tolist() == [7, 1, 2, 1] and b2["member_idx"].tolist() == b["member_idx"].tolist()
 
 
 def test_module_surface_matches_reference_signatures():
@@ -334,6 +339,40 @@ def test_state_dict_is_a_plain_weights_file(tmp_path):
     sd = torch.load(path, map_location="cpu", weights_only=True)
     assert set(sd) == set(sg.state_dict())
     assert "base_model.vision_model.encoder.layers.1.mlp.fc2.weight" in sd and "cell_layer.weight" in sd and "lla_geocells" in sd
+
+
+def test_model_summary_text_and_partial_freeze():
+    """`print(model)` is what the reference's run scripts log (models/super_guessr.py:486-501): same lines, same tabs.  A CLIP
+    tower that is not frozen keeps only its last encoder layer trainable (:146-160; the pretrained-head load is skipped in
+    serving mode, so this runs without a checkpoint)."""
+    from pigeon_b200 import CLIPVisionTower, SuperGuessr, VitDims, synthetic
+    dims = VitDims(image_size=56, patch_size=14, hidden=256, heads=4, intermediate=512, layers=3)
+    sg = SuperGuessr(CLIPVisionTower(dims), panorama=True, serving=True, geocells=synthetic.synthetic_geocells(12, 0))
+    assert str(sg) == ("SuperGuessr(\n\tbase_model\t= True\n\tpanorama\t= True\n\thierarchical\t= False\n"
+                       "\tmulti-task\t= False\n\tyfcc\t\t= False\n\tembedding_size\t= 256\n\tinput_dim\t= 256\n"
+                       "\tnum_geocells\t= 12\n\tlabel_smoothing\t= False\n\tuses_headings\t= False\n"
+                       "\tfreeze_base\t= False\n\tserving\t\t= True\n)")
+    frozen = SuperGuessr(CLIPVisionTower(dims), freeze_base=True, geocells=synthetic.synthetic_geocells(12, 0))
+    assert not any(p.requires_grad for p in frozen.base_model.parameters())
+    assert all(p.requires_grad for p in frozen.cell_layer.parameters())
+
+
+def test_load_state_copies_by_name_and_reports_unknown_keys(tmp_path, capsys):
+    """models/super_guessr.py:222-238."""
+    from pigeon_b200 import SuperGuessr
+    sg = SuperGuessr(None, panorama=True, embed_dim=16, geocells=np.zeros((5, 2)))
+    sd = {k: torch.full_like(v, 0.5) for k, v in sg.state_dict().items() if v.is_floating_point()}
+    sd["not_a_parameter"] = torch.zeros(1)
+    path = tmp_path / "head.model"
+    torch.save(sd, path)
+    real_load = torch.load
+    try:
+        torch.load = lambda f, map_location=None, **kw: real_load(f, map_location="cpu", **kw)   # no GPU in this suite
+        sg.load_state(str(path))
+    finally:
+        torch.load = real_load
+    assert "Parameter not_a_parameter not in model's state." in capsys.readouterr().out
+    assert float(sg.cell_layer.weight.detach().mean()) == 0.5
 
 
 def test_docs_only_name_entry_points_that_exist():

@@ -59,6 +59,26 @@ def test_loss_grad_matches_oracle(cuda, G, mode):
     assert np.abs(dl.cpu().numpy() - xl.grad.numpy()).max() <= 2e-7 * np.abs(ref_g).max()
 
 
+def test_loss_with_label_out_of_range_is_nan_not_a_wild_read(cuda):
+    """include/pigeon_b200.h (pg_head_loss): a class index outside [0, C) poisons the loss and zeroes that gradient row."""
+    from pigeon_b200._lib import check, current_stream_ptr, load, ptr
+    lib = load()
+    Cc, B = 130, 4
+    logits = torch.randn(B, Cc, generator=torch.Generator().manual_seed(3)).to(cuda)
+    idx = torch.tensor([5, Cc, -100, 7], dtype=torch.int64, device=cuda)
+    per = torch.empty(B, dtype=torch.float64, device=cuda)
+    out = torch.empty(1, dtype=torch.float64, device=cuda)
+    dl = torch.full((B, Cc), 9.0, dtype=torch.float32, device=cuda)
+    check(lib.pg_head_loss_grad(ptr(logits), B, Cc, 0, ptr(idx), None, None, None, 65.0, 1.0, ptr(per), ptr(out), ptr(dl),
+                                current_stream_ptr()), "pg_head_loss_grad")
+    torch.cuda.synchronize()
+    assert torch.isnan(out).item()
+    assert torch.isnan(per[1]).item() and torch.isnan(per[2]).item() and torch.isfinite(per[[0, 3]]).all()
+    assert (dl[1] == 0).all() and (dl[2] == 0).all()
+    ref = torch.nn.functional.cross_entropy(logits[[0, 3]].double().cpu(), idx[[0, 3]].cpu(), reduction="none")
+    np.testing.assert_allclose(per[[0, 3]].cpu().numpy(), ref.numpy(), rtol=1e-12)
+
+
 @pytest.mark.parametrize("B,Cc,D,acc", [(8, 1000, 128, 0), (37, 2076, 1024, 1), (256, 130, 768, 0)])
 def test_head_backward_matches_fp64(cuda, B, Cc, D, acc):
     from pigeon_b200._lib import check, current_stream_ptr, load, ptr
