@@ -121,12 +121,23 @@ class CLIPVisionTower(nn.Module):
     def _weights_version(self):
         return tuple((p.data_ptr(), p._version, _versions.get(p)) for p in self.parameters())
 
+    def _group_versions(self):
+        """Version key per repack group: "embeddings" (patch / class / position embeddings, pre-LayerNorm) and one per encoder
+        layer — under the reference's fine-tune policy only the last layer moves between optimizer steps."""
+        def key(module_params):
+            return tuple((p.data_ptr(), p._version, _versions.get(p)) for p in module_params)
+        vm = self.vision_model
+        groups = {"embeddings": key(list(vm.embeddings.parameters()) + list(vm.pre_layrnorm.parameters()))}
+        for i, layer in enumerate(vm.encoder.layers):
+            groups[i] = key(layer.parameters())
+        return groups
+
     def engine(self) -> VitEngine:
         p0 = next(self.parameters())
         if not p0.is_cuda:
             raise PigeonB200Error("CLIPVisionTower is on the CPU: move the model with .to('cuda') — the B200 path "
                                   "has no CPU implementation")
-        v = self._weights_version()
+        v = self._group_versions()
         if self._engine is None or self._packed_version != v:
             sd = {k: t.detach() for k, t in self.state_dict().items()}
             if (self._engine is None or self._engine.device != p0.device
@@ -134,7 +145,9 @@ class CLIPVisionTower(nn.Module):
                 self._engine = VitEngine(sd, self.dims, device=p0.device, max_views_per_pass=self.max_views_per_pass,
                                          fold_layernorm=self.fold_layernorm)
             else:
-                self._engine.load_state_dict(sd)
+                old = self._packed_version
+                changed = None if old is None else {g for g, key in v.items() if old.get(g) != key}
+                self._engine.load_state_dict(sd, changed=changed)
             self._packed_version = v
         return self._engine
 

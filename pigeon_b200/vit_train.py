@@ -97,20 +97,23 @@ class TowerTrainer:
         self._saved, self._saved_layers, self._saved_views = saved, layers, n_views
 
     def _transposed_weights(self):
-        v = self.tower._weights_version()
-        if self._wt is not None and self._wt_version == v:
-            return self._wt
-        out = []
+        """bf16 transposes of the four weight matrices of every layer (B operands of the backward GEMMs); only the layers whose
+        parameters moved since the last call are redone (the last one, under the reference's fine-tune policy)."""
+        versions = self.tower._group_versions()
+        if self._wt is None:
+            self._wt, self._wt_version = [None] * self.dims.layers, {}
         bf = torch.bfloat16
         with torch.no_grad():
-            for L in self.tower.vision_model.encoder.layers:
+            for l, L in enumerate(self.tower.vision_model.encoder.layers):
+                if self._wt[l] is not None and self._wt_version.get(l) == versions[l]:
+                    continue
                 sa, mlp = L.self_attn, L.mlp
                 wqkv = torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], dim=0)      # [3H, H]
-                out.append(dict(w_qkv_t=wqkv.t().contiguous().to(bf), w_o_t=sa.out_proj.weight.t().contiguous().to(bf),
-                                w_fc1_t=mlp.fc1.weight.t().contiguous().to(bf),
-                                w_fc2_t=mlp.fc2.weight.t().contiguous().to(bf)))
-        self._wt, self._wt_version = out, v
-        return out
+                self._wt[l] = dict(w_qkv_t=wqkv.t().contiguous().to(bf), w_o_t=sa.out_proj.weight.t().contiguous().to(bf),
+                                   w_fc1_t=mlp.fc1.weight.t().contiguous().to(bf),
+                                   w_fc2_t=mlp.fc2.weight.t().contiguous().to(bf))
+                self._wt_version[l] = versions[l]
+        return self._wt
 
     def _pending_grads(self):
         if self._pending is not None:

@@ -341,6 +341,23 @@ def test_state_dict_is_a_plain_weights_file(tmp_path):
     assert "base_model.vision_model.encoder.layers.1.mlp.fc2.weight" in sd and "cell_layer.weight" in sd and "lla_geocells" in sd
 
 
+def test_repack_groups_follow_the_parameters_that_moved():
+    """After an optimizer step only the groups whose parameters changed are repacked for the kernels (one encoder layer under
+    the reference's last-layer fine-tune policy, train_eval_loop.py:187 + super_guessr.py:159-160)."""
+    from pigeon_b200 import CLIPVisionTower, VitDims, _versions
+    dims = VitDims(image_size=56, patch_size=14, hidden=256, heads=4, intermediate=512, layers=3)
+    tower = CLIPVisionTower(dims)
+    before = tower._group_versions()
+    assert set(before) == {"embeddings", 0, 1, 2}
+    for p in tower.vision_model.encoder.layers[2].parameters():
+        _versions.bump(p)                                   # what pg_adamw_step's wrapper does after a raw-pointer update
+    after = tower._group_versions()
+    assert {g for g in after if after[g] != before[g]} == {2}
+    with torch.no_grad():
+        tower.vision_model.embeddings.class_embedding.add_(1.0)   # an in-place torch update bumps ._version
+    assert {g for g in after if tower._group_versions()[g] != after[g]} == {"embeddings"}
+
+
 def test_model_summary_text_and_partial_freeze():
     """`print(model)` is what the reference's run scripts log (models/super_guessr.py:486-501): same lines, same tabs.  A CLIP
     tower that is not frozen keeps only its last encoder layer trainable (:146-160; the pretrained-head load is skipped in

@@ -7,7 +7,7 @@ export ATTN_AB_VARIANTS="1:0,0:2,3:0,3:3,3:4"
 export ATTN_AB_VARIANTS="0:2,3:0,3:2,3:3,3:4"
 ( timeout 300 python tools/attn_ab.py time 64 2>&1 | tail -12 ) > gpurun_out/r2r_attn_time64.log; tail -5 gpurun_out/r2r_attn_time64.log
 ( timeout 300 python tools/attn_ab.py time 256 2>&1 | tail -12 ) > gpurun_out/r2r_attn_time256.log; tail -5 gpurun_out/r2r_attn_time256.log
-( timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "test_gemm or test_attention" 2>&1 | tail -3 ) > gpurun_out/r2r_pytest.log; tail -2 gpurun_out/r2r_pytest.log
+( timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_vit.py tests/test_gpu_train.py -x -q -m gpu -k "test_gemm or test_attention or vit_tiny or test_vit_large_336 or chunking or train or tower" 2>&1 | tail -3 ) > gpurun_out/r2r_pytest.log; tail -2 gpurun_out/r2r_pytest.log
 ( timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2> gpurun_out/r2r_bench_stderr.log | tail -1 ) > gpurun_out/r2r_bench_n1.json; python -c "
 import json;d=json.load(open('gpurun_out/r2r_bench_n1.json'));print('infer n1 pair:',d['value'],d['ms_per_step'],d['parity_check']['ok'],d.get('family_ms_per_step'))"; tail -2 gpurun_out/r2r_bench_stderr.log
 ( PG_ATTN_VARIANT=fold timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2> gpurun_out/r2r_bench_fold_stderr.log | tail -1 ) > gpurun_out/r2r_bench_n1_fold.json; python -c "
