@@ -274,6 +274,21 @@ int pg_profile_end(void);
 void pg_profile_read(const char** names, float* ms, int32_t* counts, int32_t n);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Multi-GPU exchange: the all-gather of per-rank results that the reference does with accelerate's
+ * `gather` (preprocessing/embed.py:36-37; in evaluation the per-rank head outputs before the retrieval step).  One process
+ * per GPU.  NCCL is resolved at run time by soname (libnccl.so.2): no link-time dependency, never loaded by single-GPU callers.
+ * ------------------------------------------------------------------------------------------------- */
+/* id128: HOST buffer of 128 bytes (ncclUniqueId).  Rank 0 creates it and hands it to the other ranks by any side channel. */
+int pg_nccl_unique_id(void* id128);
+/* Collective over the n_ranks processes (ncclCommInitRank on the current device).  *comm is an ncclComm_t. */
+int pg_nccl_comm_create(const void* id128, int32_t n_ranks, int32_t rank, void** comm);
+void pg_nccl_comm_destroy(void* comm);
+/* recv[r * bytes_per_rank ...] = rank r's send[0 .. bytes_per_rank), for every r, enqueued on `stream` (ncclAllGather of
+ * bytes: the caller packs whatever it exchanges - embeddings f32 [B, V, D], top-k candidates, predictions - into one
+ * buffer, as pigeon_b200/dist.py does).  `comm` may also be a communicator the host created itself with NCCL. */
+int pg_allgather_embeddings(void* comm, const void* send, void* recv, size_t bytes_per_rank, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Building blocks (exported for unit tests and for callers that fuse differently)
  * ------------------------------------------------------------------------------------------------- */
 enum {

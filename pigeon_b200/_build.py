@@ -28,6 +28,7 @@ SOURCES = [
     "attention_pair_tcgen05.cu",
     "attention_split_tcgen05.cu",
     "attention_fold_tcgen05.cu",
+    "nccl_gather.cu",
     "vit_misc.cu",
     "head.cu",
     "refiner.cu",
@@ -98,7 +99,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         objs = list(ex.map(compile_one, SOURCES))
     tmp = LIB_PATH.with_suffix(".so.tmp")
     cmd = [nvcc, "-shared", "-o", str(tmp), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a",
-           "-cudart", "static", "-Xlinker", "--exclude-libs,ALL"]
+           "-cudart", "static", "-Xlinker", "--exclude-libs,ALL", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -118,6 +118,10 @@ SIGNATURES = {
     "pg_profile_begin": (None, []),
     "pg_profile_end": (c_int32, []),
     "pg_profile_read": (None, [C.POINTER(C.c_char_p), C.POINTER(c_float), C.POINTER(c_int32), c_int32]),
+    "pg_nccl_unique_id": (c_int32, [c_void_p]),
+    "pg_nccl_comm_create": (c_int32, [c_void_p, c_int32, c_int32, C.POINTER(c_void_p)]),
+    "pg_nccl_comm_destroy": (None, [c_void_p]),
+    "pg_allgather_embeddings": (c_int32, [c_void_p, c_void_p, c_void_p, C.c_size_t, c_void_p]),
     "pg_gemm_f16": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32,
                               c_int32, c_int32, c_void_p]),
     "pg_layernorm_f16": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p]),

@@ -13,8 +13,9 @@
 //     in a 5th k-step: Q' = [c q | -ref 0 .. 0] (80 columns), K' = [k | 1 0 .. 0] (a constant shared-memory tile), so that
 //     S' = Q' K'^T arrives in TMEM as c q.k - ref, the exponent itself.  ref = (maximum of the row's first KV block) + 4,
 //     rounded to fp16; the first block of a job is computed without the extra k-step and shifted in registers.
-//   * the row sum l = sum_j P_j . 1 is a third MMA per block, P (128 x 64, TMEM) times a constant 64 x 16 tile whose first
-//     column is ones, into a 16-column accumulator next to O.
+//   * the row sum l = sum_j P_j . 1 is column 64 of the output accumulator: the P V MMA runs with N = 80, its MN-major B
+//     operand being the V block followed (leading-dimension offset of the descriptor = distance to the constant tile) by 16
+//     columns [1 0 .. 0] — the same shared-memory tile that extends K.
 //   Per logit the softmax warps are left with: tcgen05.ld, ex2 (MUFU, or the FMA-pipe polynomial for a share of them), pack.
 //   * no running maximum, no rescale: P = 2^(S') is fp16, so a row is exact while its largest logit stays within
 //     [ref - 24, ref + 16) log2 units.  A row that overflows shows l = inf in the epilogue, which then recomputes that row
@@ -22,7 +23,7 @@
 //     row maximum lose precision or vanish, as they do in any fp16-P attention kernel.
 //
 // TMEM columns: tile 0 S buffers [0,64) [64,128), tile 1 [128,192) [192,256) (P aliases the first 32 columns of its S buffer
-// as packed fp16), O0 [256,320) O1 [320,384), l0 [384,400) l1 [400,416), Q'0 [416,456) Q'1 [464,504).
+// as packed fp16), O0 | l0 [256,336) O1 | l1 [336,416) (column 64 of each = row sum), Q'0 [416,456) Q'1 [464,504).
 // Warps: 0-3 softmax tile 0, 4-7 softmax tile 1, 8-11 epilogue, 12 TMA producer, 13 / 14 MMA issuers of tile 0 / 1 (13 also
 // allocates TMEM), 15 idle.
 #include "attention.h"
@@ -48,13 +49,15 @@ constexpr int kSlots = 8;                              // K/V ring of 16 KB slot
 constexpr int kSlotBytes = 2 * kSubBytes;
 constexpr int kThreads = 512;                          // 16 warps: setmaxnreg is a per-warpgroup (4 warps) operation
 constexpr int kWarpEpi = 8, kWarpTma = 12, kWarpMma = 13;   // MMA issuers: warp 13 (tile 0), warp 14 (tile 1)
-constexpr uint32_t kColS = 0, kColO = 256, kColL = 384, kColQ = 416;
+constexpr uint32_t kColS = 0, kColO = 256, kColQ = 416;
+constexpr int kOCols = 80;                             // 64 output columns, the row sum, 15 zero columns
 constexpr int kQCols = 40;                             // 80 fp16 per row: 64 of c*q, then -ref and 15 zeros
 constexpr int kQStride = 48;                           // column distance between the two tiles' Q'
+static_assert(kQCols <= kQStride && kColQ + kQStride + kQCols <= 512, "Q' does not fit");
 constexpr int kTmemCols = 512;
 constexpr float kRefMargin = 4.0f;                     // ref = first-block maximum + 4: P <= 2^-4 there, overflow 20 binades above
-constexpr int kOnesKBytes = kSub * 128;                // K' extension: 64 rows x 128 B (only the first k-step, 32 B, is read)
-constexpr int kOnesLBytes = 16 * 128;                  // row-sum B operand: 16 rows (N) x 64 k, row 0 = ones
+constexpr int kOnesBytes = kSub * 128;                 // constant tile: 64 rows (kv index) x 128 B, element 0 of every row = 1.0.  Read
+                                                       // K-major as the 5th k-step of K' and MN-major as columns 64..79 of V'
 
 struct Bars {
   uint64_t kv_full[kSlots], kv_empty[kSlots];
@@ -70,9 +73,8 @@ struct Bars {
 };
 constexpr int kRingBytes = kSlots * kSlotBytes;
 constexpr int kOffQ = kRingBytes;
-constexpr int kOffOnesK = kOffQ + 2 * kQBytes;
-constexpr int kOffOnesL = kOffOnesK + kOnesKBytes;
-constexpr int kOffBars = kOffOnesL + kOnesLBytes;
+constexpr int kOffOnes = kOffQ + 2 * kQBytes;
+constexpr int kOffBars = kOffOnes + kOnesBytes;
 constexpr int kOffRef = kOffBars + 1024;
 constexpr int kSmemBytes = 1024 + kOffRef + 2 * kBlock * 4;
 
@@ -224,8 +226,7 @@ attention_fold_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FoldAr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_kv = smem;
   uint8_t* smem_q = smem + kOffQ;
-  uint8_t* smem_ones_k = smem + kOffOnesK;
-  uint8_t* smem_ones_l = smem + kOffOnesL;
+  uint8_t* smem_ones = smem + kOffOnes;
   Bars* bars = reinterpret_cast<Bars*>(smem + kOffBars);
   float* refs = reinterpret_cast<float*>(smem + kOffRef);   // [slot][row]: the row's reference (log2 units), for lse2
 
@@ -238,17 +239,10 @@ attention_fold_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FoldAr
   const int n_jobs = args.n_jobs;
   const int stride = gridDim.x;
 
-  // constant B operands (128-byte swizzle: 16-byte piece c of row r sits at piece c ^ (r & 7))
-  for (int x = threadIdx.x; x < (kOnesKBytes + kOnesLBytes) / 16; x += kThreads) {
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (x < kOnesKBytes / 16) {
-      const int r = x >> 3, piece = x & 7;
-      if (piece == (r & 7)) v.x = 0x00003C00u;                 // K'[r][64] = 1.0: element 0 of logical piece 0
-    } else {
-      const int r = (x - kOnesKBytes / 16) >> 3;
-      if (r == 0) v = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);   // row n = 0: ones over all 64 k
-    }
-    reinterpret_cast<uint4*>(smem_ones_k)[x] = v;
+  // constant B operand (128-byte swizzle: 16-byte piece c of row r sits at piece c ^ (r & 7)): element 0 of every row = 1.0
+  for (int x = threadIdx.x; x < kOnesBytes / 16; x += kThreads) {
+    const int r = x >> 3, piece = x & 7;
+    reinterpret_cast<uint4*>(smem_ones)[x] = make_uint4(piece == (r & 7) ? 0x00003C00u : 0u, 0u, 0u, 0u);
   }
   fence_proxy_async_smem();
 
@@ -350,29 +344,9 @@ attention_fold_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FoldAr
         }
         const bool full = (j < nb - 1) || (last_valid == kSub);
         const int valid = full ? kSub : last_valid;
-        float shift = 0.f;
-        if (j == 0) {
-          // ---- reference of the job: maximum of the first block (c q.k, log2 units) + margin, as an fp16 value.  Written
-          // (negated) into column 64 of Q', so that every later block of the job comes out of the MMA already shifted.
+        // Q'[:, 64] = -ref and the go-ahead for the MMA warp to issue this job's later blocks
+        auto publish_ref = [&]() {
           if (warp_active) {
-            float b0 = -INFINITY, b1 = -INFINITY;
-            for (int ch = 0; ch * 16 < valid; ++ch) {
-              uint32_t r[16];
-              tmem_ld16p(s_tmem + 16 * ch, r);
-              tmem_ld_wait16(r);
-              if ((ch + 1) * 16 <= valid) {
-#pragma unroll
-                for (int x = 0; x < 16; x += 4) {
-                  b0 = fmax3(b0, __uint_as_float(r[x]), __uint_as_float(r[x + 1]));
-                  b1 = fmax3(b1, __uint_as_float(r[x + 2]), __uint_as_float(r[x + 3]));
-                }
-              } else {
-#pragma unroll
-                for (int x = 0; x < 16; ++x)
-                  if (ch * 16 + x < valid) b0 = fmaxf(b0, __uint_as_float(r[x]));
-              }
-            }
-            ref = __half2float(__float2half_rn(fmaxf(b0, b1) + kRefMargin));
             uint32_t qe[8];
             qe[0] = pack_half2(-ref, 0.f);
 #pragma unroll
@@ -383,35 +357,49 @@ attention_fold_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FoldAr
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->ref_ready[i]);
-          shift = -ref;
-        }
-        if (!warp_active) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->p_ready[i][b]);
-          ++n_blk;
-          continue;
-        }
-        if (full) {
-          // ---- a block of 64 valid key columns: one branch-free basic block; all 64 exponents are in registers before P
-          // (packed fp16) goes over the first 32 columns of the same buffer
-          uint32_t pk[32];
-          uint32_t ra[16], rb[16];
-          tmem_ld16p(s_tmem, ra);
-          if (j == 0) {
-            const float2 sh2 = make_float2(shift, shift);
+        };
+        if (j == 0 && full) {
+          // ---- first block of a job: all 64 logits (c q.k, log2 units) into registers once; reference = their maximum + margin
+          // as an fp16 value; then P = 2^(x - ref) from the same registers
+          if (!warp_active) {
+            publish_ref();
+          } else {
+            uint32_t r0[16], r1[16], r2[16], r3[16], pk[32];
+            tmem_ld16p(s_tmem, r0);
+            tmem_ld16p(s_tmem + 16, r1);
+            tmem_ld16p(s_tmem + 32, r2);
+            tmem_ld16p(s_tmem + 48, r3);
+            tmem_ld_wait16(r0);
+            tmem_ld_wait16(r1);
+            tmem_ld_wait16(r2);
+            tmem_ld_wait16(r3);
+            float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
+#pragma unroll
+            for (int x = 0; x < 16; x += 2) {
+              b0 = fmax3(b0, __uint_as_float(r0[x]), __uint_as_float(r0[x + 1]));
+              b1 = fmax3(b1, __uint_as_float(r1[x]), __uint_as_float(r1[x + 1]));
+              b2 = fmax3(b2, __uint_as_float(r2[x]), __uint_as_float(r2[x + 1]));
+              b3 = fmax3(b3, __uint_as_float(r3[x]), __uint_as_float(r3[x + 1]));
+            }
+            ref = __half2float(__float2half_rn(fmaxf(fmaxf(b0, b1), fmaxf(b2, b3)) + kRefMargin));
+            publish_ref();
+            const float2 sh2 = make_float2(-ref, -ref);
+            exp_chunk<POLY, true>(r0, pk, sh2);
+            exp_chunk<POLY, true>(r1, pk + 8, sh2);
+            exp_chunk<POLY, true>(r2, pk + 16, sh2);
+            exp_chunk<POLY, true>(r3, pk + 24, sh2);
+            tmem_st32p(s_tmem, pk);
+          }
+        } else if (full) {
+          if (warp_active) {
+            // ---- a later block of 64 valid key columns: the exponents come out of the MMA; one branch-free basic block, all 64
+            // in registers before P (packed fp16) goes over the first 32 columns of the same buffer
+            uint32_t pk[32];
+            uint32_t ra[16], rb[16];
+            const float2 z2 = make_float2(0.f, 0.f);
+            tmem_ld16p(s_tmem, ra);
 #pragma unroll
             for (int ch = 0; ch < 4; ch += 2) {   // software-pipelined: the next chunk's load is in flight during the arithmetic
-              tmem_ld_wait16(ra);
-              tmem_ld16p(s_tmem + 16 * (ch + 1), rb);
-              exp_chunk<POLY, true>(ra, pk + 8 * ch, sh2);
-              tmem_ld_wait16(rb);
-              if (ch + 2 < 4) tmem_ld16p(s_tmem + 16 * (ch + 2), ra);
-              exp_chunk<POLY, true>(rb, pk + 8 * (ch + 1), sh2);
-            }
-          } else {
-            const float2 z2 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int ch = 0; ch < 4; ch += 2) {
               tmem_ld_wait16(ra);
               tmem_ld16p(s_tmem + 16 * (ch + 1), rb);
               exp_chunk<POLY, false>(ra, pk + 8 * ch, z2);
@@ -419,27 +407,51 @@ attention_fold_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FoldAr
               if (ch + 2 < 4) tmem_ld16p(s_tmem + 16 * (ch + 2), ra);
               exp_chunk<POLY, false>(rb, pk + 8 * (ch + 1), z2);
             }
+            tmem_st32p(s_tmem, pk);
           }
-          tmem_st32p(s_tmem, pk);
         } else {
-          // ---- ragged last block: nfull whole 16-column chunks + `rem` valid columns of one more (P of chunk ch lands on S
-          // columns of chunks <= ch, already read)
+          // ---- ragged last block (also the first one when the sequence is shorter than a block): nfull whole 16-column
+          // chunks + `rem` valid columns of one more (P of chunk ch lands on S columns of chunks <= ch, already read)
           const int nfull = valid >> 4, rem = valid & 15;
-          const float2 sh2 = make_float2(shift, shift);
-          for (int ch = 0; ch < nfull; ++ch) {
-            uint32_t r[16], pk8[8];
-            tmem_ld16p(s_tmem + 16 * ch, r);
-            tmem_ld_wait16(r);
-            exp_chunk<0, true>(r, pk8, sh2);
-            tmem_st8p(s_tmem + 8 * ch, pk8);
+          if (j == 0) {
+            if (warp_active) {
+              float b0 = -INFINITY;
+              for (int ch = 0; ch * 16 < valid; ++ch) {
+                uint32_t r[16];
+                tmem_ld16p(s_tmem + 16 * ch, r);
+                tmem_ld_wait16(r);
+#pragma unroll
+                for (int x = 0; x < 16; ++x)
+                  if (ch * 16 + x < valid) b0 = fmaxf(b0, __uint_as_float(r[x]));
+              }
+              ref = __half2float(__float2half_rn(b0 + kRefMargin));
+            }
+            publish_ref();
           }
-          if (rem) {
-            uint32_t r[16], pk8[8];
-            tmem_ld16p(s_tmem + 16 * nfull, r);
-            tmem_ld_wait16(r);
-            exp_chunk_masked(r, pk8, rem, shift);
-            tmem_st8p(s_tmem + 8 * nfull, pk8);
+          if (warp_active) {
+            const float shift = (j == 0) ? -ref : 0.f;
+            const float2 sh2 = make_float2(shift, shift);
+            for (int ch = 0; ch < nfull; ++ch) {
+              uint32_t r[16], pk8[8];
+              tmem_ld16p(s_tmem + 16 * ch, r);
+              tmem_ld_wait16(r);
+              exp_chunk<0, true>(r, pk8, sh2);
+              tmem_st8p(s_tmem + 8 * ch, pk8);
+            }
+            if (rem) {
+              uint32_t r[16], pk8[8];
+              tmem_ld16p(s_tmem + 16 * nfull, r);
+              tmem_ld_wait16(r);
+              exp_chunk_masked(r, pk8, rem, shift);
+              tmem_st8p(s_tmem + 8 * nfull, pk8);
+            }
           }
+        }
+        if (!warp_active) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->p_ready[i][b]);
+          ++n_blk;
+          continue;
         }
         tmem_st_wait();
         tc_fence_before();
@@ -475,9 +487,9 @@ attention_fold_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FoldAr
         ++n_e[i];
         tc_fence_after();
         const float ref = refs[i * kBlock + row];
-        const float l_sum = tmem_ld1(tmem_base + lane_base + kColL + 16 * i);
+        const uint32_t o_tmem = tmem_base + lane_base + kColO + kOCols * i;
+        const float l_sum = tmem_ld1(o_tmem + 64);
         const float inv_l = 1.0f / l_sum;
-        const uint32_t o_tmem = tmem_base + lane_base + kColO + 64 * i;
         uint32_t pk[32];
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -578,15 +590,16 @@ attention_fold_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FoldAr
     // smem descriptors of a slot's first (offset 0) / second (offset 8 KB) block: K is K-major (rows of 128 B, k-step = 32 B),
     // V is MN-major (row = kv index, k-step = 16 rows); the two constant tiles are K-major
     const uint64_t k_desc0 = make_smem_desc(smem_u32(smem_kv), 16, 1024, kLayoutSw128);
-    const uint64_t v_desc0 = make_smem_desc(smem_u32(smem_kv), 1024, 1024, kLayoutSw128);
-    const uint64_t ke_desc = make_smem_desc(smem_u32(smem_ones_k), 16, 1024, kLayoutSw128);
-    const uint64_t le_desc = make_smem_desc(smem_u32(smem_ones_l), 16, 1024, kLayoutSw128);
+    const uint64_t v_desc0 = make_smem_desc(smem_u32(smem_kv), 0, 1024, kLayoutSw128);
+    const uint64_t ke_desc = make_smem_desc(smem_u32(smem_ones), 16, 1024, kLayoutSw128);
+    // V' = [V_j | ones tile]: the second 64-wide group of the MN-major operand starts LBO bytes after the first, i.e. at the
+    // constant tile; LBO depends on the slot (descriptor bits [16,30), units of 16 bytes)
+    const uint32_t ones_off16 = (smem_u32(smem_ones) - smem_u32(smem_kv)) >> 4;
     const uint32_t idesc_s = make_idesc_f16(kBlock, kSub, 0, 0);
     const uint32_t idesc_s_last = make_idesc_f16(kBlock, last_n, 0, 0);
-    const uint32_t idesc_pv = make_idesc_f16(kBlock, kHeadDim, 0, 1);    // B (= V) is MN-major
-    const uint32_t idesc_l = make_idesc_f16(kBlock, 16, 0, 0);
-    const uint32_t s_base = tmem_base + kColS + 128 * I, o_base = tmem_base + kColO + 64 * I;
-    const uint32_t l_base = tmem_base + kColL + 16 * I, q_base = tmem_base + kColQ + kQStride * I;
+    const uint32_t idesc_pv = make_idesc_f16(kBlock, kOCols, 0, 1);      // B (= V') is MN-major, N = 64 + 16
+    const uint32_t s_base = tmem_base + kColS + 128 * I, o_base = tmem_base + kColO + kOCols * I;
+    const uint32_t q_base = tmem_base + kColQ + kQStride * I;
     // S[buf] = Q'_I K'_j^T, j = block index inside its job; block 0 without the reference k-step   (inside an elected region)
     auto issue_s = [&](uint64_t kd, int j, uint32_t buf) {
       const uint32_t idesc = (j == nb - 1) ? idesc_s_last : idesc_s;
@@ -646,7 +659,7 @@ attention_fold_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FoldAr
         mbar_wait(&bars->kv_full[slot], (p / kSlots) & 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t vd = v_desc0 + d0;
+          const uint64_t vd = v_desc0 + d0 + ((uint64_t)(ones_off16 - (uint32_t)d0) << 16);
           const uint32_t a = s_base + kSub * (gb & 1);            // P (packed fp16 over the S buffer)
           const int ksteps = (j == nb - 1) ? last_n / 16 : kSub / 16;
           umma_ts(o_base, a, vd, idesc_pv, j != 0);
@@ -655,14 +668,6 @@ attention_fold_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FoldAr
           } else {
 #pragma unroll
             for (int k = 1; k < kSub / 16; ++k) umma_ts(o_base, a + 8 * k, vd + 128 * k, idesc_pv, 1);
-          }
-          // l_I += P . ones
-          umma_ts(l_base, a, le_desc, idesc_l, j != 0);
-          if (j == nb - 1) {
-            for (int k = 1; k < ksteps; ++k) umma_ts(l_base, a + 8 * k, le_desc + 2 * k, idesc_l, 1);
-          } else {
-#pragma unroll
-            for (int k = 1; k < kSub / 16; ++k) umma_ts(l_base, a + 8 * k, le_desc + 2 * k, idesc_l, 1);
           }
           if (j == nb - 1) tc_commit(&bars->o_full[I]);
           if (j + 2 < nb) issue_s(k_desc0 + d1, j + 2, gb & 1);

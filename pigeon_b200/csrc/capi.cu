@@ -461,7 +461,7 @@ int pg_attention_f16(const void* qkv, void* out, int32_t n_views, int32_t seq, i
 int pg_attention_f16_variant(const void* qkv, void* out, float* lse2, int32_t n_views, int32_t seq, int32_t heads,
                              int32_t variant, int32_t poly, void* stream) {
   if (!qkv || !out) { set_last_error("pg_attention_f16_variant: null argument"); return 1; }
-  if (variant < 0 || variant > 2) { set_last_error("pg_attention_f16_variant: variant %d not in {0, 1, 2}", variant); return 1; }
+  if (variant < 0 || variant > 3) { set_last_error("pg_attention_f16_variant: variant %d not in {0, 1, 2, 3}", variant); return 1; }
   return attention_f16_variant(qkv, out, n_views, seq, heads, reinterpret_cast<cudaStream_t>(stream), lse2, variant, poly);
 }
 

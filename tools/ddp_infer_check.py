@@ -68,6 +68,30 @@ def _main():
               f"preds_LLH max |diff| {(ll - ll1).abs().max().item() if ll.shape == ll1.shape else -1:.3e}, "
               f"geocell mismatches {(cell != cell1).sum().item() if cell.shape == cell1.shape else -1})")
         ok = ok and same
+    # the C-ABI exchange entry point on its own communicator (include/pigeon_b200.h: pg_nccl_*, pg_allgather_embeddings): the
+    # 128-byte id travels over torch.distributed, the gathered bytes must equal torch's all_gather of the same buffers
+    import ctypes as Ct
+    from pigeon_b200._lib import check, current_stream_ptr, load, ptr
+    lib = load()
+    idbuf = (Ct.c_char * 128)()
+    if rank == 0:
+        check(lib.pg_nccl_unique_id(idbuf), "pg_nccl_unique_id")
+    idt = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).to(dev)
+    dist.broadcast(idt, 0)
+    idbuf = (Ct.c_char * 128).from_buffer_copy(bytes(idt.cpu().numpy().tobytes()))
+    comm = Ct.c_void_p()
+    check(lib.pg_nccl_comm_create(idbuf, world, rank, Ct.byref(comm)), "pg_nccl_comm_create")
+    send = out1.embedding[lo:hi].contiguous()
+    recv = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=dev)
+    check(lib.pg_allgather_embeddings(comm, ptr(send), ptr(recv), send.numel() * send.element_size(), current_stream_ptr()),
+          "pg_allgather_embeddings")
+    torch.cuda.synchronize()
+    theirs = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(theirs, send)
+    e_gather = torch.equal(recv, torch.stack(theirs)) and torch.equal(recv.reshape(out1.embedding.shape), out1.embedding)
+    lib.pg_nccl_comm_destroy(comm)
+    _say(rank, f"rank {rank} world {world} pg_allgather_embeddings == torch.distributed.all_gather == whole-batch embedding: {e_gather}")
+    ok = ok and e_gather
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()
