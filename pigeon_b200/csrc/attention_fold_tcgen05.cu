@@ -744,16 +744,16 @@ int launch_fold(int variant, const void* qkv, void* out, int n_views, int seq, i
 
 }  // namespace
 
-// poly: share of the exponentials evaluated on the FMA pipe, in eighths (0 .. 4 of every 8 pairs; other values = 3).
+// poly: share of the exponentials evaluated on the FMA pipe, in eighths (0 .. 4 of every 8 pairs; other values = 2).
 int attention_fold_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream, float* lse2,
                        int poly) {
   if (n_views <= 0) return 0;
   switch (poly) {
     case 0: return launch_fold<0x00>(0, qkv, out, n_views, seq, heads, stream, lse2);
     case 1: return launch_fold<0x08>(1, qkv, out, n_views, seq, heads, stream, lse2);
-    case 2: return launch_fold<0x88>(2, qkv, out, n_views, seq, heads, stream, lse2);
+    case 3: return launch_fold<0x4A>(3, qkv, out, n_views, seq, heads, stream, lse2);
     case 4: return launch_fold<0xAA>(4, qkv, out, n_views, seq, heads, stream, lse2);
-    default: return launch_fold<0x4A>(3, qkv, out, n_views, seq, heads, stream, lse2);
+    default: return launch_fold<0x88>(2, qkv, out, n_views, seq, heads, stream, lse2);
   }
 }
 

@@ -472,16 +472,18 @@ int launch_attention(const void* qkv, void* out, int n_views, int seq, int heads
 
 }  // namespace
 
-// Variant switches are read ONCE per process (PG_ATTN_VARIANT: "pair" (default) | "legacy" | "64" | "64s" | "64h" | "32c";
-// PG_ATTN_POLY: eighths of the exponentials on the FMA pipe for the pair kernel, or 4 / 2 = every 4th / 2nd group for
-// the legacy kernel).
+// Variant switches are read ONCE per process (PG_ATTN_VARIANT: unset = fold kernel for inference and pair kernel when the
+// log-sum-exp side output is requested | "fold" | "pair" | "split" | "legacy" | "64" | "64s" | "64h" | "32c";
+// PG_ATTN_POLY: eighths of the exponentials on the FMA pipe for the fold / pair / split kernels, or 4 / 2 = every 4th / 2nd
+// group for the legacy kernel).
 struct AttnSwitches {
-  int variant = 0;   // 0 pair, 1 legacy 32/2/4, 2 "64", 3 "64s", 4 "64h", 5 "32c", 6 split, 7 fold
+  int variant = -1;  // -1 default, 0 pair, 1 legacy 32/2/4, 2 "64", 3 "64s", 4 "64h", 5 "32c", 6 split, 7 fold
   int poly = -1;
   AttnSwitches() {
     const char* v = getenv("PG_ATTN_VARIANT");
     if (v) {
-      if (!strcmp(v, "legacy") || !strcmp(v, "32")) variant = 1;
+      if (!strcmp(v, "pair")) variant = 0;
+      else if (!strcmp(v, "legacy") || !strcmp(v, "32")) variant = 1;
       else if (!strcmp(v, "split")) variant = 6;
       else if (!strcmp(v, "fold")) variant = 7;
       else if (!strcmp(v, "64")) variant = 2;
@@ -499,7 +501,7 @@ int attention_f16_variant(const void* qkv, void* out, int n_views, int seq, int 
   if (n_views <= 0) return 0;
   if (variant == 0) return attention_pair_f16(qkv, out, n_views, seq, heads, stream, lse2, poly < 0 ? 2 : poly);
   if (variant == 2) return attention_split_f16(qkv, out, n_views, seq, heads, stream, lse2, poly < 0 ? 2 : poly);
-  if (variant == 3) return attention_fold_f16(qkv, out, n_views, seq, heads, stream, lse2, poly < 0 ? 3 : poly);
+  if (variant == 3) return attention_fold_f16(qkv, out, n_views, seq, heads, stream, lse2, poly < 0 ? 2 : poly);
   if (n_views > 65535) { set_last_error("attention (legacy kernel): n_views %d > 65535 (grid.z)", n_views); return 1; }
   if (poly == 4) return launch_attention<AttnCfg<32, 2, 4, 4>>(qkv, out, n_views, seq, heads, stream, lse2);
   if (poly == 2) return launch_attention<AttnCfg<32, 2, 4, 2>>(qkv, out, n_views, seq, heads, stream, lse2);
@@ -509,14 +511,20 @@ int attention_f16_variant(const void* qkv, void* out, int n_views, int seq, int 
 int attention_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream, float* lse2) {
   if (n_views <= 0) return 0;
   static const AttnSwitches sw;
-  if (sw.variant != 0 && n_views > 65535) {
+  if (sw.variant < 0) {
+    // Training keeps the pair kernel: its lse2 is the log-sum-exp of exactly the fp16 q.k products the backward recomputes
+    // (the fold kernel rounds c*q to fp16 once more, 1e-3 in log2 units).
+    if (lse2 == nullptr) return attention_fold_f16(qkv, out, n_views, seq, heads, stream, nullptr, sw.poly < 0 ? 2 : sw.poly);
+    return attention_pair_f16(qkv, out, n_views, seq, heads, stream, lse2, sw.poly < 0 ? 2 : sw.poly);
+  }
+  if (sw.variant != 0 && sw.variant != 7 && n_views > 65535) {
     set_last_error("attention (legacy kernel): n_views %d > 65535 (grid.z)", n_views);
     return 1;
   }
   switch (sw.variant) {
     case 0: return attention_pair_f16(qkv, out, n_views, seq, heads, stream, lse2, sw.poly < 0 ? 2 : sw.poly);
     case 6: return attention_split_f16(qkv, out, n_views, seq, heads, stream, lse2, sw.poly < 0 ? 2 : sw.poly);
-    case 7: return attention_fold_f16(qkv, out, n_views, seq, heads, stream, lse2, sw.poly < 0 ? 3 : sw.poly);
+    case 7: return attention_fold_f16(qkv, out, n_views, seq, heads, stream, lse2, sw.poly < 0 ? 2 : sw.poly);
     case 2: return launch_attention<AttnCfg<64, 3, 2>>(qkv, out, n_views, seq, heads, stream, lse2);
     case 3: return launch_attention<AttnCfg<64, 1, 4, 0, 4>>(qkv, out, n_views, seq, heads, stream, lse2);
     case 4: return launch_attention<AttnCfg<64, 1, 4, 0, 4, true>>(qkv, out, n_views, seq, heads, stream, lse2);
