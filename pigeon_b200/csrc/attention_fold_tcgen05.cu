@@ -47,8 +47,14 @@ constexpr int kSubBytes = kSub * kHeadDim * 2;         // 8 KB: one K or V block
 constexpr int kQBytes = 2 * kSubBytes;
 constexpr int kSlots = 8;                              // K/V ring of 16 KB slots: {K_0, K_1} or {V_j, K_(j+2)} of one tile stream
 constexpr int kSlotBytes = 2 * kSubBytes;
-constexpr int kThreads = 512;                          // 16 warps: setmaxnreg is a per-warpgroup (4 warps) operation
-constexpr int kWarpEpi = 8, kWarpTma = 12, kWarpMma = 13;   // MMA issuers: warp 13 (tile 0), warp 14 (tile 1)
+// Warp layout, H2 = softmax warps per query row quarter and tile (1: one thread per row and 64-column block; 2: two threads
+// per row, 32 columns each): 8 * H2 softmax warps, 4 epilogue warps, then TMA producer, MMA issuers of tile 0 / 1, one idle warp.
+// Warpgroups (4 warps) are the unit of setmaxnreg.
+template <int H2>
+struct Layout {
+  static constexpr int kThreads = 256 * H2 + 256;
+  static constexpr int kWarpEpi = 8 * H2, kWarpTma = kWarpEpi + 4, kWarpMma = kWarpTma + 1;
+};
 constexpr uint32_t kColS = 0, kColO = 256, kColQ = 416;
 constexpr int kOCols = 80;                             // 64 output columns, the row sum, 15 zero columns
 constexpr int kQCols = 40;                             // 80 fp16 per row: 64 of c*q, then -ref and 15 zeros
@@ -76,7 +82,8 @@ constexpr int kOffQ = kRingBytes;
 constexpr int kOffOnes = kOffQ + 2 * kQBytes;
 constexpr int kOffBars = kOffOnes + kOnesBytes;
 constexpr int kOffRef = kOffBars + 1024;
-constexpr int kSmemBytes = 1024 + kOffRef + 2 * kBlock * 4;
+constexpr int kOffXmax = kOffRef + 2 * kBlock * 4;       // [tile][half][row] partial first-block maxima (H2 = 2)
+constexpr int kSmemBytes = 1024 + kOffXmax + 2 * 2 * kBlock * 4;
 
 struct FoldArgs {
   const __half* qkv;
@@ -219,9 +226,11 @@ __device__ __forceinline__ void exact_row(const __half* __restrict__ qkv, int vi
   if (lse2_out != nullptr) *lse2_out = m_final + log2f(l_final);
 }
 
-template <int POLY>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int POLY, int H2>
+__global__ void __launch_bounds__(Layout<H2>::kThreads, 1)
 attention_fold_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FoldArgs args) {
+  constexpr int kThreads = Layout<H2>::kThreads;
+  constexpr int kWarpEpi = Layout<H2>::kWarpEpi, kWarpTma = Layout<H2>::kWarpTma, kWarpMma = Layout<H2>::kWarpMma;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_kv = smem;
@@ -254,12 +263,12 @@ attention_fold_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FoldAr
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->qs_full[i], 1);
-      mbar_init(&bars->qs_empty[i], 4);
-      mbar_init(&bars->q_ready[i], 4);
+      mbar_init(&bars->qs_empty[i], 4 * H2);
+      mbar_init(&bars->q_ready[i], 4 * H2);
       mbar_init(&bars->ref_ready[i], 4);
       for (int b = 0; b < 2; ++b) {
         mbar_init(&bars->s_full[i][b], 1);
-        mbar_init(&bars->p_ready[i][b], 4);
+        mbar_init(&bars->p_ready[i][b], 4 * H2);
       }
       mbar_init(&bars->o_full[i], 1);
       mbar_init(&bars->o_free[i], 4);
@@ -284,6 +293,170 @@ attention_fold_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FoldAr
   // otherwise the two streams are interleaved slot by slot (the owner commits twice), or there is a single stream.
   if (warp < kWarpEpi) {
     // ---------------------------------------------------------------- softmax warps: thread = query row = TMEM lane
+   if constexpr (H2 == 2) {
+    // ---- two threads per query row: warps 8 i + 0..3 take columns [0, 32) of every S block of tile i, warps 8 i + 4..7 columns
+    // [32, 64); each writes its P over the first 16 columns of its own half.  768 threads: 80 registers each, no setmaxnreg.
+    const int i = warp >> 3;            // tile slot
+    const int half = (warp >> 2) & 1;   // column half
+    const int wq = warp & 3;            // lane quarter
+    const int row = wq * 32 + lane;
+    const uint32_t lane_base = uint32_t(wq * 32) << 16;
+    const uint32_t s_tmem0 = tmem_base + lane_base + kColS + 128 * i + 32 * half;
+    const uint32_t q_tmem = tmem_base + lane_base + kColQ + kQStride * i;
+    const uint32_t q_smem = smem_u32(smem_q + i * kQBytes) + row * 128;
+    float* xmax = reinterpret_cast<float*>(smem + kOffXmax) + i * 2 * kBlock;
+    const int pair_bar = 1 + i * 4 + wq;   // named barrier of the two warps that share these 32 rows
+    const float c = args.scale_log2;
+    uint32_t n_q = 0, n_blk = 0, n_job = 0;
+    bool q_done = false;
+
+    auto copy_q = [&]() {   // this half's 32 of the 64 head dimensions
+      mbar_wait(&bars->qs_full[i], n_q & 1);
+      ++n_q;
+      uint32_t qr[16];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const uint4 v = lds128(q_smem + (((4 * half + ch) ^ (row & 7)) << 4));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          const float2 f = half2_bits_to_float2(w[y]);
+          qr[4 * ch + y] = pack_half2(f.x * c, f.y * c);
+        }
+      }
+      tmem_st16p(q_tmem + 16 * half, qr);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars->q_ready[i]);
+        mbar_arrive(&bars->qs_empty[i]);
+      }
+    };
+
+    for (int job = blockIdx.x; job < n_jobs; job += stride) {
+      const Job jb = decode_job(job, args);
+      if (i == 1 && !jb.a1) continue;
+      const int t = i ? jb.t1 : jb.t0;
+      const bool warp_active = t * kBlock + wq * 32 < S;
+      bool next_active = job + stride < n_jobs;
+      if (next_active && i == 1) next_active = decode_job(job + stride, args).a1;
+      if (!q_done) copy_q();
+      q_done = false;
+      float ref = 0.f;
+
+      for (int j = 0; j < nb; ++j) {
+        const int b = n_blk & 1;
+        const uint32_t s_tmem = s_tmem0 + kSub * b;
+        mbar_wait(&bars->s_full[i][b], (n_blk >> 1) & 1);
+        tc_fence_after();
+        if (j == nb - 1 && next_active) {
+          copy_q();
+          q_done = true;
+        }
+        const bool full = (j < nb - 1) || (last_valid == kSub);
+        const int valid = full ? kSub : last_valid;
+        int hv = valid - 32 * half;              // valid columns of this half
+        hv = hv < 0 ? 0 : (hv > 32 ? 32 : hv);
+        uint32_t r0[16], r1[16];
+        if (j == 0) {
+          // ---- reference of the job: each half takes the maximum of its own columns, the two warps of a row quarter swap
+          // them through shared memory (one 64-thread named barrier per job), both derive the same fp16 reference
+          float pm = -INFINITY;
+          if (warp_active) {
+            if (hv == 32) {
+              tmem_ld16p(s_tmem, r0);
+              tmem_ld16p(s_tmem + 16, r1);
+              tmem_ld_wait16(r0);
+              tmem_ld_wait16(r1);
+              float b0 = -INFINITY, b1 = -INFINITY;
+#pragma unroll
+              for (int x = 0; x < 16; x += 2) {
+                b0 = fmax3(b0, __uint_as_float(r0[x]), __uint_as_float(r0[x + 1]));
+                b1 = fmax3(b1, __uint_as_float(r1[x]), __uint_as_float(r1[x + 1]));
+              }
+              pm = fmaxf(b0, b1);
+            } else {
+              for (int ch = 0; ch * 16 < hv; ++ch) {
+                uint32_t r[16];
+                tmem_ld16p(s_tmem + 16 * ch, r);
+                tmem_ld_wait16(r);
+#pragma unroll
+                for (int x = 0; x < 16; ++x)
+                  if (ch * 16 + x < hv) pm = fmaxf(pm, __uint_as_float(r[x]));
+              }
+            }
+            xmax[half * kBlock + row] = pm;
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+          if (warp_active) ref = __half2float(__float2half_rn(fmaxf(pm, xmax[(half ^ 1) * kBlock + row]) + kRefMargin));
+          if (half == 0) {
+            if (warp_active) {
+              uint32_t qe[8];
+              qe[0] = pack_half2(-ref, 0.f);
+#pragma unroll
+              for (int x = 1; x < 8; ++x) qe[x] = 0u;
+              tmem_st8p(q_tmem + 32, qe);
+              tmem_st_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->ref_ready[i]);
+          }
+        }
+        if (warp_active) {
+          if (hv == 32) {
+            uint32_t pk[16];
+            if (j == 0) {
+              const float2 sh2 = make_float2(-ref, -ref);
+              exp_chunk<POLY, true>(r0, pk, sh2);
+              exp_chunk<POLY, true>(r1, pk + 8, sh2);
+            } else {
+              const float2 z2 = make_float2(0.f, 0.f);
+              tmem_ld16p(s_tmem, r0);
+              tmem_ld16p(s_tmem + 16, r1);
+              tmem_ld_wait16(r0);
+              exp_chunk<POLY, false>(r0, pk, z2);
+              tmem_ld_wait16(r1);
+              exp_chunk<POLY, false>(r1, pk + 8, z2);
+            }
+            tmem_st16p(s_tmem, pk);
+          } else {
+            const int nfull = hv >> 4, rem = hv & 15;
+            const float shift = (j == 0) ? -ref : 0.f;
+            const float2 sh2 = make_float2(shift, shift);
+            for (int ch = 0; ch < nfull; ++ch) {
+              uint32_t r[16], pk8[8];
+              tmem_ld16p(s_tmem + 16 * ch, r);
+              tmem_ld_wait16(r);
+              exp_chunk<0, true>(r, pk8, sh2);
+              tmem_st8p(s_tmem + 8 * ch, pk8);
+            }
+            if (rem) {
+              uint32_t r[16], pk8[8];
+              tmem_ld16p(s_tmem + 16 * nfull, r);
+              tmem_ld_wait16(r);
+              exp_chunk_masked(r, pk8, rem, shift);
+              tmem_st8p(s_tmem + 8 * nfull, pk8);
+            }
+          }
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->p_ready[i][b]);
+        ++n_blk;
+      }
+
+      if (half == 0) {
+        if (n_job > 0) mbar_wait(&bars->o_free[i], (n_job - 1) & 1);
+        refs[i * kBlock + row] = ref;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->l_ready[i]);
+      }
+      ++n_job;
+    }
+   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     const int i = warp >> 2;        // tile slot
     const int wq = warp & 3;        // lane quarter
@@ -467,9 +640,10 @@ attention_fold_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FoldAr
       if (lane == 0) mbar_arrive(&bars->l_ready[i]);
       ++n_job;
     }
+   }
   } else if (warp < kWarpTma) {
     // ---------------------------------------------------------------- epilogue warps: O / l -> fp16 -> global
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if constexpr (H2 == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     const int wq = warp & 3;
     const int row = wq * 32 + lane;
     const uint32_t lane_base = uint32_t(wq * 32) << 16;
@@ -522,7 +696,7 @@ attention_fold_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FoldAr
   // (every warpgroup's setmaxnreg sits inside its own role branch, and no role calls a non-inlined function: ptxas compiles a
   // shared callee for the smallest budget and then holds every caller to it)
   } else {
-   asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+   if constexpr (H2 == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
    if (warp > kWarpMma + 1) {
     // idle warp of the last warpgroup
    } else if (warp == kWarpTma) {
@@ -600,6 +774,9 @@ attention_fold_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FoldAr
     const uint32_t idesc_pv = make_idesc_f16(kBlock, kOCols, 0, 1);      // B (= V') is MN-major, N = 64 + 16
     const uint32_t s_base = tmem_base + kColS + 128 * I, o_base = tmem_base + kColO + kOCols * I;
     const uint32_t q_base = tmem_base + kColQ + kQStride * I;
+    // TMEM column (relative to the S buffer) of the packed-fp16 P columns of k-step k: contiguous with one softmax thread per
+    // row; with two, the second half's P sits over its own logits (columns 32..47)
+    auto p_col = [](int k) -> uint32_t { return (H2 == 2 && k >= 2) ? 32u + 8u * (k - 2) : 8u * k; };
     // S[buf] = Q'_I K'_j^T, j = block index inside its job; block 0 without the reference k-step   (inside an elected region)
     auto issue_s = [&](uint64_t kd, int j, uint32_t buf) {
       const uint32_t idesc = (j == nb - 1) ? idesc_s_last : idesc_s;
@@ -664,10 +841,10 @@ attention_fold_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FoldAr
           const int ksteps = (j == nb - 1) ? last_n / 16 : kSub / 16;
           umma_ts(o_base, a, vd, idesc_pv, j != 0);
           if (j == nb - 1) {
-            for (int k = 1; k < ksteps; ++k) umma_ts(o_base, a + 8 * k, vd + 128 * k, idesc_pv, 1);
+            for (int k = 1; k < ksteps; ++k) umma_ts(o_base, a + p_col(k), vd + 128 * k, idesc_pv, 1);
           } else {
 #pragma unroll
-            for (int k = 1; k < kSub / 16; ++k) umma_ts(o_base, a + 8 * k, vd + 128 * k, idesc_pv, 1);
+            for (int k = 1; k < kSub / 16; ++k) umma_ts(o_base, a + p_col(k), vd + 128 * k, idesc_pv, 1);
           }
           if (j == nb - 1) tc_commit(&bars->o_full[I]);
           if (j + 2 < nb) issue_s(k_desc0 + d1, j + 2, gb & 1);
@@ -701,15 +878,15 @@ attention_fold_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const FoldAr
   }
 }
 
-std::atomic<int> g_attr_set[64][5];   // per device and kernel variant: dynamic shared memory opt-in done
+std::atomic<int> g_attr_set[64][10];   // per device and kernel variant: dynamic shared memory opt-in done
 
-template <int POLY>
+template <int POLY, int H2>
 int launch_fold(int variant, const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream,
                 float* lse2) {
   const int hidden = heads * kHeadDim;
   CUtensorMap tm;
   if (make_tmap_f16_2d(&tm, qkv, (uint64_t)n_views * seq, 3 * hidden, 3 * hidden, kSub, kHeadDim)) return 1;
-  auto kern = attention_fold_kernel<POLY>;
+  auto kern = attention_fold_kernel<POLY, H2>;
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
@@ -736,7 +913,7 @@ int launch_fold(int variant, const void* qkv, void* out, int n_views, int seq, i
   a.n_jobs = n_views * a.jobs_per_view;
   const int grid = a.n_jobs < sms ? a.n_jobs : sms;
   ProfScope prof("attention", stream);
-  kern<<<grid, kThreads, kSmemBytes, stream>>>(tm, a);
+  kern<<<grid, Layout<H2>::kThreads, kSmemBytes, stream>>>(tm, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_last_error("attention launch: %s", cudaGetErrorString(e)); return 1; }
   return 0;
@@ -745,15 +922,20 @@ int launch_fold(int variant, const void* qkv, void* out, int n_views, int seq, i
 }  // namespace
 
 // poly: share of the exponentials evaluated on the FMA pipe, in eighths (0 .. 4 of every 8 pairs; other values = 2).
+// poly + 10: the variant with two softmax threads per query row (768 threads).
 int attention_fold_f16(const void* qkv, void* out, int n_views, int seq, int heads, cudaStream_t stream, float* lse2,
                        int poly) {
   if (n_views <= 0) return 0;
   switch (poly) {
-    case 0: return launch_fold<0x00>(0, qkv, out, n_views, seq, heads, stream, lse2);
-    case 1: return launch_fold<0x08>(1, qkv, out, n_views, seq, heads, stream, lse2);
-    case 3: return launch_fold<0x4A>(3, qkv, out, n_views, seq, heads, stream, lse2);
-    case 4: return launch_fold<0xAA>(4, qkv, out, n_views, seq, heads, stream, lse2);
-    default: return launch_fold<0x88>(2, qkv, out, n_views, seq, heads, stream, lse2);
+    case 0: return launch_fold<0x00, 1>(0, qkv, out, n_views, seq, heads, stream, lse2);
+    case 1: return launch_fold<0x08, 1>(1, qkv, out, n_views, seq, heads, stream, lse2);
+    case 3: return launch_fold<0x4A, 1>(3, qkv, out, n_views, seq, heads, stream, lse2);
+    case 4: return launch_fold<0xAA, 1>(4, qkv, out, n_views, seq, heads, stream, lse2);
+    case 10: return launch_fold<0x00, 2>(5, qkv, out, n_views, seq, heads, stream, lse2);
+    case 12: return launch_fold<0x88, 2>(6, qkv, out, n_views, seq, heads, stream, lse2);
+    case 13: return launch_fold<0x4A, 2>(7, qkv, out, n_views, seq, heads, stream, lse2);
+    case 14: return launch_fold<0xAA, 2>(8, qkv, out, n_views, seq, heads, stream, lse2);
+    default: return launch_fold<0x88, 1>(2, qkv, out, n_views, seq, heads, stream, lse2);
   }
 }
 

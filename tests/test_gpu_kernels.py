@@ -97,9 +97,37 @@ def test_attention(cuda, n_views, seq, heads):
     assert torch.isfinite(out.float()).all()
 
 
-def test_attention_growing_logits_exercise_rescale(cuda):
-    """Key norms grow along the sequence so that later KV blocks raise the row maximum by far more than 2^8:
-    the lazy-rescale path (O and l rescaled in TMEM) must give the same answer as an exact softmax."""
+ATTN_KERNELS = [(None, -1), (3, 2), (3, 12), (0, 2), (2, 2), (1, 0)]   # default, fold, fold with two threads per row, pair, split, first
+
+
+def _attention_reference(qkv, n_views, seq, heads):
+    xf = qkv.float().view(n_views, seq, 3, heads, 64)
+    q, k, v = (xf[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    logits = q @ k.transpose(-1, -2) * 0.125
+    out = (torch.softmax(logits, dim=-1) @ v).permute(0, 2, 1, 3).reshape(n_views * seq, heads * 64)
+    return out, logits
+
+
+@pytest.mark.parametrize("variant,poly", ATTN_KERNELS[1:])
+@pytest.mark.parametrize("n_views,seq,heads", [(2, 577, 3), (1, 17, 4), (3, 200, 1), (2, 64, 2), (1, 129, 5)])
+def test_attention_every_kernel_and_its_lse2(cuda, n_views, seq, heads, variant, poly):
+    """Every forward kernel generation against torch fp32, output and the log2-domain log-sum-exp side output (what the
+    training forward keeps for the backward)."""
+    from pigeon_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(seq * 5 + heads)
+    qkv = (torch.randn(n_views * seq, 3 * heads * 64, generator=g) * 1.5).half().to(cuda)
+    out, lse2 = ops.attention_f16(qkv, n_views, seq, heads, variant=variant, poly=poly, return_lse2=True)
+    ref, logits = _attention_reference(qkv, n_views, seq, heads)
+    assert torch.isfinite(out.float()).all() and _rel(out.float(), ref) < 2e-3
+    lse_ref = torch.logsumexp(logits, dim=-1) * 1.4426950408889634
+    assert (lse2.view(n_views, heads, seq) - lse_ref).abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("variant,poly", ATTN_KERNELS)
+def test_attention_growing_logits_exercise_rescale(cuda, variant, poly):
+    """Key norms grow along the sequence so that later KV blocks raise the row maximum far beyond what fp16 P can hold
+    relative to the first block: the pair / first-generation kernels must rescale O and l in TMEM, the fold kernel must take
+    its exact per-row repair path — all must agree with an exact softmax."""
     from pigeon_b200 import ops
     n_views, seq, heads = 2, 577, 2
     g = torch.Generator(device="cpu").manual_seed(77)
@@ -108,14 +136,16 @@ def test_attention_growing_logits_exercise_rescale(cuda):
     ramp = (0.25 + 6.0 * torch.arange(seq) / seq).view(1, seq, 1, 1)
     x[:, :, 1] *= ramp                                   # k
     qkv = x.reshape(n_views * seq, 3 * hidden).half().to(cuda)
-    out = ops.attention_f16(qkv, n_views, seq, heads)
-    xf = qkv.float().view(n_views, seq, 3, heads, 64)
-    q, k, v = (xf[:, :, i].permute(0, 2, 1, 3) for i in range(3))
-    logits = q @ k.transpose(-1, -2) * 0.125
-    assert (logits.max(-1).values - logits[..., :64].max(-1).values).max() * 1.4427 > 16, "test must trigger rescales"
-    ref = (torch.softmax(logits, dim=-1) @ v).permute(0, 2, 1, 3).reshape(n_views * seq, hidden)
+    out = ops.attention_f16(qkv, n_views, seq, heads, variant=variant, poly=poly)
+    ref, logits = _attention_reference(qkv, n_views, seq, heads)
+    spread = (logits.max(-1).values - logits[..., :64].max(-1).values) * 1.4427
+    assert (spread > 20).float().mean() > 0.05, "test must push a share of the rows out of the fp16 window"
+    assert (spread < 18).float().mean() > 0.2, "and leave others inside it"
     err = _rel(out.float(), ref)
     assert torch.isfinite(out.float()).all() and err < 2e-3, err
+    # row by row: the repaired rows and the fast-path rows are both right
+    row_err = (out.float() - ref).norm(dim=1) / ref.norm(dim=1).clamp_min(1e-6)
+    assert row_err.max().item() < 2e-2, row_err.max().item()
 
 
 # ------------------------------------------------------------------------------------------------ head
