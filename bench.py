@@ -300,7 +300,9 @@ def run_infer(args):
                        "peak_source": peaks["source"] + ", sustained bf16 cuBLAS figure (kernel timed inside a long step)",
                        "launches": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1), "share_of_step": gemm_ms / total_ms}
     a_ach = ATTN_FLOP_PER_VIEW * views / (attn_ms / 1e3) / 1e12 if attn_ms else 0.0
-    out["roofline_attention"] = {"kernel": "attention_pair_kernel (tcgen05 QK^T / PV, softmax in between)", "bound": "tensor",
+    attn_kernel = {None: "attention_fold_kernel", "fold": "attention_fold_kernel", "pair": "attention_pair_kernel",
+                   "split": "attention_split_kernel"}.get(os.environ.get("PG_ATTN_VARIANT"), "attention_kernel (first generation)")
+    out["roofline_attention"] = {"kernel": attn_kernel + " (tcgen05 QK^T / PV, softmax in between)", "bound": "tensor",
                                  "achieved": a_ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                                  "frac": a_ach / peaks["tflops_sustained"], "share_of_step": attn_ms / total_ms}
     out["kernel_ms_per_step"] = {"gemm_ms": round(gemm_ms, 3), "attention_ms": round(attn_ms, 3),

@@ -233,22 +233,6 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
-      if (EpiTraits<EPI>::kResid && args.vec_ok) {
-        // the residual rows this warp will read-modify-write one tile from now: pulled into L2 a whole epilogue ahead (one
-        // 512-byte bulk prefetch per lane = row), because the register prefetch inside epilogue_tile keeps only 4 KB per
-        // warp in flight — too little for HBM latency when the epilogue is the longer phase (out_proj: K = 1024)
-        const int nt = tile + num_pairs;
-        if (nt < num_tiles) {
-          const int nm = nt / n_blocks, nn = nt % n_blocks;
-          const long row = (long)nm * 2 * BLOCK_M_CTA + rank * BLOCK_M_CTA + q * 32 + lane;
-          const int col = nn * BLOCK_N + ((warp - kEpiWarp0) >= 4 ? BLOCK_N / 2 : 0);
-          if (row < args.M && col + BLOCK_N / 2 <= args.N)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const float*>(args.resid) +
-                                                                          row * args.ldo + col),
-                         "r"(BLOCK_N / 2 * 4)
-                         : "memory");
-        }
-      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N;
