@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 2
+#define PG_ABI_VERSION 3
 
 /* ---------------------------------------------------------------------------------------------------
  * Library
@@ -226,7 +226,13 @@ typedef struct pg_refiner_bank {
   const int64_t* member_idx;   /* [sum count] rows of data_emb/data_lnglat */
   const float* data_emb;       /* [Ntrain, D] */
   const float* data_lnglat;    /* [Ntrain, 2] */
+  const float* proto_sqnorm;   /* [P] squared L2 norm of every prototype row (pg_refiner_bank_sqnorm), or NULL: the scans
+                                  that need it (schedule 3) are then replaced by the ones that do not */
 } pg_refiner_bank;
+
+/* |p|^2 of every row of proto_emb f32 [P, D] -> sqnorm_out f32 [P]; once per bank (the squared Euclidean distance of
+ * reference models/proto_refiner.py:176-178 in the |p|^2 + |q|^2 - 2 p.q form torch.cdist itself uses). */
+int pg_refiner_bank_sqnorm(const float* proto_emb, int64_t P, int32_t D, float* sqnorm_out, void* stream);
 
 size_t pg_refiner_workspace_bytes(int64_t B, int32_t topk, int32_t D, int32_t num_cells);
 /* The two stages of pg_refiner_forward as separate calls, for a CELL-SHARDED bank across GPUs (rank r holds the geocells with
@@ -242,7 +248,8 @@ int pg_refiner_finalize(const float* best_logit, const float* best_lnglat, const
                         float temperature, double max_refinement_km, float* out_lnglat, int64_t* out_cell, int32_t* choice,
                         void* stream);
 /* Measurement aid: scan schedule of pg_refiner_forward for this process: 0 = automatic (cell-major when geocells are shared
- * by >= 2 (query, candidate) pairs on average), 1 = query-major, 2 = cell-major.  Same results either way. */
+ * by >= 2 (query, candidate) pairs on average: the tile scan when the bank carries proto_sqnorm), 1 = query-major,
+ * 2 = cell-major, 3 = tile scan.  Same selections either way. */
 int pg_refiner_set_schedule(int32_t mode);
 /* emb f32 [B, V, D]; init_lnglat f64 [B, 2]; cand_idx i64 [B, cand_stride]; cand_prob f32 [B, cand_stride];
  * only the first `topk` candidates of each row are used (topk <= cand_stride).

@@ -61,7 +61,7 @@ class VitWeights(C.Structure):
 class RefinerBank(C.Structure):
     _fields_ = [("num_cells", c_int32), ("dim", c_int32), ("cell_off", c_void_p), ("proto_emb", c_void_p),
                 ("proto_lnglat", c_void_p), ("proto_count", c_void_p), ("member_off", c_void_p),
-                ("member_idx", c_void_p), ("data_emb", c_void_p), ("data_lnglat", c_void_p)]
+                ("member_idx", c_void_p), ("data_emb", c_void_p), ("data_lnglat", c_void_p), ("proto_sqnorm", c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/pigeon_b200.h
@@ -110,6 +110,7 @@ SIGNATURES = {
                                      c_int32, c_int32, c_float, c_double, c_void_p, c_size_t, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pg_refiner_set_schedule": (c_int32, [c_int32]),
+    "pg_refiner_bank_sqnorm": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "pg_refiner_scan": (c_int32, [C.POINTER(RefinerBank), c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_void_p,
                                   c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pg_refiner_finalize": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32,
@@ -130,7 +131,7 @@ SIGNATURES = {
                                            c_void_p]),
 }
 
-ABI_VERSION = 2   # == PG_ABI_VERSION in include/pigeon_b200.h; bumped whenever a signature or struct changes
+ABI_VERSION = 3   # == PG_ABI_VERSION in include/pigeon_b200.h; bumped whenever a signature or struct changes
 
 EPI_F16_BIAS, EPI_F16_BIAS_QGELU, EPI_F32_BIAS_RESID, EPI_F32_BIAS = 0, 1, 2, 3
 

@@ -294,8 +294,29 @@ size_t pg_refiner_workspace_bytes(int64_t B, int32_t topk, int32_t D, int32_t nu
   return c.off;
 }
 
+static RefinerBank to_bank(const pg_refiner_bank* bank) {
+  RefinerBank rb;
+  rb.num_cells = bank->num_cells; rb.dim = bank->dim;
+  rb.cell_off = reinterpret_cast<const long long*>(bank->cell_off);
+  rb.proto_emb = bank->proto_emb; rb.proto_lnglat = bank->proto_lnglat; rb.proto_count = bank->proto_count;
+  rb.member_off = reinterpret_cast<const long long*>(bank->member_off);
+  rb.member_idx = reinterpret_cast<const long long*>(bank->member_idx);
+  rb.data_emb = bank->data_emb; rb.data_lnglat = bank->data_lnglat;
+  rb.proto_sqnorm = bank->proto_sqnorm;
+  return rb;
+}
+
+// Which scan the schedule and the call shape select: 1 query-major, 2 cell-major (v3), 3 tile scan (v4).
+static int pick_scan(int sched, int64_t B, int32_t topk, const pg_refiner_bank* bank) {
+  if (sched == 1 || sched == 2) return sched;
+  if (sched == 3) return bank->proto_sqnorm ? 3 : 2;
+  if ((long)B * topk < 2L * bank->num_cells) return 1;   // small batches: the sort would dominate
+  return bank->proto_sqnorm ? 3 : 2;
+}
+
 // Scan schedule of pg_refiner_forward: 0 = automatic (cell-major when geocells are shared by >= 2 pairs on average),
-// 1 = query-major, 2 = cell-major.  Process-wide A/B switch (pg_refiner_set_schedule); the environment variable
+// 1 = query-major, 2 = cell-major (v3), 3 = tile scan (v4; what automatic picks for shared cells when the bank carries
+// proto_sqnorm).  Process-wide A/B switch (pg_refiner_set_schedule); the environment variable
 // PG_REFINER_QUERY_MAJOR=1 only sets the initial value, once.
 static std::atomic<int> g_refiner_schedule{-1};
 static int refiner_schedule() {
@@ -309,7 +330,7 @@ static int refiner_schedule() {
 }
 
 int pg_refiner_set_schedule(int32_t mode) {
-  if (mode < 0 || mode > 2) { set_last_error("pg_refiner_set_schedule: mode %d not in {0, 1, 2}", mode); return 1; }
+  if (mode < 0 || mode > 3) { set_last_error("pg_refiner_set_schedule: mode %d not in {0, 1, 2, 3}", mode); return 1; }
   g_refiner_schedule.store(mode, std::memory_order_relaxed);
   return 0;
 }
@@ -339,23 +360,18 @@ int pg_refiner_forward(const pg_refiner_bank* bank, const float* emb, int64_t B,
   if (best_logit) bl = best_logit;
   if (best_lnglat) bll = best_lnglat;
   if (best_proto) bp = best_proto;
-  RefinerBank rb;
-  rb.num_cells = bank->num_cells; rb.dim = bank->dim;
-  rb.cell_off = reinterpret_cast<const long long*>(bank->cell_off);
-  rb.proto_emb = bank->proto_emb; rb.proto_lnglat = bank->proto_lnglat; rb.proto_count = bank->proto_count;
-  rb.member_off = reinterpret_cast<const long long*>(bank->member_off);
-  rb.member_idx = reinterpret_cast<const long long*>(bank->member_idx);
-  rb.data_emb = bank->data_emb; rb.data_lnglat = bank->data_lnglat;
+  const RefinerBank rb = to_bank(bank);
   if (refiner_pool(emb, q, B, V, bank->dim, stream)) return 1;
   // cell-major (each touched prototype segment read once) as soon as cells are shared by several pairs on average;
   // the query-major kernel (one warp per pair) for small batches where the sort would dominate
-  const int sched = refiner_schedule();
-  const bool cell_major = sched == 2 || (sched == 0 && (long)B * topk >= 2L * bank->num_cells);
-  if (cell_major) {
-    if (refiner_scan_cell_major(rb, q, reinterpret_cast<const long long*>(cand_idx), cand_stride, B, topk, sort_ws, bl,
-                                bll, bp, sms, stream)) return 1;
+  const int scan = pick_scan(refiner_schedule(), B, topk, bank);
+  const long long* cand = reinterpret_cast<const long long*>(cand_idx);
+  if (scan == 3) {
+    if (refiner_scan_tiles(rb, q, cand, cand_stride, B, topk, sort_ws, bl, bll, bp, sms, stream)) return 1;
+  } else if (scan == 2) {
+    if (refiner_scan_cell_major(rb, q, cand, cand_stride, B, topk, sort_ws, bl, bll, bp, sms, stream)) return 1;
   } else {
-    if (refiner_scan(rb, q, reinterpret_cast<const long long*>(cand_idx), cand_stride, B, topk, bl, bll, bp, sms, stream)) return 1;
+    if (refiner_scan(rb, q, cand, cand_stride, B, topk, bl, bll, bp, sms, stream)) return 1;
   }
   return refiner_finalize(bl, bll, reinterpret_cast<const long long*>(cand_idx), cand_prob, cand_stride, init_lnglat, B,
                           topk, temperature, max_refinement_km, out_lnglat, reinterpret_cast<long long*>(out_cell),
@@ -384,21 +400,23 @@ int pg_refiner_scan(const pg_refiner_bank* bank, const float* emb, int64_t B, in
   c.take((size_t)B * topk * 2 * 4);
   c.take((size_t)B * topk * 4);
   void* sort_ws = c.take(refiner_sort_workspace_bytes(bank->num_cells, (long)B * topk));
-  RefinerBank rb;
-  rb.num_cells = bank->num_cells; rb.dim = bank->dim;
-  rb.cell_off = reinterpret_cast<const long long*>(bank->cell_off);
-  rb.proto_emb = bank->proto_emb; rb.proto_lnglat = bank->proto_lnglat; rb.proto_count = bank->proto_count;
-  rb.member_off = reinterpret_cast<const long long*>(bank->member_off);
-  rb.member_idx = reinterpret_cast<const long long*>(bank->member_idx);
-  rb.data_emb = bank->data_emb; rb.data_lnglat = bank->data_lnglat;
+  const RefinerBank rb = to_bank(bank);
   if (refiner_pool(emb, q, B, V, bank->dim, stream)) return 1;
-  const int sched = refiner_schedule();
-  const bool cell_major = sched == 2 || (sched == 0 && (long)B * topk >= 2L * bank->num_cells);
-  if (cell_major)
-    return refiner_scan_cell_major(rb, q, reinterpret_cast<const long long*>(cand_idx), cand_stride, B, topk, sort_ws,
-                                   best_logit, best_lnglat, best_proto, sms, stream);
-  return refiner_scan(rb, q, reinterpret_cast<const long long*>(cand_idx), cand_stride, B, topk, best_logit, best_lnglat,
-                      best_proto, sms, stream);
+  const int scan = pick_scan(refiner_schedule(), B, topk, bank);
+  const long long* cand = reinterpret_cast<const long long*>(cand_idx);
+  if (scan == 3)
+    return refiner_scan_tiles(rb, q, cand, cand_stride, B, topk, sort_ws, best_logit, best_lnglat, best_proto, sms, stream);
+  if (scan == 2)
+    return refiner_scan_cell_major(rb, q, cand, cand_stride, B, topk, sort_ws, best_logit, best_lnglat, best_proto, sms,
+                                   stream);
+  return refiner_scan(rb, q, cand, cand_stride, B, topk, best_logit, best_lnglat, best_proto, sms, stream);
+}
+
+int pg_refiner_bank_sqnorm(const float* proto_emb, int64_t P, int32_t D, float* sqnorm_out, void* stream) {
+  if (!proto_emb || !sqnorm_out || P < 0 || D <= 0) { set_last_error("pg_refiner_bank_sqnorm: bad argument"); return 1; }
+  const int sms = sm_count();
+  if (sms < 0) return 1;
+  return refiner_bank_sqnorm(proto_emb, P, D, sqnorm_out, sms, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int pg_refiner_finalize(const float* best_logit, const float* best_lnglat, const double* init_lnglat,

@@ -126,7 +126,8 @@ constexpr int kPT = 4;  // prototypes per warp register tile
 
 __global__ void pair_hist_kernel(const RefinerBank bank, const long long* __restrict__ cand, int cand_stride, long B,
                                  int topk, int* __restrict__ cell_cnt, float* __restrict__ best_logit,
-                                 float* __restrict__ best_lnglat, int* __restrict__ best_proto) {
+                                 float* __restrict__ best_lnglat, int* __restrict__ best_proto,
+                                 unsigned long long* __restrict__ best_packed = nullptr) {
   const long pairs = B * topk;
   for (long pair = (long)blockIdx.x * blockDim.x + threadIdx.x; pair < pairs; pair += (long)gridDim.x * blockDim.x) {
     const long b = pair / topk;
@@ -136,6 +137,7 @@ __global__ void pair_hist_kernel(const RefinerBank bank, const long long* __rest
     if (cell >= 0 && cell < bank.num_cells) live = bank.cell_off[cell + 1] > bank.cell_off[cell];
     if (live) {
       atomicAdd(&cell_cnt[cell], 1);
+      if (best_packed) best_packed[pair] = ~0ull;   // identity of the tile scan's atomicMin
     } else {  // reference: protos[cell] is None -> logit -100000, prediction [0., 0.]   (proto_refiner.py:168-174)
       best_logit[pair] = -100000.f;
       best_lnglat[2 * pair] = 0.f;
@@ -382,6 +384,425 @@ cell_major_scan_kernel(const RefinerBank bank, const float* __restrict__ q, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tile scan (v4).  The cell-major kernel above is latency-bound on its prototype stream: a warp requests 12 KB, waits for
+// it, computes, and only then requests again (ncu: issue slots 36 %, DRAM 25 %).  Here the stream is decoupled from the
+// arithmetic:
+//   * persistent CTAs (one per SM, 8 consumer warps + 1 producer warp); the work is the list of 16-prototype TILES of all
+//     touched (geocell, query pass) pairs in cell order, cut into gridDim.x equal contiguous ranges (no tail, no wave
+//     quantisation); a geocell that straddles two ranges is merged through a 64-bit atomicMin on (d2 bits, prototype);
+//   * the producer warp copies each tile (16 rows x D floats) into a shared-memory ring with one cp.async.bulk per row,
+//     completion on an mbarrier, and pulls the tiles kPrefetchTiles further ahead into L2 (cp.async.bulk.prefetch.L2),
+//     so HBM latency is hidden by L2 depth rather than by shared memory;
+//   * up to QS queries of the geocell sit in shared memory for the whole pass, interleaved in pairs (one FFMA2 advances
+//     two queries); the 8 consumer warps split D eight ways, each computing a 16 x QS block of partial dot products with
+//     a 2-prototype x NCH-pair register tile per thread (lanes = 8 prototype groups x 4 query groups: every LDS.128 is a
+//     single conflict-free wavefront thanks to the 16-byte row padding), then add the eight partials in a fixed order
+//     through shared memory -> d2 = |p|^2 + |q|^2 - 2 p.q with |p|^2 precomputed per bank (proto_sqnorm).
+// Every (prototype, query) distance is computed by the same instruction sequence wherever the tile lands, so a sharded bank
+// reproduces the single-GPU selections bit for bit.  FP32-FMA floor at cfg5: 0.5 ms; HBM floor 0.47 ms.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTP = 16;                 // prototypes per tile = one ring stage
+constexpr int kTileWarps = 8;           // consumer warps (D split 8 ways)
+constexpr int kTileConsumers = kTileWarps * 32;
+constexpr int kTileThreads = kTileConsumers + 32;
+constexpr int kPrefetchTiles = 3;       // L2 prefetch distance in tiles
+
+template <int NV4, int QS>
+struct TileCfg {
+  static constexpr int D = NV4 * 128;
+  static constexpr int KS = D / kTileWarps;            // columns per consumer warp
+  static constexpr int QROW = 2 * D + 4;               // floats per staged query-pair row (16 B pad: conflict-free)
+  static constexpr int PROW = D + 4;                   // floats per staged prototype row
+  static constexpr int SROW = QS + 8;                  // floats per row of partial sums
+  static constexpr int NST = (D <= 512) ? 4 : 2;       // ring stages
+  static constexpr int RG = kTileConsumers / QS;       // prototype rows covered by one sweep of the reduce threads
+  static constexpr int RPT = kTP / RG;                 // rows per reduce thread
+  static constexpr size_t q_bytes = (size_t)(QS / 2) * QROW * 4;
+  static constexpr size_t p_bytes = (size_t)NST * kTP * PROW * 4;
+  static constexpr size_t s_bytes = (size_t)kTileWarps * kTP * SROW * 4;
+  static constexpr size_t rb_bytes = (size_t)kTileConsumers * 8;
+  static constexpr size_t qn_bytes = (size_t)QS * 4;
+  static constexpr size_t bar_bytes = 2 * NST * 8;
+  static constexpr size_t smem = q_bytes + p_bytes + s_bytes + rb_bytes + qn_bytes + bar_bytes;
+  static_assert(KS % 8 == 0 && kTP % RG == 0, "tile geometry");
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+};
+
+// Walks the tiles [x, x_hi) of the global tile list: one item = consecutive tiles of one (geocell, query pass).
+struct TileWalk {
+  long long x, x_hi;
+  int c;                  // current geocell
+  long lo;                // its first prototype
+  int Pc, tpc;            // prototypes / tiles of the geocell
+  int pair0, n_pairs;     // its sorted pairs
+  int pass, t0, t1;       // query pass, tile range of this item
+  __device__ __forceinline__ void init(long long x0, long long x1, const int* __restrict__ tile_prefix, int C) {
+    x = x0; x_hi = x1;
+    int a = 0, b = C;     // largest c with tile_prefix[c] <= x0
+    while (b - a > 1) { const int m = (a + b) >> 1; if (tile_prefix[m] <= x0) a = m; else b = m; }
+    c = a;
+  }
+  __device__ __forceinline__ bool next(const RefinerBank& bank, const int* __restrict__ cell_start,
+                                       const int* __restrict__ tile_prefix) {
+    if (x >= x_hi) return false;
+    while (tile_prefix[c + 1] <= x) ++c;
+    lo = bank.cell_off[c];
+    Pc = (int)(bank.cell_off[c + 1] - lo);
+    tpc = (Pc + kTP - 1) / kTP;
+    pair0 = cell_start[c];
+    n_pairs = cell_start[c + 1] - pair0;
+    const int local = (int)(x - tile_prefix[c]);
+    pass = local / tpc;
+    t0 = local % tpc;
+    const long long rem = x_hi - x;
+    t1 = (rem < (long long)(tpc - t0)) ? t0 + (int)rem : tpc;
+    x += t1 - t0;
+    return true;
+  }
+};
+
+// The same walk one tile at a time (producer: one iterator for the copies, one running ahead for the L2 prefetch).
+struct TileIter {
+  TileWalk w;
+  int t;
+  bool valid;
+  __device__ __forceinline__ void start(const RefinerBank& bank, const int* cell_start, const int* tile_prefix) {
+    valid = w.next(bank, cell_start, tile_prefix);
+    t = w.t0;
+  }
+  __device__ __forceinline__ void advance(const RefinerBank& bank, const int* cell_start, const int* tile_prefix) {
+    if (++t >= w.t1) { valid = w.next(bank, cell_start, tile_prefix); t = w.t0; }
+  }
+};
+
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kTileConsumers) : "memory"); }
+
+// One item of the walk on the consumer side: NCH chunks of 8 staged queries against tiles [t0, t1).
+template <int NV4, int QS, int NCH>
+__device__ __forceinline__ void tile_item(const RefinerBank& bank, const TileWalk& w, const float* __restrict__ qs,
+                                          const float* __restrict__ ps, float* __restrict__ scratch,
+                                          const float* __restrict__ qn, uint64_t* full, uint64_t* empty, int& stage,
+                                          uint32_t& phase, float (&bd)[TileCfg<NV4, QS>::RPT],
+                                          int (&bp)[TileCfg<NV4, QS>::RPT]) {
+  using Cfg = TileCfg<NV4, QS>;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, h = lane & 3;
+  const int j = tid % QS, rr = tid / QS;
+  for (int t = w.t0; t < w.t1; ++t) {
+    // |p|^2 of the rows this thread reduces: requested before the wait, used after the arithmetic
+    float pn[Cfg::RPT];
+    bool ok[Cfg::RPT];
+#pragma unroll
+    for (int i = 0; i < Cfg::RPT; ++i) {
+      const int idx = t * kTP + rr + i * Cfg::RG;
+      ok[i] = idx < w.Pc;
+      pn[i] = ok[i] ? __ldg(bank.proto_sqnorm + w.lo + idx) : 0.f;
+    }
+    mbar_wait(&full[stage], phase);
+    const float* pa_ptr = ps + (size_t)(stage * kTP + g) * Cfg::PROW + warp * Cfg::KS;
+    const float* pb_ptr = pa_ptr + 8 * Cfg::PROW;
+    const float* q_ptr = qs + (size_t)h * Cfg::QROW + 2 * warp * Cfg::KS;
+    float2 acc[2][NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { acc[0][c] = make_float2(0.f, 0.f); acc[1][c] = make_float2(0.f, 0.f); }
+    // two register sets in ping-pong: the shared-memory loads of step k + 4 are in flight while step k is on the FMA pipe
+    // (only two warps per scheduler: nothing else would hide the LDS latency)
+    struct Step { float4 pa, pb, q0[NCH], q1[NCH]; };
+    auto load = [&](Step& s, int k) {
+      s.pa = *reinterpret_cast<const float4*>(pa_ptr + k);
+      s.pb = *reinterpret_cast<const float4*>(pb_ptr + k);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        s.q0[c] = *reinterpret_cast<const float4*>(q_ptr + (size_t)c * 4 * Cfg::QROW + 2 * k);
+        s.q1[c] = *reinterpret_cast<const float4*>(q_ptr + (size_t)c * 4 * Cfg::QROW + 2 * k + 4);
+      }
+    };
+    auto fma = [&](const Step& s) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        acc[0][c] = ffma2(make_float2(s.pa.x, s.pa.x), make_float2(s.q0[c].x, s.q0[c].y), acc[0][c]);
+        acc[1][c] = ffma2(make_float2(s.pb.x, s.pb.x), make_float2(s.q0[c].x, s.q0[c].y), acc[1][c]);
+        acc[0][c] = ffma2(make_float2(s.pa.y, s.pa.y), make_float2(s.q0[c].z, s.q0[c].w), acc[0][c]);
+        acc[1][c] = ffma2(make_float2(s.pb.y, s.pb.y), make_float2(s.q0[c].z, s.q0[c].w), acc[1][c]);
+        acc[0][c] = ffma2(make_float2(s.pa.z, s.pa.z), make_float2(s.q1[c].x, s.q1[c].y), acc[0][c]);
+        acc[1][c] = ffma2(make_float2(s.pb.z, s.pb.z), make_float2(s.q1[c].x, s.q1[c].y), acc[1][c]);
+        acc[0][c] = ffma2(make_float2(s.pa.w, s.pa.w), make_float2(s.q1[c].z, s.q1[c].w), acc[0][c]);
+        acc[1][c] = ffma2(make_float2(s.pb.w, s.pb.w), make_float2(s.q1[c].z, s.q1[c].w), acc[1][c]);
+      }
+    };
+    Step sa, sb;
+    load(sa, 0);
+#pragma unroll 1
+    for (int k = 0; k < Cfg::KS; k += 8) {
+      load(sb, k + 4);
+      fma(sa);
+      if (k + 8 < Cfg::KS) load(sa, k + 8);
+      fma(sb);
+    }
+    // this warp's slice of the 16 x (8 NCH) dot products; the ring slot is free once every warp has read it
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      *reinterpret_cast<float2*>(scratch + (size_t)(warp * kTP + g) * Cfg::SROW + c * 8 + 2 * h) = acc[0][c];
+      *reinterpret_cast<float2*>(scratch + (size_t)(warp * kTP + g + 8) * Cfg::SROW + c * 8 + 2 * h) = acc[1][c];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+    if (++stage == Cfg::NST) { stage = 0; phase ^= 1; }
+    consumer_bar();
+    if (j < 8 * NCH) {
+      const float qnj = qn[j];
+#pragma unroll
+      for (int i = 0; i < Cfg::RPT; ++i) {
+        const int row = rr + i * Cfg::RG;
+        float dot = scratch[(size_t)row * Cfg::SROW + j];
+#pragma unroll
+        for (int ww = 1; ww < kTileWarps; ++ww) dot += scratch[(size_t)(ww * kTP + row) * Cfg::SROW + j];
+        const float d2 = ok[i] ? fmaxf(pn[i] + qnj - 2.f * dot, 0.f) + 0.f : INFINITY;
+        if (d2 < bd[i]) { bd[i] = d2; bp[i] = t * kTP + row; }   // strict: first minimum wins
+      }
+    }
+    consumer_bar();
+  }
+}
+
+template <int NV4, int QS>
+__global__ void __launch_bounds__(kTileThreads, 1)
+tile_scan_kernel(const RefinerBank bank, const float* __restrict__ q, const int* __restrict__ cell_start,
+                 const int* __restrict__ order, const int* __restrict__ tile_prefix, int topk,
+                 unsigned long long* __restrict__ best_packed) {
+  using Cfg = TileCfg<NV4, QS>;
+  constexpr int D = Cfg::D;
+  extern __shared__ __align__(128) unsigned char tile_smem[];
+  float* qs = reinterpret_cast<float*>(tile_smem);
+  float* ps = reinterpret_cast<float*>(tile_smem + Cfg::q_bytes);
+  float* scratch = reinterpret_cast<float*>(tile_smem + Cfg::q_bytes + Cfg::p_bytes);
+  float* rb_d = reinterpret_cast<float*>(tile_smem + Cfg::q_bytes + Cfg::p_bytes + Cfg::s_bytes);
+  int* rb_p = reinterpret_cast<int*>(rb_d + kTileConsumers);
+  float* qn = reinterpret_cast<float*>(rb_p + kTileConsumers);
+  uint64_t* full = reinterpret_cast<uint64_t*>(qn + QS);
+  uint64_t* empty = full + Cfg::NST;
+
+  const int C = bank.num_cells;
+  const long long T = tile_prefix[C];
+  const long long x_lo = T * blockIdx.x / gridDim.x, x_hi = T * (blockIdx.x + 1) / gridDim.x;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kTileWarps); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (x_lo >= x_hi) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (warp == kTileWarps) {
+    // ---------------------------------------------------------------- producer: ring copies + L2 prefetch ahead
+    TileIter ld, pf;
+    ld.w.init(x_lo, x_hi, tile_prefix, C);
+    pf.w = ld.w;
+    ld.start(bank, cell_start, tile_prefix);
+    pf.start(bank, cell_start, tile_prefix);
+    auto prefetch = [&](const TileIter& it) {   // the rows of a tile are contiguous in the bank: one request
+      const int row0 = it.t * kTP;
+      if (lane == 0)
+        bulk_prefetch_l2(bank.proto_emb + (size_t)(it.w.lo + row0) * D, (uint32_t)min(kTP, it.w.Pc - row0) * D * 4);
+    };
+    for (int i = 0; i < kPrefetchTiles && pf.valid; ++i) { prefetch(pf); pf.advance(bank, cell_start, tile_prefix); }
+    int stage = 0;
+    uint32_t phase = 0;
+    while (ld.valid) {
+      if (pf.valid) { prefetch(pf); pf.advance(bank, cell_start, tile_prefix); }
+      const int row0 = ld.t * kTP;
+      const int nrows = min(kTP, ld.w.Pc - row0);
+      mbar_wait(&empty[stage], phase ^ 1);
+      if (lane == 0) mbar_arrive_expect_tx(&full[stage], (uint32_t)nrows * D * 4);
+      __syncwarp();
+      if (lane < nrows)
+        bulk_load_1d(ps + (size_t)(stage * kTP + lane) * Cfg::PROW, bank.proto_emb + (size_t)(ld.w.lo + row0 + lane) * D,
+                     D * 4, &full[stage]);
+      if (++stage == Cfg::NST) { stage = 0; phase ^= 1; }
+      ld.advance(bank, cell_start, tile_prefix);
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------ consumers
+  TileWalk w;
+  w.init(x_lo, x_hi, tile_prefix, C);
+  int stage = 0;
+  uint32_t phase = 0;
+  while (w.next(bank, cell_start, tile_prefix)) {
+    const int nq = min(QS, w.n_pairs - w.pass * QS);
+    const int nch = (nq + 7) >> 3;
+    const int* ord = order + w.pair0 + w.pass * QS;
+    consumer_bar();   // the previous item's readers are done with qs / qn / rb
+    // stage the queries two by two: pair row u holds (qA[k], qB[k]) interleaved, A = 2u, B = 2u + 1; missing ones are zero
+    for (int idx = tid; idx < 4 * nch * (D / 4); idx += kTileConsumers) {
+      const int u = idx / (D / 4), i4 = idx % (D / 4);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (2 * u < nq) a = reinterpret_cast<const float4*>(q + (size_t)(ord[2 * u] / topk) * D)[i4];
+      if (2 * u + 1 < nq) b = reinterpret_cast<const float4*>(q + (size_t)(ord[2 * u + 1] / topk) * D)[i4];
+      float* dst = qs + (size_t)u * Cfg::QROW + 8 * i4;
+      *reinterpret_cast<float4*>(dst) = make_float4(a.x, b.x, a.y, b.y);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(a.z, b.z, a.w, b.w);
+    }
+    for (int qi = warp; qi < 8 * nch; qi += kTileWarps) {   // |q|^2, warp per query
+      float acc_q = 0.f;
+      if (qi < nq) {
+        const float4* q4 = reinterpret_cast<const float4*>(q + (size_t)(ord[qi] / topk) * D);
+#pragma unroll
+        for (int i = 0; i < NV4; ++i) {
+          const float4 t = q4[lane + 32 * i];
+          acc_q = fmaf(t.x, t.x, acc_q); acc_q = fmaf(t.y, t.y, acc_q);
+          acc_q = fmaf(t.z, t.z, acc_q); acc_q = fmaf(t.w, t.w, acc_q);
+        }
+      }
+      acc_q = warp_sum(acc_q);
+      if (lane == 0) qn[qi] = acc_q;
+    }
+    consumer_bar();
+    float bd[Cfg::RPT];
+    int bp[Cfg::RPT];
+#pragma unroll
+    for (int i = 0; i < Cfg::RPT; ++i) { bd[i] = INFINITY; bp[i] = 0x7fffffff; }
+    switch (nch) {
+      case 1: tile_item<NV4, QS, 1>(bank, w, qs, ps, scratch, qn, full, empty, stage, phase, bd, bp); break;
+      case 2: tile_item<NV4, QS, 2>(bank, w, qs, ps, scratch, qn, full, empty, stage, phase, bd, bp); break;
+      case 3: if constexpr (QS >= 24) tile_item<NV4, QS, 3>(bank, w, qs, ps, scratch, qn, full, empty, stage, phase, bd, bp); break;
+      default: if constexpr (QS >= 32) tile_item<NV4, QS, 4>(bank, w, qs, ps, scratch, qn, full, empty, stage, phase, bd, bp); break;
+    }
+    // rows of one thread ascend, so do the groups rr: lexicographic (d2, prototype) minimum over the RG groups
+    float d = bd[0];
+    int pi = bp[0];
+#pragma unroll
+    for (int i = 1; i < Cfg::RPT; ++i) if (bd[i] < d || (bd[i] == d && bp[i] < pi)) { d = bd[i]; pi = bp[i]; }
+    rb_d[tid] = d;
+    rb_p[tid] = pi;
+    consumer_bar();
+    if (tid < nq) {
+      for (int r = 0; r < Cfg::RG; ++r) {
+        const float od = rb_d[r * QS + tid];
+        const int op = rb_p[r * QS + tid];
+        if (od < d || (od == d && op < pi)) { d = od; pi = op; }
+      }
+      const unsigned long long packed = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)pi;
+      atomicMin(&best_packed[ord[tid]], packed);
+    }
+  }
+}
+
+// After the tile scan: decode the packed winner of every live pair, farthest-member pick (:233-255), outputs.
+template <int NV4>
+__global__ void __launch_bounds__(256)
+tile_finish_kernel(const RefinerBank bank, const float* __restrict__ q, const long long* __restrict__ cand,
+                   int cand_stride, const int* __restrict__ order, const int* __restrict__ n_live, int topk,
+                   const unsigned long long* __restrict__ best_packed, float* __restrict__ best_logit,
+                   float* __restrict__ best_lnglat, int* __restrict__ best_proto) {
+  constexpr int D = NV4 * 128;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int live = *n_live;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < live; i += warps) {
+    const long pair = order[i];
+    const long b = pair / topk;
+    const int jj = (int)(pair % topk);
+    const long long cell = cand[b * cand_stride + jj];
+    const unsigned long long packed = best_packed[pair];
+    const float bd = __uint_as_float((unsigned int)(packed >> 32));
+    const long bp = bank.cell_off[cell] + (long)(unsigned int)(packed & 0xffffffffull);
+    float lng = bank.proto_lnglat[2 * bp], lat = bank.proto_lnglat[2 * bp + 1];
+    if (bank.proto_count[bp] != 1) {
+      float4 qv[NV4];
+      const float4* q4 = reinterpret_cast<const float4*>(q + b * D);
+#pragma unroll
+      for (int k = 0; k < NV4; ++k) qv[k] = q4[lane + 32 * k];
+      const long mlo = bank.member_off[bp], mhi = bank.member_off[bp + 1];
+      float far = -INFINITY;
+      long bm = -1;
+      for (long mi = mlo; mi < mhi; ++mi) {
+        const long idx = bank.member_idx[mi];
+        const float dd = sqdist<NV4>(qv, bank.data_emb + idx * D, lane);
+        if (dd > far) { far = dd; bm = idx; }
+      }
+      if (bm >= 0) { lng = bank.data_lnglat[2 * bm]; lat = bank.data_lnglat[2 * bm + 1]; }
+    }
+    if (lane == 0) {
+      best_logit[pair] = -sqrtf(bd);
+      best_lnglat[2 * pair] = lng;
+      best_lnglat[2 * pair + 1] = lat;
+      best_proto[pair] = (int)bp;
+    }
+  }
+}
+
+// exclusive scans of the pair counts (-> cell_start, cursors zeroed) and of the tile counts (-> tile_prefix) of the cells:
+// tiles(c) = ceil(n_pairs(c) / qs) query passes x ceil(P_c / 16) prototype tiles.  Single block.
+__global__ void cell_tile_offsets_kernel(const RefinerBank bank, const int* __restrict__ cell_cnt,
+                                         int* __restrict__ cell_start, int* __restrict__ cursor,
+                                         int* __restrict__ tile_prefix, int C, int qs) {
+  __shared__ int carry[2];
+  __shared__ int warp_tot[2][32];
+  if (threadIdx.x < 2) carry[threadIdx.x] = 0;
+  __syncthreads();
+  const int ln = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  for (int base = 0; base < C; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    int v[2] = {0, 0};
+    if (i < C) {
+      v[0] = cell_cnt[i];
+      const int pc = (int)(bank.cell_off[i + 1] - bank.cell_off[i]);
+      v[1] = ((v[0] + qs - 1) / qs) * ((pc + kTP - 1) / kTP);
+    }
+    int x[2] = {v[0], v[1]};
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int y = __shfl_up_sync(0xffffffffu, x[a], o);
+        if (ln >= o) x[a] += y;
+      }
+    }
+    if (ln == 31) { warp_tot[0][wp] = x[0]; warp_tot[1][wp] = x[1]; }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int a = threadIdx.x >> 5;
+      int t = (ln < (int)(blockDim.x >> 5)) ? warp_tot[a][ln] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (ln >= o) t += y;
+      }
+      warp_tot[a][ln] = t;
+    }
+    __syncthreads();
+    const int off0 = wp ? warp_tot[0][wp - 1] : 0, off1 = wp ? warp_tot[1][wp - 1] : 0;
+    if (i < C) {
+      cell_start[i] = carry[0] + off0 + x[0] - v[0];
+      tile_prefix[i] = carry[1] + off1 + x[1] - v[1];
+      cursor[i] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) { carry[0] += off0 + x[0]; carry[1] += off1 + x[1]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { cell_start[C] = carry[0]; tile_prefix[C] = carry[1]; }
+}
+
+__global__ void proto_sqnorm_kernel(const float* __restrict__ proto_emb, long P, int D, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long warps = ((long)gridDim.x * blockDim.x) >> 5;
+  const int d4 = D >> 2;
+  for (long p = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < P; p += warps) {
+    const float4* r4 = reinterpret_cast<const float4*>(proto_emb + p * D);
+    float t = 0.f;
+    for (int c = lane; c < d4; c += 32) {
+      const float4 v = __ldg(r4 + c);
+      t = fmaf(v.x, v.x, t); t = fmaf(v.y, v.y, t); t = fmaf(v.z, v.z, t); t = fmaf(v.w, v.w, t);
+    }
+    t = warp_sum(t);
+    if (lane == 0) out[p] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Bank builder (reference models/proto_refiner.py:359-378, `_compute_protos_for_cell`): prototype embedding = mean of its
 // members' embeddings (members' 4-view mean first).  One warp per prototype, lanes strided over D as float4.
 // ------------------------------------------------------------------------------------------------
@@ -501,7 +922,8 @@ int refiner_scan(const RefinerBank& bank, const float* q, const long long* cand,
 }
 
 size_t refiner_sort_workspace_bytes(int num_cells, long pairs) {
-  return (size_t)(3 * (num_cells + 1) + pairs) * sizeof(int) + 1024;
+  // cell_cnt, cell_start, cursor, tile_prefix [C+1] | order [pairs] | packed winners of the tile scan u64 [pairs]
+  return (size_t)(4 * (num_cells + 1) + pairs + 2) * sizeof(int) + (size_t)pairs * 8 + 1024;
 }
 
 int refiner_scan_cell_major(const RefinerBank& bank, const float* q, const long long* cand, int cand_stride, long B,
@@ -544,6 +966,82 @@ int refiner_scan_cell_major(const RefinerBank& bank, const float* q, const long 
       return 1;
   }
   return check_launch("refiner_scan_cell_major");
+}
+
+template <int NV4, int QS>
+static int launch_tile_scan(const RefinerBank& bank, const float* q, const long long* cand, int cand_stride, int topk,
+                            const int* cell_start, const int* order, const int* tile_prefix,
+                            unsigned long long* best_packed, float* best_logit, float* best_lnglat, int* best_proto,
+                            long pairs, int num_sms, cudaStream_t stream) {
+  using Cfg = TileCfg<NV4, QS>;
+  auto kern = tile_scan_kernel<NV4, QS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem);
+  if (e != cudaSuccess) { set_last_error("refiner tile scan: shared memory attribute: %s", cudaGetErrorString(e)); return 1; }
+  {
+    ProfScope prof("refiner_scan", stream);
+    kern<<<num_sms, kTileThreads, Cfg::smem, stream>>>(bank, q, cell_start, order, tile_prefix, topk, best_packed);
+  }
+  if (check_launch("refiner_tile_scan")) return 1;
+  long blocks = (pairs + 7) / 8;
+  if (blocks > (long)num_sms * 8) blocks = (long)num_sms * 8;
+  ProfScope prof("refiner_scan_finish", stream);
+  tile_finish_kernel<NV4><<<(int)blocks, 256, 0, stream>>>(bank, q, cand, cand_stride, order, cell_start + bank.num_cells,
+                                                           topk, best_packed, best_logit, best_lnglat, best_proto);
+  return check_launch("refiner_tile_finish");
+}
+
+int refiner_scan_tiles(const RefinerBank& bank, const float* q, const long long* cand, int cand_stride, long B, int topk,
+                       void* sort_ws, float* best_logit, float* best_lnglat, int* best_proto, int num_sms,
+                       cudaStream_t stream) {
+  const long pairs = B * topk;
+  if (pairs == 0) return 0;
+  if (bank.dim % 128) { set_last_error("refiner: embedding dim %d not a multiple of 128", bank.dim); return 1; }
+  if (!bank.proto_sqnorm) { set_last_error("refiner tile scan: bank.proto_sqnorm is null"); return 1; }
+  if ((reinterpret_cast<uintptr_t>(bank.proto_emb) | reinterpret_cast<uintptr_t>(q)) & 15) {
+    set_last_error("refiner tile scan: proto_emb / queries must be 16-byte aligned"); return 1;
+  }
+  const int C = bank.num_cells;
+  int* cell_cnt = reinterpret_cast<int*>(sort_ws);
+  int* cell_start = cell_cnt + (C + 1);
+  int* cursor = cell_start + (C + 1);
+  int* tile_prefix = cursor + (C + 1);
+  int* order = tile_prefix + (C + 1);
+  unsigned long long* best_packed =
+      reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(order + pairs) + 7) & ~uintptr_t(7));
+  cudaError_t e = cudaMemsetAsync(cell_cnt, 0, (size_t)(C + 1) * sizeof(int), stream);
+  if (e != cudaSuccess) { set_last_error("refiner: memset: %s", cudaGetErrorString(e)); return 1; }
+  long blocks = (pairs + 255) / 256;
+  if (blocks > (long)num_sms * 8) blocks = (long)num_sms * 8;
+  const int qs = bank.dim > 768 ? 16 : 32;
+  {
+    ProfScope prof("refiner_sort", stream);
+    pair_hist_kernel<<<(int)blocks, 256, 0, stream>>>(bank, cand, cand_stride, B, topk, cell_cnt, best_logit, best_lnglat,
+                                                      best_proto, best_packed);
+    cell_tile_offsets_kernel<<<1, 1024, 0, stream>>>(bank, cell_cnt, cell_start, cursor, tile_prefix, C, qs);
+    pair_scatter_kernel<<<(int)blocks, 256, 0, stream>>>(bank, cand, cand_stride, B, topk, cell_start, cursor, order);
+  }
+  if (check_launch("refiner_sort")) return 1;
+  switch (bank.dim / 128) {
+#define PG_CASE(N, Q)                                                                                                \
+  case N:                                                                                                            \
+    return launch_tile_scan<N, Q>(bank, q, cand, cand_stride, topk, cell_start, order, tile_prefix, best_packed,     \
+                                  best_logit, best_lnglat, best_proto, pairs, num_sms, stream);
+    PG_CASE(1, 32) PG_CASE(2, 32) PG_CASE(4, 32) PG_CASE(6, 32) PG_CASE(8, 16)
+#undef PG_CASE
+    default:
+      set_last_error("refiner: embedding dim %d unsupported (need 128*{1,2,4,6,8})", bank.dim);
+      return 1;
+  }
+}
+
+int refiner_bank_sqnorm(const float* proto_emb, long P, int D, float* out, int num_sms, cudaStream_t stream) {
+  if (P == 0) return 0;
+  if (D % 4) { set_last_error("refiner_bank_sqnorm: D=%d not a multiple of 4", D); return 1; }
+  long blocks = (P + 7) / 8;
+  if (blocks > (long)num_sms * 16) blocks = (long)num_sms * 16;
+  ProfScope prof("bank_sqnorm", stream);
+  proto_sqnorm_kernel<<<(int)blocks, 256, 0, stream>>>(proto_emb, P, D, out);
+  return check_launch("bank_sqnorm");
 }
 
 int bank_build(const float* data_views, long N, int V, int D, const long long* member_off, const long long* member_idx,

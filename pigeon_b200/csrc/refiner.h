@@ -17,6 +17,7 @@ struct RefinerBank {
   const long long* member_idx; // [...]  rows of data_emb / data_lnglat
   const float* data_emb;       // [Ntrain, D] training embeddings (4-view mean already applied)
   const float* data_lnglat;    // [Ntrain, 2] training labels (lng, lat) fp32
+  const float* proto_sqnorm;   // [P] |prototype|^2 (refiner_bank_sqnorm), or nullptr: the tile scan needs it
 };
 
 int refiner_pool(const float* emb, float* q, long B, int V, int D, cudaStream_t stream);
@@ -27,6 +28,13 @@ size_t refiner_sort_workspace_bytes(int num_cells, long pairs);
 int refiner_scan_cell_major(const RefinerBank& bank, const float* q, const long long* cand, int cand_stride, long B,
                             int topk, void* sort_ws, float* best_logit, float* best_lnglat, int* best_proto,
                             int num_sms, cudaStream_t stream);
+// Tile scan (v4): same contract as refiner_scan_cell_major, needs bank.proto_sqnorm.  Persistent CTAs stream 16-prototype
+// tiles through a shared-memory ring (cp.async.bulk) and score them against up to 32 staged queries of the geocell.
+int refiner_scan_tiles(const RefinerBank& bank, const float* q, const long long* cand, int cand_stride, long B, int topk,
+                       void* sort_ws, float* best_logit, float* best_lnglat, int* best_proto, int num_sms,
+                       cudaStream_t stream);
+// |p|^2 of every prototype row (once per bank)
+int refiner_bank_sqnorm(const float* proto_emb, long P, int D, float* out, int num_sms, cudaStream_t stream);
 // data_views [N, V, D] -> data_mean [N, D] (view mean) and proto_emb [P, D] (mean of member rows of data_mean)
 int bank_build(const float* data_views, long N, int V, int D, const long long* member_off, const long long* member_idx,
                long P, float* data_mean, float* proto_emb, int num_sms, cudaStream_t stream);

@@ -111,7 +111,7 @@ def refiner_finalize(best_logit: torch.Tensor, best_lnglat: torch.Tensor, init_l
 
 
 def refiner_set_schedule(mode: int) -> None:
-    """A/B switch of the refiner scan: 0 automatic, 1 query-major, 2 cell-major (same results)."""
+    """A/B switch of the refiner scan: 0 automatic, 1 query-major, 2 cell-major, 3 tile scan (same selections)."""
     check(load().pg_refiner_set_schedule(int(mode)), "pg_refiner_set_schedule")
 
 
@@ -168,7 +168,16 @@ class DeviceBank:
             setattr(self, f, t)
         self.num_cells = int(arrays["cell_off"].shape[0]) - 1
         self.dim = int(self.proto_emb.shape[1])
-        self.c_struct = _lib.RefinerBank(self.num_cells, self.dim, *(ptr(getattr(self, f)) for f in self.FIELDS))
+        # |p|^2 per prototype, once per bank: the tile scan (schedule 3) scores in the |p|^2 + |q|^2 - 2 p.q form
+        self.proto_sqnorm = None
+        P = int(arrays["proto_emb"].shape[0])
+        if self.device.type == "cuda" and P > 0:
+            self.proto_sqnorm = torch.empty(P, dtype=torch.float32, device=self.device)
+            with torch.cuda.device(self.device):
+                check(load().pg_refiner_bank_sqnorm(ptr(self.proto_emb), P, self.dim, ptr(self.proto_sqnorm),
+                                                    current_stream_ptr()), "pg_refiner_bank_sqnorm")
+        self.c_struct = _lib.RefinerBank(self.num_cells, self.dim, *(ptr(getattr(self, f)) for f in self.FIELDS),
+                                         ptr(self.proto_sqnorm) if self.proto_sqnorm is not None else None)
 
 
 def refiner_forward(bank: DeviceBank, emb: torch.Tensor, init_lnglat: torch.Tensor, cand_idx: torch.Tensor,

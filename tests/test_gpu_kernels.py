@@ -249,6 +249,65 @@ def test_refiner_cell_major_equals_query_major(cuda, C, P, D, B, kc, topk, membe
     assert torch.equal(cell_q[rows], cell_c[rows]) and torch.equal(ll_q[rows], ll_c[rows])
 
 
+@pytest.mark.parametrize("C,P,D,B,kc,topk,members", [
+    (30, 900, 1024, 256, 8, 8, 4.0),       # D = 1024: 16 staged queries, 68 pairs per cell -> 5 query passes
+    (64, 4000, 768, 512, 10, 5, 0.0),      # 40 pairs per cell -> two passes of 32 + 8, ragged last tiles
+    (20, 150, 128, 3, 4, 4, 3.0),          # a handful of pairs, cells smaller than one tile
+    (7, 3000, 512, 2000, 3, 3, 0.0),       # 857 pairs per cell (27 passes), 4-stage ring
+    (200, 20000, 256, 1500, 6, 5, 2.0),    # more cells than SMs: ranges of several cells, straddling cells merged by atomicMin
+    (3, 5000, 768, 40, 2, 2, 0.0),         # fewer cells than SMs: every cell cut across many CTAs
+])
+def test_refiner_tile_scan_equals_cell_major(cuda, C, P, D, B, kc, topk, members):
+    """The tile scan (persistent CTAs, cp.async.bulk ring, 8-way split of D, packed atomicMin merge) against the cell-major
+    and query-major schedules: same winners wherever two prototypes do not tie within fp32 summation-order noise."""
+    from pigeon_b200 import ops, synthetic
+    bank = synthetic.synthetic_bank(C, P, D, seed=31, members_mean=members, empty_cells=min(2, C - 1))
+    cand, probs = synthetic.synthetic_candidates(B, kc, C, seed=32)
+    emb = torch.from_numpy(synthetic.synthetic_queries(bank, cand, views=1, seed=33)).to(cuda)
+    init = torch.from_numpy(synthetic.synthetic_geocells(B, seed=34)).to(cuda)
+    dbank = ops.DeviceBank(cuda, **bank)
+    assert dbank.proto_sqnorm is not None
+    ref_norm = (dbank.proto_emb.double() ** 2).sum(1)
+    assert torch.allclose(dbank.proto_sqnorm.double(), ref_norm, rtol=1e-6)
+    args = (dbank, emb, init, torch.from_numpy(cand).to(cuda), torch.from_numpy(probs).to(cuda), topk, 1.6, 1e6)
+    try:
+        ops.refiner_set_schedule(1)
+        _, _, dq = ops.refiner_forward(*args, debug=True)
+        ops.refiner_set_schedule(2)
+        ll_c, cell_c, dc = ops.refiner_forward(*args, debug=True)
+        ops.refiner_set_schedule(3)
+        ll_t, cell_t, dt = ops.refiner_forward(*args, debug=True)
+        ll_t2, cell_t2, dt2 = ops.refiner_forward(*args, debug=True)
+    finally:
+        ops.refiner_set_schedule(0)
+    torch.cuda.synchronize()
+    # run to run: the merge is an atomicMin on (d2, prototype), so the result does not depend on arrival order
+    assert torch.equal(dt["best_proto"], dt2["best_proto"]) and torch.equal(dt["best_logit"], dt2["best_logit"])
+    assert torch.equal(ll_t, ll_t2) and torch.equal(cell_t, cell_t2)
+    for other in (dc, dq):
+        same = dt["best_proto"] == other["best_proto"]
+        assert same.float().mean() > 0.995, same.float().mean()
+        assert torch.allclose(dt["best_logit"], other["best_logit"], rtol=5e-5, atol=1e-5)
+        assert torch.equal(dt["best_lnglat"][same], other["best_lnglat"][same])
+    rows = (dt["best_proto"] == dc["best_proto"]).all(dim=1)
+    assert torch.equal(cell_t[rows], cell_c[rows]) and torch.equal(ll_t[rows], ll_c[rows])
+    # the winner really is the nearest prototype of its cell (fp64 check on a sample of pairs)
+    bp = dt["best_proto"].cpu()
+    off = torch.as_tensor(bank["cell_off"])
+    pe = dbank.proto_emb.double().cpu()
+    q = emb[:, 0].double().cpu()
+    for b in range(0, B, max(1, B // 16)):
+        for j in range(topk):
+            c = int(cand[b, j])
+            lo, hi = int(off[c]), int(off[c + 1])
+            if hi <= lo:
+                assert int(bp[b, j]) == -1
+                continue
+            d = ((pe[lo:hi] - q[b]) ** 2).sum(1)
+            win = int(bp[b, j]) - lo
+            assert 0 <= win < hi - lo and d[win] <= d.min() * (1 + 1e-5) + 1e-6
+
+
 @pytest.mark.parametrize("world,members", [(2, 0.0), (4, 3.0), (8, 0.0)])
 def test_refiner_cell_sharded_equals_replicated(cuda, world, members):
     """SURVEY.md 8e-ii on one GPU: scan the same queries against each of `world` cell shards (bank.shard_bank), merge the
