@@ -103,6 +103,11 @@ int pg_head_forward(const float* emb, int32_t B, int32_t V, int32_t D, const voi
                     const double* centroids, int32_t C, int32_t k, void* workspace, size_t workspace_bytes,
                     float* pooled, float* logits, float* probs, int64_t* pred_cell, double* pred_lnglat,
                     float* topk_val, int64_t* topk_idx, void* stream);
+/* Measurement / deployment switch of pg_head_forward for this process: 0 (default) = three kernels (view mean + split,
+ * tcgen05 GEMM + bias, softmax / arg-max / top-k); 1 = ONE kernel doing all of it (D % 64 == 0 and C <= 6144, otherwise the
+ * three-kernel sequence runs): the view mean and the hi/lo split happen in the GEMM's A-operand producer warps and the CTA
+ * that completes a block of 128 samples last normalises its rows.  Same results to fp32 summation order. */
+int pg_head_set_fused(int32_t on);
 
 /* Classification loss of reference models/super_guessr.py:468-474 (CrossEntropyLoss, mean over the batch).
  *   mode 0: labels_idx i64 [B] class indices;  mode 1: soft f32 [B, C] target probabilities;

@@ -31,6 +31,7 @@ SOURCES = [
     "nccl_gather.cu",
     "vit_misc.cu",
     "head.cu",
+    "head_fused_tcgen05.cu",
     "refiner.cu",
     "train.cu",
     "preprocess.cu",

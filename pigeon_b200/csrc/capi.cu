@@ -208,6 +208,22 @@ size_t pg_head_workspace_bytes(int32_t B, int32_t D) {
   return align_up((size_t)B * 3 * D * 2, 1024);
 }
 
+// Process-wide switch like pg_refiner_set_schedule; PG_HEAD_FUSED=1 only sets the initial value, once.
+static std::atomic<int> g_head_fused{-1};
+static bool head_fused_on() {
+  int v = g_head_fused.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("PG_HEAD_FUSED");
+    v = (e && e[0] == '1') ? 1 : 0;
+    g_head_fused.store(v, std::memory_order_relaxed);
+  }
+  return v == 1;
+}
+int pg_head_set_fused(int32_t on) {
+  g_head_fused.store(on ? 1 : 0, std::memory_order_relaxed);
+  return 0;
+}
+
 int pg_head_forward(const float* emb, int32_t B, int32_t V, int32_t D, const void* w3, const float* bias,
                     const double* centroids, int32_t C, int32_t k, void* workspace, size_t workspace_bytes,
                     float* pooled, float* logits, float* probs, int64_t* pred_cell, double* pred_lnglat,
@@ -220,6 +236,12 @@ int pg_head_forward(const float* emb, int32_t B, int32_t V, int32_t D, const voi
   const int sms = sm_count();
   if (sms < 0) return 1;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  // pg_head_set_fused(1): one kernel (view mean + split -> tcgen05 GEMM -> bias -> softmax / arg-max / top-k) whenever the
+  // shape allows; the default is the three-kernel sequence, which is faster at the batch sizes of this path
+  if (head_fused_on() && head_fused_supported(B, V, D, C, k))
+    return head_fused_forward(emb, B, V, D, w3, bias, centroids, C, k, workspace, pooled, logits, probs,
+                              reinterpret_cast<long long*>(pred_cell), pred_lnglat, topk_val,
+                              reinterpret_cast<long long*>(topk_idx), stream);
   if (view_mean_split(emb, pooled, workspace, B, V, D, stream)) return 1;
   GemmProblem p{};
   p.M = B; p.N = C; p.K = 3 * D;

@@ -110,6 +110,11 @@ def refiner_finalize(best_logit: torch.Tensor, best_lnglat: torch.Tensor, init_l
     return out_ll, out_cell, choice
 
 
+def head_set_fused(on: bool) -> None:
+    """A/B switch of the geocell head: False (default) three kernels, True the single fused kernel (same results)."""
+    check(load().pg_head_set_fused(1 if on else 0), "pg_head_set_fused")
+
+
 def refiner_set_schedule(mode: int) -> None:
     """A/B switch of the refiner scan: 0 automatic, 1 query-major, 2 cell-major, 3 tile scan (same selections)."""
     check(load().pg_refiner_set_schedule(int(mode)), "pg_refiner_set_schedule")

@@ -150,8 +150,18 @@ def test_attention_growing_logits_exercise_rescale(cuda, variant, poly):
 
 # ------------------------------------------------------------------------------------------------ head
 @pytest.mark.parametrize("B,V,D,C,k", [(8, 4, 1024, 1000, 50), (3, 1, 1024, 2076, 5), (256, 4, 1024, 1000, 50),
-                                       (5, 4, 256, 331, 7)])
-def test_head(cuda, B, V, D, C, k):
+                                       (5, 4, 256, 331, 7), (300, 4, 1024, 2076, 5)])
+@pytest.mark.parametrize("fused", [False, True])
+def test_head(cuda, B, V, D, C, k, fused):
+    from pigeon_b200 import ops
+    ops.head_set_fused(fused)
+    try:
+        _check_head(cuda, B, V, D, C, k)
+    finally:
+        ops.head_set_fused(False)
+
+
+def _check_head(cuda, B, V, D, C, k):
     from pigeon_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(B + C)
     emb = (torch.randn(B, V, D, generator=g) * 0.3).to(cuda)
