@@ -422,7 +422,8 @@ def run_refiner(args):
         "ms_per_step_by_rank": [m / args.steps for m in ms_by_rank],
         "e2e": {"value": B * args.steps / (ms_e2e / 1e3), "unit": "queries/s",
                 "h2d_bytes_per_step": B * dim * 4 + B * 16 + B * k * 12, "d2h_bytes_per_step": B * 16},
-        "roofline": {"kernel": ("tile_scan_kernel + tile_finish_kernel" if args.refiner_schedule in (0, 3) else
+        "roofline": {"kernel": ("slab_scan_kernel + tile_finish_kernel" if args.refiner_schedule in (0, 4) else
+                                "tile_scan_kernel + tile_finish_kernel" if args.refiner_schedule == 3 else
                                 "cell_major_scan_kernel" if args.refiner_schedule == 2 else "scan_kernel") + " (rank 0's shard)",
                      "bound": "hbm",
                      "achieved": alg_bytes / (scan_ms / 1e3) / 1e9 if scan_ms else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -637,8 +638,8 @@ def main():
     ap.add_argument("--no-ln-fold", action="store_true", help="A/B: run the LayerNorm kernels instead of the folded epilogues")
     ap.add_argument("--replicated-bank", action="store_true", help="infer, N > 1: every rank holds the whole bank (A/B)")
     ap.add_argument("--refiner-topk", type=int, default=5)
-    ap.add_argument("--refiner-schedule", type=int, default=0, choices=[0, 1, 2, 3],
-                    help="refiner scan: 0 automatic (tile scan), 1 query-major, 2 cell-major (round-1/2 kernel), 3 tile scan")
+    ap.add_argument("--refiner-schedule", type=int, default=0, choices=[0, 1, 2, 3, 4],
+                    help="refiner scan: 0 automatic (slab scan at this shape), 1 query-major, 2 cell-major (round-1/2 kernel), 3 tile scan, 4 slab scan")
     ap.add_argument("--refiner-dim", type=int, default=768)
     ap.add_argument("--train-batch", type=int, default=128, help="train: four-view samples per GPU per step")
     ap.add_argument("--chunk-views", type=int, default=64)

@@ -328,17 +328,21 @@ static RefinerBank to_bank(const pg_refiner_bank* bank) {
   return rb;
 }
 
-// Which scan the schedule and the call shape select: 1 query-major, 2 cell-major (v3), 3 tile scan (v4).
+// Which scan the schedule and the call shape select: 1 query-major, 2 cell-major (v3), 3 tile scan (v4), 4 slab scan (v5).
 static int pick_scan(int sched, int64_t B, int32_t topk, const pg_refiner_bank* bank) {
+  const bool slab_ok = bank->proto_sqnorm && bank->num_protos > 0;
   if (sched == 1 || sched == 2) return sched;
   if (sched == 3) return bank->proto_sqnorm ? 3 : 2;
+  if (sched == 4) return slab_ok ? 4 : 2;
   if ((long)B * topk < 2L * bank->num_cells) return 1;   // small batches: the sort would dominate
-  return bank->proto_sqnorm ? 3 : 2;
+  // a slab is 64 prototypes of ONE geocell and a CTA tile 512: only banks with large geocells fill them
+  if (slab_ok && bank->num_protos >= 256L * bank->num_cells) return 4;
+  return 2;
 }
 
 // Scan schedule of pg_refiner_forward: 0 = automatic (cell-major when geocells are shared by >= 2 pairs on average),
-// 1 = query-major, 2 = cell-major (v3), 3 = tile scan (v4; what automatic picks for shared cells when the bank carries
-// proto_sqnorm).  Process-wide A/B switch (pg_refiner_set_schedule); the environment variable
+// 1 = query-major, 2 = cell-major (v3), 3 = tile scan (v4), 4 = slab scan (v5; what automatic picks for banks with large
+// geocells).  Process-wide A/B switch (pg_refiner_set_schedule); the environment variable
 // PG_REFINER_QUERY_MAJOR=1 only sets the initial value, once.
 static std::atomic<int> g_refiner_schedule{-1};
 static int refiner_schedule() {
@@ -352,7 +356,7 @@ static int refiner_schedule() {
 }
 
 int pg_refiner_set_schedule(int32_t mode) {
-  if (mode < 0 || mode > 3) { set_last_error("pg_refiner_set_schedule: mode %d not in {0, 1, 2, 3}", mode); return 1; }
+  if (mode < 0 || mode > 4) { set_last_error("pg_refiner_set_schedule: mode %d not in {0, 1, 2, 3, 4}", mode); return 1; }
   g_refiner_schedule.store(mode, std::memory_order_relaxed);
   return 0;
 }
@@ -388,7 +392,9 @@ int pg_refiner_forward(const pg_refiner_bank* bank, const float* emb, int64_t B,
   // the query-major kernel (one warp per pair) for small batches where the sort would dominate
   const int scan = pick_scan(refiner_schedule(), B, topk, bank);
   const long long* cand = reinterpret_cast<const long long*>(cand_idx);
-  if (scan == 3) {
+  if (scan == 4) {
+    if (refiner_scan_slabs(rb, bank->num_protos, q, cand, cand_stride, B, topk, sort_ws, bl, bll, bp, sms, stream)) return 1;
+  } else if (scan == 3) {
     if (refiner_scan_tiles(rb, q, cand, cand_stride, B, topk, sort_ws, bl, bll, bp, sms, stream)) return 1;
   } else if (scan == 2) {
     if (refiner_scan_cell_major(rb, q, cand, cand_stride, B, topk, sort_ws, bl, bll, bp, sms, stream)) return 1;
@@ -426,6 +432,9 @@ int pg_refiner_scan(const pg_refiner_bank* bank, const float* emb, int64_t B, in
   if (refiner_pool(emb, q, B, V, bank->dim, stream)) return 1;
   const int scan = pick_scan(refiner_schedule(), B, topk, bank);
   const long long* cand = reinterpret_cast<const long long*>(cand_idx);
+  if (scan == 4)
+    return refiner_scan_slabs(rb, bank->num_protos, q, cand, cand_stride, B, topk, sort_ws, best_logit, best_lnglat,
+                              best_proto, sms, stream);
   if (scan == 3)
     return refiner_scan_tiles(rb, q, cand, cand_stride, B, topk, sort_ws, best_logit, best_lnglat, best_proto, sms, stream);
   if (scan == 2)

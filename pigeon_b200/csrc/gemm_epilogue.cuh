@@ -117,6 +117,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
   constexpr bool kStats = EpiTraits<EPI>::kStats;
   constexpr bool kLn = EpiTraits<EPI>::kLn;
   const int sub = lane >> 3, c16 = lane & 7;
+  // the staging buffer through explicit st.shared / ld.shared: `stage` went through integer alignment arithmetic in the
+  // callers, so the compiler treats it as a generic pointer and would emit ST.E / LD.E (address-space check per access)
+  const uint32_t stage_s = smem_u32(stage);
   float4 res[8], res_next[8];
   const uint64_t pol_stream = kResid ? l2_policy_evict_first() : 0;
   // LayerNorm consumer: statistics of this thread's A row (= output row) from the producer's per-128-column partials
@@ -208,7 +211,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
       }
     }
     if (kSave && fast) {    // keep the pre-activation (fp16) for the backward pass: same staging / coalesced store, to aux
-      uint8_t* srow = stage + lane * 128;
+      const uint32_t srow = stage_s + lane * 128;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         uint4 pk;
@@ -216,7 +219,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
         pk.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
         pk.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
         pk.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
-        *reinterpret_cast<uint4*>(srow + ((j ^ (lane & 7)) << 4)) = pk;
+        sts_u4(srow + ((j ^ (lane & 7)) << 4), pk);
       }
       __syncwarp();
 #pragma unroll
@@ -225,7 +228,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
         const int grow = warp_row0 + rr;
         if (grow < args.M)
           *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(args.aux) + ((long)grow * args.ldo + col0) * 2 + c16 * 16) =
-              *reinterpret_cast<const uint4*>(stage + rr * 128 + ((c16 ^ (rr & 7)) << 4));
+              lds_u4(stage_s + rr * 128 + ((c16 ^ (rr & 7)) << 4));
       }
       __syncwarp();
     }
@@ -244,7 +247,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
     }
     if (fast) {
       // ---- stage this thread's row (128 bytes); 16-byte piece j of row `lane` lives at piece slot j ^ (lane & 7)
-      uint8_t* srow = stage + lane * 128;
+      const uint32_t srow = stage_s + lane * 128;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         uint4 pk;
@@ -259,7 +262,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
           pk.z = __float_as_uint(v[4 * j + 2]);
           pk.w = __float_as_uint(v[4 * j + 3]);
         }
-        *reinterpret_cast<uint4*>(srow + ((j ^ (lane & 7)) << 4)) = pk;
+        sts_u4(srow + ((j ^ (lane & 7)) << 4), pk);
       }
       __syncwarp();
       // ---- coalesced global phase
@@ -268,7 +271,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& args, uint32_t t_r
         const int rr = i * 4 + sub;
         const int grow = warp_row0 + rr;
         if (grow < args.M) {
-          uint4 val = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((c16 ^ (rr & 7)) << 4));
+          uint4 val = lds_u4(stage_s + rr * 128 + ((c16 ^ (rr & 7)) << 4));
           long orow = grow;
           if (EPI == EPI_F32_ROWMAP)
             orow = (long)args.rowmap_mul * (grow / args.rowmap_div) + (grow % args.rowmap_div) + args.rowmap_add;

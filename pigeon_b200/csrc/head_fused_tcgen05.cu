@@ -168,7 +168,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadArgs h) 
         }
       }
       mbar_wait(&empty_bar[stage], phase ^ 1);
-      uint8_t* st = smem + stage * kHeadStageBytes;
+      const uint32_t st = smem_u32(smem) + stage * kHeadStageBytes;   // explicit st.shared: `smem` is generic to the compiler
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {   // 16-byte piece ch of row r sits at piece ch ^ (r & 7)
         uint32_t hi4[4], lo4[4];
@@ -181,8 +181,8 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadArgs h) 
           lo4[e] = (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(cl) << 16);
         }
         const uint32_t off = row_off + (uint32_t)((ch ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(st + off) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
-        *reinterpret_cast<uint4*>(st + kHeadABytes + off) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+        sts_u4(st + off, make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]));
+        sts_u4(st + kHeadABytes + off, make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]));
       }
       fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async proxy
       __syncwarp();
@@ -222,32 +222,32 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadArgs h) 
 
   // ------------------------------------------------------------------ softmax, arg-max + centroid, top-k: warp per sample
   const int cpad = (h.C + 3) & ~3;
-  float* sp = reinterpret_cast<float*>(smem) + (size_t)warp * cpad;
+  const uint32_t sp = smem_u32(smem) + (uint32_t)warp * cpad * 4;   // this warp's probability row (explicit ld/st.shared)
   for (int r = warp; r < HB_M; r += kHeadThreads / 32) {
     const long b = (long)m_blk * HB_M + r;
     if (b >= h.B) break;
     const float* lr = h.logits + b * h.C;
     float m = -INFINITY;
-    for (int c0 = 0; c0 < h.C; c0 += 32 * 8) {   // eight independent L2 reads in flight per lane (the stores into the
-      float v[8];                                 // generic `sp` pointer would otherwise order every load behind them)
+    for (int c0 = 0; c0 < h.C; c0 += 32 * 8) {   // eight independent L2 reads in flight per lane
+      float v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) { const int c = c0 + u * 32 + lane; v[u] = c < h.C ? __ldcg(lr + c) : -INFINITY; }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) { const int c = c0 + u * 32 + lane; if (c < h.C) { sp[c] = v[u]; m = fmaxf(m, v[u]); } }
+      for (int u = 0; u < 8; ++u) { const int c = c0 + u * 32 + lane; if (c < h.C) { sts_f1(sp + c * 4, v[u]); m = fmaxf(m, v[u]); } }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     float s = 0.f;
-    for (int c = lane; c < h.C; c += 32) { const float e = expf(sp[c] - m); sp[c] = e; s += e; }
+    for (int c = lane; c < h.C; c += 32) { const float e = expf(lds_f1(sp + c * 4) - m); sts_f1(sp + c * 4, e); s += e; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    for (int c = lane; c < h.C; c += 32) { const float p = sp[c] / s; sp[c] = p; h.probs[b * h.C + c] = p; }
+    for (int c = lane; c < h.C; c += 32) { const float p = lds_f1(sp + c * 4) / s; sts_f1(sp + c * 4, p); h.probs[b * h.C + c] = p; }
     __syncwarp();
     for (int j = 0; j < h.k; ++j) {
       float bv = -INFINITY;
       int bi = 0x7fffffff;
       for (int c = lane; c < h.C; c += 32) {
-        const float p = sp[c];
+        const float p = lds_f1(sp + c * 4);
         if (p != -1.f && head_better(p, c, bv, bi)) { bv = p; bi = c; }
       }
 #pragma unroll
@@ -264,7 +264,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const HeadArgs h) 
           h.pred_lnglat[2 * b] = h.centroids[2 * (long)bi];
           h.pred_lnglat[2 * b + 1] = h.centroids[2 * (long)bi + 1];
         }
-        sp[bi] = -1.f;   // probabilities are >= 0, so -1 marks "taken"
+        sts_f1(sp + bi * 4, -1.f);   // probabilities are >= 0, so -1 marks "taken"
       }
       __syncwarp();
     }

@@ -428,8 +428,10 @@ struct TileCfg {
   static_assert(smem <= 227 * 1024, "shared memory budget");
 };
 
-// Walks the tiles [x, x_hi) of the global tile list: one item = consecutive tiles of one (geocell, query pass).
-struct TileWalk {
+// Walks the units [x, x_hi) of the global work list (UNIT prototypes each): one item = consecutive units of one
+// (geocell, query pass).
+template <int UNIT>
+struct UnitWalk {
   long long x, x_hi;
   int c;                  // current geocell
   long lo;                // its first prototype
@@ -448,7 +450,7 @@ struct TileWalk {
     while (tile_prefix[c + 1] <= x) ++c;
     lo = bank.cell_off[c];
     Pc = (int)(bank.cell_off[c + 1] - lo);
-    tpc = (Pc + kTP - 1) / kTP;
+    tpc = (Pc + UNIT - 1) / UNIT;
     pair0 = cell_start[c];
     n_pairs = cell_start[c + 1] - pair0;
     const int local = (int)(x - tile_prefix[c]);
@@ -460,6 +462,8 @@ struct TileWalk {
     return true;
   }
 };
+
+using TileWalk = UnitWalk<kTP>;
 
 // The same walk one tile at a time (producer: one iterator for the copies, one running ahead for the L2 prefetch).
 struct TileIter {
@@ -689,6 +693,230 @@ tile_scan_kernel(const RefinerBank bank, const float* __restrict__ q, const int*
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Slab scan (v5).  Measured on this GPU (tools/ubench/fp32_lds.cu): shared memory delivers 128 bytes per clock per SM to the
+// registers whatever the broadcast pattern — an LDS.128 costs four LSU cycles — and FFMA2 retires 128 FMA per clock per SM.
+// A kernel whose operands come from shared memory is therefore FMA-bound only from 4 FMA per delivered float upwards; the
+// tile scan's 2 x 2NCH register tile delivers 1.5 (ncu: LSU wavefronts 76 %, FMA pipe 33 %), the cell-major kernel 4 but
+// pays a 31-shuffle reduction per 32 results.  This kernel uses the 8-prototype x 8-query outer-product tile (4 FMA per
+// float: 79 % of the FMA peak in the micro-benchmark) without any cross-lane reduction:
+//   * a warp owns a SLAB of 64 prototypes (lanes = 8 prototype groups x 4 query groups; thread = 8 prototypes x up to 4
+//     query pairs, accumulators in registers over the whole embedding), a CTA up to 8 consecutive slabs of one geocell;
+//   * the embedding dimension is streamed in chunks of 32 floats: one TMA box of [256 prototypes x 128 bytes] per half tile
+//     (tensor map over the bank, 128-byte swizzle -> conflict-free LDS.128 of 8 rows), 3 stages of 64 KB, mbarrier ring;
+//   * the query chunk [32 queries x 32 floats] is gathered by the consumer threads one chunk ahead (registers -> double
+//     buffer, pairs interleaved for FFMA2, rows padded by 16 bytes);
+//   * d2 = |p|^2 + |q|^2 - 2 p.q, minimum over the thread's prototypes, three shuffles across the prototype groups, one
+//     packed atomicMin per (warp, query): partition-independent like the tile scan.
+// Work list = slabs of all touched (geocell, query pass) pairs, cut into gridDim.x equal contiguous ranges.
+// Meant for banks whose geocells hold hundreds of prototypes (BASELINE configs[4]: 482 on average).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSlab = 64;
+constexpr int kSlabWarps = 8;
+constexpr int kSlabConsumers = kSlabWarps * 32;
+constexpr int kSlabThreads = kSlabConsumers + 32;
+constexpr int kKC = 32;                                   // floats per embedding chunk (128 bytes)
+constexpr int kSlabStages = 3;
+constexpr int kBoxRows = 256;
+constexpr int kBoxBytes = kBoxRows * kKC * 4;             // 32 KB
+constexpr int kPStageBytes = 2 * kBoxBytes;               // 512 prototypes x 128 B
+constexpr int kQS = 32;                                   // queries per pass
+constexpr int kQRowF4 = 17;                               // float4 per query-pair row of a chunk (16 + 1 pad)
+constexpr int kQBufBytes = (kQS / 2) * kQRowF4 * 16;
+constexpr int kSlabSmem = kSlabStages * kPStageBytes + 2 * kQBufBytes + kQS * 4 + 2 * kSlabStages * 8 + 1024;
+using SlabWalk = UnitWalk<kSlab>;
+
+__device__ __forceinline__ void slab_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kSlabConsumers) : "memory"); }
+
+template <int NJ>
+__device__ __forceinline__ void slab_item(const RefinerBank& bank, const SlabWalk& w, const float* __restrict__ q, int D,
+                                          int topk, const int* __restrict__ ord, int nq, uint32_t pstages,
+                                          uint32_t qbuf, const float* __restrict__ qn, uint64_t* full, uint64_t* empty,
+                                          int& stage, uint32_t& phase, unsigned long long* __restrict__ best_packed) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, h = lane & 3;
+  const int nchunks = D / kKC;
+  // query-chunk gather: thread = (pair row u, float2 slot part)
+  const int u = tid >> 4, part = tid & 15;
+  const bool stage_q = u < 4 * NJ;
+  const float* qa = (2 * u < nq) ? q + (size_t)(ord[2 * u] / topk) * D + 2 * part : nullptr;
+  const float* qb = (2 * u + 1 < nq) ? q + (size_t)(ord[2 * u + 1] / topk) * D + 2 * part : nullptr;
+  auto fetch = [&](int c, float2& a, float2& b) {
+    a = make_float2(0.f, 0.f); b = a;
+    if (qa) a = *reinterpret_cast<const float2*>(qa + c * kKC);
+    if (qb) b = *reinterpret_cast<const float2*>(qb + c * kKC);
+  };
+  for (int s0 = w.t0; s0 < w.t1; s0 += kSlabWarps) {
+    const int slab = s0 + warp;
+    const bool active = slab < w.t1;
+    float pn[8];
+    bool ok[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = slab * kSlab + g + 8 * i;
+      ok[i] = active && idx < w.Pc;
+      pn[i] = ok[i] ? __ldg(bank.proto_sqnorm + w.lo + idx) : 0.f;
+    }
+    float2 acc[8][NJ];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    float2 ra, rb;
+    fetch(0, ra, rb);
+    slab_bar();   // every warp is done with both query buffers (previous tile / item)
+    if (stage_q) sts_f4(qbuf + (u * kQRowF4 + part) * 16, make_float4(ra.x, rb.x, ra.y, rb.y));
+    slab_bar();
+    // this warp's rows inside the stage: box (rows 0..255 | 256..511), row & 7 == g
+    const uint32_t prow = (uint32_t)((warp * kSlab) >> 8) * kBoxBytes + (uint32_t)((warp * kSlab) & 255) * 128 + g * 128;
+    for (int c = 0; c < nchunks; ++c) {
+      if (c + 1 < nchunks) fetch(c + 1, ra, rb);
+      mbar_wait(&full[stage], phase);
+      if (active) {
+        const uint32_t pw = pstages + (uint32_t)stage * kPStageBytes + prow;
+        const uint32_t qv = qbuf + ((c & 1) * ((kQS / 2) * kQRowF4) + h * kQRowF4) * 16;
+#pragma unroll 2
+        for (int c4 = 0; c4 < kKC / 4; ++c4) {
+          float4 p[8], q0[NJ], q1[NJ];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) p[i] = lds_f4(pw + i * 8 * 128 + ((c4 ^ g) << 4));
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) { q0[j] = lds_f4(qv + (4 * j * kQRowF4 + 2 * c4) * 16); q1[j] = lds_f4(qv + (4 * j * kQRowF4 + 2 * c4 + 1) * 16); }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+              acc[i][j] = ffma2(make_float2(p[i].x, p[i].x), make_float2(q0[j].x, q0[j].y), acc[i][j]);
+              acc[i][j] = ffma2(make_float2(p[i].y, p[i].y), make_float2(q0[j].z, q0[j].w), acc[i][j]);
+              acc[i][j] = ffma2(make_float2(p[i].z, p[i].z), make_float2(q1[j].x, q1[j].y), acc[i][j]);
+              acc[i][j] = ffma2(make_float2(p[i].w, p[i].w), make_float2(q1[j].z, q1[j].w), acc[i][j]);
+            }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (++stage == kSlabStages) { stage = 0; phase ^= 1; }
+      if (c + 1 < nchunks) {
+        if (stage_q) sts_f4(qbuf + (((c + 1) & 1) * ((kQS / 2) * kQRowF4) + u * kQRowF4 + part) * 16, make_float4(ra.x, rb.x, ra.y, rb.y));
+        slab_bar();
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int qi = 8 * j + 2 * h + e;
+          const float qnj = qn[qi];
+          float bd = INFINITY;
+          int bp = 0x7fffffff;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {   // rows ascend with i: strict < keeps the first minimum
+            const float dot = e ? acc[i][j].y : acc[i][j].x;
+            const float d2 = ok[i] ? fmaxf(pn[i] + qnj - 2.f * dot, 0.f) + 0.f : INFINITY;
+            if (d2 < bd) { bd = d2; bp = slab * kSlab + g + 8 * i; }
+          }
+#pragma unroll
+          for (int o = 4; o <= 16; o <<= 1) {   // across the 8 prototype groups (lanes with the same h)
+            const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+            if (od < bd || (od == bd && op < bp)) { bd = od; bp = op; }
+          }
+          if (g == 0 && qi < nq) {
+            const unsigned long long packed = ((unsigned long long)__float_as_uint(bd) << 32) | (unsigned int)bp;
+            atomicMin(&best_packed[ord[qi]], packed);
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSlabThreads, 1)
+slab_scan_kernel(const __grid_constant__ CUtensorMap tmap_p, const RefinerBank bank, const float* __restrict__ q,
+                 const int* __restrict__ cell_start, const int* __restrict__ order, const int* __restrict__ slab_prefix,
+                 int topk, unsigned long long* __restrict__ best_packed) {
+  extern __shared__ uint8_t slab_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(slab_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* pstages = smem;
+  float4* qbuf = reinterpret_cast<float4*>(smem + kSlabStages * kPStageBytes);
+  float* qn = reinterpret_cast<float*>(smem + kSlabStages * kPStageBytes + 2 * kQBufBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(qn + kQS);
+  uint64_t* empty = full + kSlabStages;
+
+  const int C = bank.num_cells, D = bank.dim;
+  const long long T = slab_prefix[C];
+  const long long x_lo = T * blockIdx.x / gridDim.x, x_hi = T * (blockIdx.x + 1) / gridDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap_p);
+    for (int s = 0; s < kSlabStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kSlabWarps); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (x_lo >= x_hi) return;
+
+  if (warp == kSlabWarps) {
+    // ---------------------------------------------------------------- producer: TMA boxes of [256 prototypes x 32 floats]
+    if (lane == 0) {
+      SlabWalk w;
+      w.init(x_lo, x_hi, slab_prefix, C);
+      int stage = 0;
+      uint32_t phase = 0;
+      const int nchunks = D / kKC;
+      while (w.next(bank, cell_start, slab_prefix)) {
+        for (int s0 = w.t0; s0 < w.t1; s0 += kSlabWarps) {
+          const int nslabs = min(kSlabWarps, w.t1 - s0);
+          const int rows = min(nslabs * kSlab, w.Pc - s0 * kSlab);
+          const int nbox = (rows + kBoxRows - 1) / kBoxRows;
+          const long row0 = w.lo + (long)s0 * kSlab;
+          for (int c = 0; c < nchunks; ++c) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], (uint32_t)nbox * kBoxBytes);
+            for (int b = 0; b < nbox; ++b)
+              tma_load_2d(pstages + (size_t)stage * kPStageBytes + (size_t)b * kBoxBytes, &tmap_p, &full[stage], c * kKC,
+                          (int32_t)(row0 + (long)b * kBoxRows));
+            if (++stage == kSlabStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------ consumers
+  SlabWalk w;
+  w.init(x_lo, x_hi, slab_prefix, C);
+  int stage = 0;
+  uint32_t phase = 0;
+  while (w.next(bank, cell_start, slab_prefix)) {
+    const int nq = min(kQS, w.n_pairs - w.pass * kQS);
+    const int nj = (nq + 7) >> 3;
+    const int* ord = order + w.pair0 + w.pass * kQS;
+    slab_bar();   // the previous item's readers are done with qn
+    for (int qi = warp; qi < kQS; qi += kSlabWarps) {   // |q|^2, warp per query
+      float acc_q = 0.f;
+      if (qi < nq) {
+        const float4* q4 = reinterpret_cast<const float4*>(q + (size_t)(ord[qi] / topk) * D);
+        for (int i = lane; i < D / 4; i += 32) {
+          const float4 t = q4[i];
+          acc_q = fmaf(t.x, t.x, acc_q); acc_q = fmaf(t.y, t.y, acc_q);
+          acc_q = fmaf(t.z, t.z, acc_q); acc_q = fmaf(t.w, t.w, acc_q);
+        }
+      }
+      acc_q = warp_sum(acc_q);
+      if (lane == 0) qn[qi] = acc_q;
+    }
+    slab_bar();
+    switch (nj) {
+      case 1: slab_item<1>(bank, w, q, D, topk, ord, nq, smem_u32(pstages), smem_u32(qbuf), qn, full, empty, stage, phase, best_packed); break;
+      case 2: slab_item<2>(bank, w, q, D, topk, ord, nq, smem_u32(pstages), smem_u32(qbuf), qn, full, empty, stage, phase, best_packed); break;
+      case 3: slab_item<3>(bank, w, q, D, topk, ord, nq, smem_u32(pstages), smem_u32(qbuf), qn, full, empty, stage, phase, best_packed); break;
+      default: slab_item<4>(bank, w, q, D, topk, ord, nq, smem_u32(pstages), smem_u32(qbuf), qn, full, empty, stage, phase, best_packed); break;
+    }
+  }
+}
+
 // After the tile scan: decode the packed winner of every live pair, farthest-member pick (:233-255), outputs.
 template <int NV4>
 __global__ void __launch_bounds__(256)
@@ -734,10 +962,10 @@ tile_finish_kernel(const RefinerBank bank, const float* __restrict__ q, const lo
 }
 
 // exclusive scans of the pair counts (-> cell_start, cursors zeroed) and of the tile counts (-> tile_prefix) of the cells:
-// tiles(c) = ceil(n_pairs(c) / qs) query passes x ceil(P_c / 16) prototype tiles.  Single block.
+// units(c) = ceil(n_pairs(c) / qs) query passes x ceil(P_c / unit_rows) prototype units.  Single block.
 __global__ void cell_tile_offsets_kernel(const RefinerBank bank, const int* __restrict__ cell_cnt,
                                          int* __restrict__ cell_start, int* __restrict__ cursor,
-                                         int* __restrict__ tile_prefix, int C, int qs) {
+                                         int* __restrict__ tile_prefix, int C, int qs, int unit_rows) {
   __shared__ int carry[2];
   __shared__ int warp_tot[2][32];
   if (threadIdx.x < 2) carry[threadIdx.x] = 0;
@@ -749,7 +977,7 @@ __global__ void cell_tile_offsets_kernel(const RefinerBank bank, const int* __re
     if (i < C) {
       v[0] = cell_cnt[i];
       const int pc = (int)(bank.cell_off[i + 1] - bank.cell_off[i]);
-      v[1] = ((v[0] + qs - 1) / qs) * ((pc + kTP - 1) / kTP);
+      v[1] = ((v[0] + qs - 1) / qs) * ((pc + unit_rows - 1) / unit_rows);
     }
     int x[2] = {v[0], v[1]};
 #pragma unroll
@@ -1017,7 +1245,7 @@ int refiner_scan_tiles(const RefinerBank& bank, const float* q, const long long*
     ProfScope prof("refiner_sort", stream);
     pair_hist_kernel<<<(int)blocks, 256, 0, stream>>>(bank, cand, cand_stride, B, topk, cell_cnt, best_logit, best_lnglat,
                                                       best_proto, best_packed);
-    cell_tile_offsets_kernel<<<1, 1024, 0, stream>>>(bank, cell_cnt, cell_start, cursor, tile_prefix, C, qs);
+    cell_tile_offsets_kernel<<<1, 1024, 0, stream>>>(bank, cell_cnt, cell_start, cursor, tile_prefix, C, qs, kTP);
     pair_scatter_kernel<<<(int)blocks, 256, 0, stream>>>(bank, cand, cand_stride, B, topk, cell_start, cursor, order);
   }
   if (check_launch("refiner_sort")) return 1;
@@ -1032,6 +1260,63 @@ int refiner_scan_tiles(const RefinerBank& bank, const float* q, const long long*
       set_last_error("refiner: embedding dim %d unsupported (need 128*{1,2,4,6,8})", bank.dim);
       return 1;
   }
+}
+
+int refiner_scan_slabs(const RefinerBank& bank, long num_protos, const float* q, const long long* cand, int cand_stride,
+                       long B, int topk, void* sort_ws, float* best_logit, float* best_lnglat, int* best_proto,
+                       int num_sms, cudaStream_t stream) {
+  const long pairs = B * topk;
+  if (pairs == 0) return 0;
+  if (bank.dim % 128) { set_last_error("refiner: embedding dim %d not a multiple of 128", bank.dim); return 1; }
+  if (!bank.proto_sqnorm) { set_last_error("refiner slab scan: bank.proto_sqnorm is null"); return 1; }
+  if ((reinterpret_cast<uintptr_t>(bank.proto_emb) | reinterpret_cast<uintptr_t>(q)) & 15) {
+    set_last_error("refiner slab scan: proto_emb / queries must be 16-byte aligned"); return 1;
+  }
+  CUtensorMap tp;
+  if (make_tmap_f32_2d(&tp, bank.proto_emb, (uint64_t)num_protos, (uint64_t)bank.dim, (uint64_t)bank.dim, kBoxRows, kKC)) return 1;
+  const int C = bank.num_cells;
+  int* cell_cnt = reinterpret_cast<int*>(sort_ws);
+  int* cell_start = cell_cnt + (C + 1);
+  int* cursor = cell_start + (C + 1);
+  int* slab_prefix = cursor + (C + 1);
+  int* order = slab_prefix + (C + 1);
+  unsigned long long* best_packed =
+      reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(order + pairs) + 7) & ~uintptr_t(7));
+  cudaError_t e = cudaMemsetAsync(cell_cnt, 0, (size_t)(C + 1) * sizeof(int), stream);
+  if (e != cudaSuccess) { set_last_error("refiner: memset: %s", cudaGetErrorString(e)); return 1; }
+  long blocks = (pairs + 255) / 256;
+  if (blocks > (long)num_sms * 8) blocks = (long)num_sms * 8;
+  {
+    ProfScope prof("refiner_sort", stream);
+    pair_hist_kernel<<<(int)blocks, 256, 0, stream>>>(bank, cand, cand_stride, B, topk, cell_cnt, best_logit, best_lnglat,
+                                                      best_proto, best_packed);
+    cell_tile_offsets_kernel<<<1, 1024, 0, stream>>>(bank, cell_cnt, cell_start, cursor, slab_prefix, C, kQS, kSlab);
+    pair_scatter_kernel<<<(int)blocks, 256, 0, stream>>>(bank, cand, cand_stride, B, topk, cell_start, cursor, order);
+  }
+  if (check_launch("refiner_sort")) return 1;
+  e = cudaFuncSetAttribute(slab_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlabSmem);
+  if (e != cudaSuccess) { set_last_error("refiner slab scan: shared memory attribute: %s", cudaGetErrorString(e)); return 1; }
+  {
+    ProfScope prof("refiner_scan", stream);
+    slab_scan_kernel<<<num_sms, kSlabThreads, kSlabSmem, stream>>>(tp, bank, q, cell_start, order, slab_prefix, topk, best_packed);
+  }
+  if (check_launch("refiner_slab_scan")) return 1;
+  long fblocks = (pairs + 7) / 8;
+  if (fblocks > (long)num_sms * 8) fblocks = (long)num_sms * 8;
+  ProfScope prof("refiner_scan_finish", stream);
+  switch (bank.dim / 128) {
+#define PG_CASE(N)                                                                                                       \
+  case N:                                                                                                                \
+    tile_finish_kernel<N><<<(int)fblocks, 256, 0, stream>>>(bank, q, cand, cand_stride, order, cell_start + C, topk,       \
+                                                            best_packed, best_logit, best_lnglat, best_proto);           \
+    break;
+    PG_CASE(1) PG_CASE(2) PG_CASE(4) PG_CASE(6) PG_CASE(8)
+#undef PG_CASE
+    default:
+      set_last_error("refiner: embedding dim %d unsupported (need 128*{1,2,4,6,8})", bank.dim);
+      return 1;
+  }
+  return check_launch("refiner_tile_finish");
 }
 
 int refiner_bank_sqnorm(const float* proto_emb, long P, int D, float* out, int num_sms, cudaStream_t stream) {

@@ -33,6 +33,11 @@ int refiner_scan_cell_major(const RefinerBank& bank, const float* q, const long 
 int refiner_scan_tiles(const RefinerBank& bank, const float* q, const long long* cand, int cand_stride, long B, int topk,
                        void* sort_ws, float* best_logit, float* best_lnglat, int* best_proto, int num_sms,
                        cudaStream_t stream);
+// Slab scan (v5): 8 x 8 register tiles, TMA-streamed embedding chunks; for banks with hundreds of prototypes per geocell.
+// num_protos = rows of bank.proto_emb (for the tensor map).
+int refiner_scan_slabs(const RefinerBank& bank, long num_protos, const float* q, const long long* cand, int cand_stride,
+                       long B, int topk, void* sort_ws, float* best_logit, float* best_lnglat, int* best_proto,
+                       int num_sms, cudaStream_t stream);
 // |p|^2 of every prototype row (once per bank)
 int refiner_bank_sqnorm(const float* proto_emb, long P, int D, float* out, int num_sms, cudaStream_t stream);
 // data_views [N, V, D] -> data_mean [N, D] (view mean) and proto_emb [P, D] (mean of member rows of data_mean)

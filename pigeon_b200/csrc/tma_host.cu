@@ -66,6 +66,30 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
   return 0;
 }
 
+// fp32 [rows, cols] row-major (ld_elems floats per row), box [box_rows, box_cols] with box_cols * 4 == 128 bytes, 128-byte swizzle.
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                     uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_last_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return 1;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld_elems * 4};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (f32) failed: CUresult %d (rows=%llu cols=%llu ld=%llu box=%ux%u)", (int)r,
+                   (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows,
+                   box_cols);
+    return 1;
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------- profiler
 namespace {
 struct ProfRec { const char* name; cudaEvent_t e0, e1; };

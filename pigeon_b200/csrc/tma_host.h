@@ -13,6 +13,9 @@ namespace pg {
 int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                      uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols);
 
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                     uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols);
+
 void set_last_error(const char* fmt, ...);
 const char* last_error();
 

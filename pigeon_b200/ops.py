@@ -116,7 +116,7 @@ def head_set_fused(on: bool) -> None:
 
 
 def refiner_set_schedule(mode: int) -> None:
-    """A/B switch of the refiner scan: 0 automatic, 1 query-major, 2 cell-major, 3 tile scan (same selections)."""
+    """A/B switch of the refiner scan: 0 automatic, 1 query-major, 2 cell-major, 3 tile scan, 4 slab scan (same selections)."""
     check(load().pg_refiner_set_schedule(int(mode)), "pg_refiner_set_schedule")
 
 
@@ -182,7 +182,7 @@ class DeviceBank:
                 check(load().pg_refiner_bank_sqnorm(ptr(self.proto_emb), P, self.dim, ptr(self.proto_sqnorm),
                                                     current_stream_ptr()), "pg_refiner_bank_sqnorm")
         self.c_struct = _lib.RefinerBank(self.num_cells, self.dim, *(ptr(getattr(self, f)) for f in self.FIELDS),
-                                         ptr(self.proto_sqnorm) if self.proto_sqnorm is not None else None)
+                                         ptr(self.proto_sqnorm) if self.proto_sqnorm is not None else None, P)
 
 
 def refiner_forward(bank: DeviceBank, emb: torch.Tensor, init_lnglat: torch.Tensor, cand_idx: torch.Tensor,

@@ -266,10 +266,13 @@ def test_refiner_cell_major_equals_query_major(cuda, C, P, D, B, kc, topk, membe
     (7, 3000, 512, 2000, 3, 3, 0.0),       # 857 pairs per cell (27 passes), 4-stage ring
     (200, 20000, 256, 1500, 6, 5, 2.0),    # more cells than SMs: ranges of several cells, straddling cells merged by atomicMin
     (3, 5000, 768, 40, 2, 2, 0.0),         # fewer cells than SMs: every cell cut across many CTAs
+    (12, 9000, 768, 300, 4, 3, 0.0),       # geocells of ~900 prototypes: two 512-prototype CTA tiles each, three query passes
 ])
-def test_refiner_tile_scan_equals_cell_major(cuda, C, P, D, B, kc, topk, members):
-    """The tile scan (persistent CTAs, cp.async.bulk ring, 8-way split of D, packed atomicMin merge) against the cell-major
-    and query-major schedules: same winners wherever two prototypes do not tie within fp32 summation-order noise."""
+@pytest.mark.parametrize("sched", [3, 4])
+def test_refiner_tile_scan_equals_cell_major(cuda, C, P, D, B, kc, topk, members, sched):
+    """The tile scan (3: persistent CTAs, cp.async.bulk ring, 8-way split of D) and the slab scan (4: TMA-streamed embedding
+    chunks, 8 x 8 register tiles), both merging through a packed atomicMin, against the cell-major and query-major schedules:
+    same winners wherever two prototypes do not tie within fp32 summation-order noise."""
     from pigeon_b200 import ops, synthetic
     bank = synthetic.synthetic_bank(C, P, D, seed=31, members_mean=members, empty_cells=min(2, C - 1))
     cand, probs = synthetic.synthetic_candidates(B, kc, C, seed=32)
@@ -285,7 +288,7 @@ def test_refiner_tile_scan_equals_cell_major(cuda, C, P, D, B, kc, topk, members
         _, _, dq = ops.refiner_forward(*args, debug=True)
         ops.refiner_set_schedule(2)
         ll_c, cell_c, dc = ops.refiner_forward(*args, debug=True)
-        ops.refiner_set_schedule(3)
+        ops.refiner_set_schedule(sched)
         ll_t, cell_t, dt = ops.refiner_forward(*args, debug=True)
         ll_t2, cell_t2, dt2 = ops.refiner_forward(*args, debug=True)
     finally:
