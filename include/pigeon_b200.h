@@ -234,6 +234,8 @@ typedef struct pg_refiner_bank {
   const float* proto_sqnorm;   /* [P] squared L2 norm of every prototype row (pg_refiner_bank_sqnorm), or NULL: the scans
                                   that need it (schedules 3, 4) are then replaced by the ones that do not */
   int64_t num_protos;          /* P = rows of proto_emb (bounds the TMA tensor map of schedule 4), or 0 */
+  int32_t live_cells;          /* geocells with at least one prototype (a cell-sharded bank holds 1/N of them), or 0 = unknown:
+                                  the automatic schedule sizes its work units by num_protos / live_cells */
 } pg_refiner_bank;
 
 /* |p|^2 of every row of proto_emb f32 [P, D] -> sqnorm_out f32 [P]; once per bank (the squared Euclidean distance of
@@ -255,7 +257,7 @@ int pg_refiner_finalize(const float* best_logit, const float* best_lnglat, const
                         void* stream);
 /* Measurement aid: scan schedule of pg_refiner_forward for this process: 0 = automatic (cell-major when geocells are shared
  * by >= 2 (query, candidate) pairs on average; the slab scan when the bank carries proto_sqnorm / num_protos and its geocells
- * hold >= 256 prototypes on average), 1 = query-major, 2 = cell-major, 3 = tile scan, 4 = slab scan.  Same selections. */
+ * hold >= 256 prototypes on average over the non-empty ones), 1 = query-major, 2 = cell-major, 3 = tile scan, 4 = slab scan.  Same selections. */
 int pg_refiner_set_schedule(int32_t mode);
 /* emb f32 [B, V, D]; init_lnglat f64 [B, 2]; cand_idx i64 [B, cand_stride]; cand_prob f32 [B, cand_stride];
  * only the first `topk` candidates of each row are used (topk <= cand_stride).

@@ -61,7 +61,7 @@ class VitWeights(C.Structure):
 class RefinerBank(C.Structure):
     _fields_ = [("num_cells", c_int32), ("dim", c_int32), ("cell_off", c_void_p), ("proto_emb", c_void_p),
                 ("proto_lnglat", c_void_p), ("proto_count", c_void_p), ("member_off", c_void_p),
-                ("member_idx", c_void_p), ("data_emb", c_void_p), ("data_lnglat", c_void_p), ("proto_sqnorm", c_void_p), ("num_protos", c_int64)]
+                ("member_idx", c_void_p), ("data_emb", c_void_p), ("data_lnglat", c_void_p), ("proto_sqnorm", c_void_p), ("num_protos", c_int64), ("live_cells", c_int32)]
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/pigeon_b200.h

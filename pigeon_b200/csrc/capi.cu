@@ -336,7 +336,8 @@ static int pick_scan(int sched, int64_t B, int32_t topk, const pg_refiner_bank* 
   if (sched == 4) return slab_ok ? 4 : 2;
   if ((long)B * topk < 2L * bank->num_cells) return 1;   // small batches: the sort would dominate
   // a slab is 64 prototypes of ONE geocell and a CTA tile 512: only banks with large geocells fill them
-  if (slab_ok && bank->num_protos >= 256L * bank->num_cells) return 4;
+  const long cells = bank->live_cells > 0 ? bank->live_cells : bank->num_cells;
+  if (slab_ok && bank->num_protos >= 256L * cells) return 4;
   return 2;
 }
 

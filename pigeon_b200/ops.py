@@ -182,7 +182,8 @@ class DeviceBank:
                 check(load().pg_refiner_bank_sqnorm(ptr(self.proto_emb), P, self.dim, ptr(self.proto_sqnorm),
                                                     current_stream_ptr()), "pg_refiner_bank_sqnorm")
         self.c_struct = _lib.RefinerBank(self.num_cells, self.dim, *(ptr(getattr(self, f)) for f in self.FIELDS),
-                                         ptr(self.proto_sqnorm) if self.proto_sqnorm is not None else None, P)
+                                         ptr(self.proto_sqnorm) if self.proto_sqnorm is not None else None, P,
+                                         int((self.cell_off[1:] > self.cell_off[:-1]).sum().item()))
 
 
 def refiner_forward(bank: DeviceBank, emb: torch.Tensor, init_lnglat: torch.Tensor, cand_idx: torch.Tensor,
