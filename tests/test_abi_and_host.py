@@ -407,3 +407,37 @@ def test_docs_only_name_entry_points_that_exist():
         names |= set(re.findall(r"\bpg_[a-z0-9_]+\b", text))
         unknown = {n for n in names if n not in declared and not (n.endswith("_") and any(d.startswith(n) for d in declared))}
         assert not unknown, (doc, sorted(unknown))
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """Every ctypes mirror in pigeon_b200/_lib.py has the size and the field offsets gcc computes from include/pigeon_b200.h
+    (a reordered, missing or mistyped field would silently corrupt the arguments of the C ABI)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from pigeon_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    pairs = {"pg_vit_config": _lib.VitConfig, "pg_image": _lib.Image, "pg_vit_layer": _lib.VitLayer,
+             "pg_vit_saved_layer": _lib.VitSavedLayer, "pg_vit_saved": _lib.VitSaved, "pg_vit_layer_bwd": _lib.VitLayerBwd,
+             "pg_vit_grads": _lib.VitGrads, "pg_vit_weights": _lib.VitWeights, "pg_refiner_bank": _lib.RefinerBank}
+    lines = ["#include <stddef.h>", "#include <stdio.h>", '#include "pigeon_b200.h"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([gcc, "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], capture_output=True,
+                       text=True)
+    assert r.returncode == 0, r.stderr
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == C.sizeof(cls), (cname, got[cname], C.sizeof(cls))
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+    assert _lib.ABI_VERSION == 3
