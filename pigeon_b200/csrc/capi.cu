@@ -238,7 +238,7 @@ int pg_head_forward(const float* emb, int32_t B, int32_t V, int32_t D, const voi
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   // pg_head_set_fused(1): one kernel (view mean + split -> tcgen05 GEMM -> bias -> softmax / arg-max / top-k) whenever the
   // shape allows; the default is the three-kernel sequence, which is faster at the batch sizes of this path
-  if (head_fused_on() && head_fused_supported(B, V, D, C, k))
+  if (head_fused_on() && head_fused_supported(B, V, D, C, k) && (reinterpret_cast<uintptr_t>(emb) & 15) == 0)
     return head_fused_forward(emb, B, V, D, w3, bias, centroids, C, k, workspace, pooled, logits, probs,
                               reinterpret_cast<long long*>(pred_cell), pred_lnglat, topk_val,
                               reinterpret_cast<long long*>(topk_idx), stream);
